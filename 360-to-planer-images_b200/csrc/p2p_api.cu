@@ -1,0 +1,694 @@
+// p2p_api.cu - C ABI (include/p2p.h) over the sm_100a kernels in p2p_kernels.cuh.
+// Host logic only: contexts, panorama slots (stream + device buffers), launches, transfers.
+#include "p2p.h"
+#include "p2p_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+using namespace p2p;
+
+namespace {
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint8_t *d_bgr = nullptr;  // staging copy of the caller's BGR rows
+    size_t bgr_cap = 0;
+    uint32_t *d_rgba = nullptr;  // packed panorama
+    size_t rgba_cap = 0;
+    int Wp = 0, Hp = 0, pitch_tex = 0;
+    bool valid = false;
+    cudaArray_t arr = nullptr;  // gather-enabled array (sampler 1)
+    int arrW = 0, arrH = 0;
+    cudaTextureObject_t tex = 0;
+    bool tex_current = false;
+    uint8_t *d_out = nullptr;  // device outputs when the caller wants them on the host
+    size_t out_cap = 0;
+    int32_t *d_tab = nullptr;  // yaw table (ix | fx), 2 * Wp
+    size_t tab_cap = 0;
+};
+
+}  // namespace
+
+struct p2p_ctx {
+    int device = 0;
+    int n_slots = 0;
+    Slot *slots = nullptr;
+    std::mutex mu;
+    std::string err;
+    int opt_sampler = 0;
+    int opt_warp_w = 32;
+    int opt_ny = 4;
+    long long launches = 0;
+    uint4 *d_flush = nullptr;
+    size_t flush_cap = 0;
+};
+
+namespace {
+
+int fail(p2p_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        ctx->err = what;
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                          \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) {                                          \
+            cudaGetLastError();                                           \
+            return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? P2P_ERR_NOMEM : P2P_ERR_CUDA, #call, e_); \
+        }                                                                 \
+    } while (0)
+
+template <typename T>
+int ensure(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *ptr) return P2P_OK;
+    if (*ptr) {
+        CK(cudaFree(*ptr));
+        *ptr = nullptr;
+        *cap = 0;
+    }
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    *ptr = static_cast<T *>(p);
+    *cap = bytes;
+    return P2P_OK;
+}
+
+int slot_ok(p2p_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < ctx->n_slots; }
+
+int check_dims(p2p_ctx *ctx, int Wp, int Hp) {
+    if (Wp <= 0 || Hp <= 0) return fail(ctx, P2P_ERR_INVALID, "panorama size must be positive");
+    // cv::remap asserts every dimension < SHRT_MAX (SURVEY 8b "limits inherited")
+    if (Wp >= 32767 || Hp >= 32767) return fail(ctx, P2P_ERR_LIMIT, "panorama dimension >= 32767");
+    return P2P_OK;
+}
+
+int prepare_slot(p2p_ctx *ctx, Slot &s, int Wp, int Hp) {
+    const int pitch_tex = ((Wp + 1) + 31) & ~31;  // 128-byte aligned rows
+    const size_t bytes = (size_t)pitch_tex * (size_t)(Hp + 1) * 4;
+    int rc = ensure(ctx, &s.d_rgba, &s.rgba_cap, bytes);
+    if (rc) return rc;
+    s.Wp = Wp;
+    s.Hp = Hp;
+    s.pitch_tex = pitch_tex;
+    s.tex_current = false;
+    return P2P_OK;
+}
+
+int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride) {
+    const int groups = s.Wp / 4 + 1;
+    dim3 block(256), grid((groups + 255) / 256, s.Hp + 1);
+    const int aligned4 = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 3) == 0);
+    pack_kernel<<<grid, block, 0, s.stream>>>(d_src, stride, s.d_rgba, s.pitch_tex, s.Wp, s.Hp, aligned4);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    s.valid = true;
+    return P2P_OK;
+}
+
+// (re)build the gather texture of a slot from its packed panorama
+int ensure_texture(p2p_ctx *ctx, Slot &s) {
+    if (s.tex_current) return P2P_OK;
+    const int aw = s.Wp + 1, ah = s.Hp + 1;
+    if (!s.arr || s.arrW != aw || s.arrH != ah) {
+        if (s.tex) {
+            CK(cudaDestroyTextureObject(s.tex));
+            s.tex = 0;
+        }
+        if (s.arr) {
+            CK(cudaFreeArray(s.arr));
+            s.arr = nullptr;
+        }
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindUnsigned);
+        CK(cudaMallocArray(&s.arr, &fd, aw, ah, cudaArrayTextureGather));
+        s.arrW = aw;
+        s.arrH = ah;
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = s.arr;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CK(cudaCreateTextureObject(&s.tex, &rd, &td, nullptr));
+    }
+    CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.d_rgba, (size_t)s.pitch_tex * 4, (size_t)aw * 4, ah,
+                                cudaMemcpyDeviceToDevice, s.stream));
+    s.tex_current = true;
+    return P2P_OK;
+}
+
+typedef void (*proj_fn)(const ProjParams);
+
+template <int WARP_W, int SAMPLER>
+proj_fn pick_ny(int ny) {
+    switch (ny) {
+        case 1: return project_kernel<WARP_W, 1, SAMPLER>;
+        case 2: return project_kernel<WARP_W, 2, SAMPLER>;
+        case 3: return project_kernel<WARP_W, 3, SAMPLER>;
+        default: return project_kernel<WARP_W, 4, SAMPLER>;
+    }
+}
+
+template <int SAMPLER>
+proj_fn pick_w(int warp_w, int ny) {
+    switch (warp_w) {
+        case 8: return pick_ny<8, SAMPLER>(ny);
+        case 16: return pick_ny<16, SAMPLER>(ny);
+        default: return pick_ny<32, SAMPLER>(ny);
+    }
+}
+
+int launch_project(p2p_ctx *ctx, Slot &s, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                   const p2p_pitch_consts *pitch, int W, int H, uint8_t *d_out) {
+    if (ctx->opt_sampler == 1) {
+        int rc = ensure_texture(ctx, s);
+        if (rc) return rc;
+    }
+    // chunk over yaws / pitches so any list length works
+    for (int y0 = 0; y0 < n_yaw; y0 += kMaxYawPerLaunch) {
+        const int ny_l = (n_yaw - y0 < kMaxYawPerLaunch) ? n_yaw - y0 : kMaxYawPerLaunch;
+        for (int p0 = 0; p0 < n_pitch; p0 += kMaxPitchPerLaunch) {
+            const int np_l = (n_pitch - p0 < kMaxPitchPerLaunch) ? n_pitch - p0 : kMaxPitchPerLaunch;
+            ProjParams P;
+            memset(&P, 0, sizeof(P));
+            P.pano = s.d_rgba;
+            P.tex = s.tex;
+            P.view_stride = (unsigned long long)W * H * 3;
+            P.pitch_tex = s.pitch_tex;
+            P.Wp = s.Wp;
+            P.Hp = s.Hp;
+            P.W = W;
+            P.H = H;
+            P.n_yaw = ny_l;
+            P.n_pitch = np_l;
+            P.halfW = (float)(W / 2.0);
+            P.halfH = (float)(H / 2.0);
+            P.Wp_f = (float)s.Wp;
+            P.Hp_f = (float)s.Hp;
+            P.Umax = (float)(s.Wp - 1);
+            P.Vmax = (float)(s.Hp - 1);
+            for (int k = 0; k < ny_l; ++k) P.shift[k] = yaw_shift[y0 + k];
+            for (int j = 0; j < np_l; ++j) {
+                P.pc[j].f = pitch[p0 + j].f;
+                P.pc[j].c = pitch[p0 + j].c;
+                P.pc[j].s = pitch[p0 + j].s;
+            }
+            P.out = d_out;
+            P.yaw_off = y0;
+            P.pitch_off = p0;
+            P.n_pitch_total = n_pitch;
+            P.quad_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0);
+            const int ny_thread = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
+            const int groups = (ny_l + ny_thread - 1) / ny_thread;
+            dim3 grid((W + 31) / 32, (H + 7) / 8, groups * np_l);
+            if (grid.y > 65535 || grid.z > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+            proj_fn fn = (ctx->opt_sampler == 1) ? pick_w<1>(ctx->opt_warp_w, ny_thread)
+                                                 : pick_w<0>(ctx->opt_warp_w, ny_thread);
+            fn<<<grid, kThreads, 0, s.stream>>>(P);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    return P2P_OK;
+}
+
+int check_project_args(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                       const p2p_pitch_consts *pitch, int W, int H, const void *out, int Wp) {
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    if (n_yaw <= 0 || n_pitch <= 0 || !yaw_shift || !pitch || !out)
+        return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
+    if (W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "output size must be positive");
+    if (W >= 32767 || H >= 32767) return fail(ctx, P2P_ERR_LIMIT, "output dimension >= 32767");
+    for (int k = 0; k < n_yaw; ++k)
+        if (yaw_shift[k] < 0 || yaw_shift[k] >= Wp) return fail(ctx, P2P_ERR_INVALID, "yaw_shift outside [0, Wp)");
+    return P2P_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int p2p_abi_version(void) { return P2P_ABI_VERSION; }
+
+int p2p_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *p2p_status_string(int status) {
+    switch (status) {
+        case P2P_OK: return "ok";
+        case P2P_ERR_INVALID: return "invalid argument";
+        case P2P_ERR_CUDA: return "CUDA error";
+        case P2P_ERR_NOMEM: return "out of memory";
+        case P2P_ERR_STATE: return "bad slot state";
+        case P2P_ERR_LIMIT: return "size limit exceeded";
+        default: return "unknown status";
+    }
+}
+
+int p2p_create(int device, int n_slots, p2p_ctx **out) {
+    if (!out || n_slots <= 0 || n_slots > 64) return P2P_ERR_INVALID;
+    *out = nullptr;
+    int n = p2p_device_count();
+    if (n <= 0 || device < 0 || device >= n) return P2P_ERR_CUDA;  // no CPU fallback
+    p2p_ctx *ctx = new (std::nothrow) p2p_ctx;
+    if (!ctx) return P2P_ERR_NOMEM;
+    ctx->device = device;
+    ctx->n_slots = n_slots;
+    ctx->slots = new (std::nothrow) Slot[n_slots];
+    if (!ctx->slots) {
+        delete ctx;
+        return P2P_ERR_NOMEM;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        delete[] ctx->slots;
+        delete ctx;
+        return P2P_ERR_CUDA;
+    }
+    for (int i = 0; i < n_slots; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < i; ++j) cudaStreamDestroy(ctx->slots[j].stream);
+            delete[] ctx->slots;
+            delete ctx;
+            return P2P_ERR_CUDA;
+        }
+        ctx->slots[i].own_stream = true;
+    }
+    *out = ctx;
+    return P2P_OK;
+}
+
+void p2p_destroy(p2p_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < ctx->n_slots; ++i) {
+        Slot &s = ctx->slots[i];
+        if (s.tex) cudaDestroyTextureObject(s.tex);
+        if (s.arr) cudaFreeArray(s.arr);
+        cudaFree(s.d_bgr);
+        cudaFree(s.d_rgba);
+        cudaFree(s.d_out);
+        cudaFree(s.d_tab);
+        if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(ctx->d_flush);
+    cudaGetLastError();
+    delete[] ctx->slots;
+    delete ctx;
+}
+
+const char *p2p_last_error(p2p_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int p2p_set_option(p2p_ctx *ctx, int key, int value) {
+    if (!ctx) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    switch (key) {
+        case P2P_OPT_SAMPLER:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "sampler must be 0 or 1");
+            ctx->opt_sampler = value;
+            return P2P_OK;
+        case P2P_OPT_WARP_W:
+            if (value != 8 && value != 16 && value != 32) return fail(ctx, P2P_ERR_INVALID, "warp_w must be 8, 16 or 32");
+            ctx->opt_warp_w = value;
+            return P2P_OK;
+        case P2P_OPT_YAWS_PER_THREAD:
+            if (value < 1 || value > 4) return fail(ctx, P2P_ERR_INVALID, "yaws per thread must be 1..4");
+            ctx->opt_ny = value;
+            return P2P_OK;
+        default:
+            return fail(ctx, P2P_ERR_INVALID, "unknown option");
+    }
+}
+
+int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
+    if (!ctx || !value) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    switch (key) {
+        case P2P_OPT_SAMPLER: *value = ctx->opt_sampler; return P2P_OK;
+        case P2P_OPT_WARP_W: *value = ctx->opt_warp_w; return P2P_OK;
+        case P2P_OPT_YAWS_PER_THREAD: *value = ctx->opt_ny; return P2P_OK;
+        case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
+        default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
+    }
+}
+
+// ---- host helpers --------------------------------------------------------------------------
+int p2p_pitch_constants(double fov_deg, double pitch_deg, int W, p2p_pitch_consts *out) {
+    if (!out || W <= 0) return P2P_ERR_INVALID;
+    const double deg = M_PI / 180.0;  // np.radians(x) == x * (pi / 180)
+    const double fov = fov_deg * deg, p = pitch_deg * deg;
+    out->f = (float)((0.5 * (double)W) / tan(fov / 2.0));
+    out->c = (float)cos(p);
+    out->s = (float)sin(p);
+    return P2P_OK;
+}
+
+int p2p_yaw_table(int Wp, double yaw_deg, int32_t *ix, int32_t *fx, int32_t *shift) {
+    if (Wp <= 0 || !ix || !fx) return P2P_ERR_INVALID;
+    const double two_pi = 2.0 * M_PI;
+    const double yaw = yaw_deg * (M_PI / 180.0);  // f64 scalar: the sum below is f64 (NEP 50)
+    const float two_pi_f = (float)two_pi;
+    bool roll = true;
+    for (int u = 0; u < Wp; ++u) {
+        // ref :95   phi = (2*pi*u / Wp) in f32: f32(2pi) * f32(u), then / f32(Wp)
+        volatile float m = two_pi_f * (float)u;
+        const float phi = m / (float)Wp;
+        // ref :98   (phi + yaw) % 2pi in f64, Python-style remainder (result takes divisor's sign)
+        double r = fmod((double)phi + yaw, two_pi);
+        if (r != 0.0) {
+            if (r < 0.0) r += two_pi;
+        } else {
+            r = 0.0;
+        }
+        // ref :101-105
+        double U = (r * (double)Wp) / two_pi;
+        if (U < 0.0) U = 0.0;
+        if (U > (double)(Wp - 1)) U = (double)(Wp - 1);
+        const float Uf = (float)U;
+        volatile float sc = Uf * 32.0f;
+        const int sx = (int)lrintf(sc);  // cvRound: round half even
+        ix[u] = sx >> 5;
+        fx[u] = sx & 31;
+        if (fx[u] != 0) roll = false;
+    }
+    if (roll) {
+        const int s0 = ix[0];
+        for (int u = 0; u < Wp && roll; ++u) roll = (ix[u] == (u + s0) % Wp);
+        if (shift) *shift = roll ? s0 : -1;
+    } else if (shift) {
+        *shift = -1;
+    }
+    return P2P_OK;
+}
+
+int p2p_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return P2P_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return P2P_ERR_NOMEM;
+    }
+    return P2P_OK;
+}
+
+int p2p_host_free(void *ptr) {
+    if (!ptr) return P2P_OK;
+    if (cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return P2P_ERR_CUDA;
+    }
+    return P2P_OK;
+}
+
+int p2p_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return P2P_ERR_INVALID;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return P2P_ERR_CUDA;
+    }
+    return P2P_OK;
+}
+
+int p2p_host_unregister(void *ptr) {
+    if (!ptr) return P2P_ERR_INVALID;
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return P2P_ERR_CUDA;
+    }
+    return P2P_OK;
+}
+
+// ---- panorama upload -----------------------------------------------------------------------
+int p2p_upload_pano(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride) {
+    if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_dims(ctx, Wp, Hp);
+    if (rc) return rc;
+    if (row_stride < (size_t)Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    // tight device staging copy (row stride rounded to 4 bytes so the packer can use word loads)
+    const size_t dstride = ((size_t)Wp * 3 + 3) & ~(size_t)3;
+    rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, dstride * Hp);
+    if (rc) return rc;
+    rc = prepare_slot(ctx, s, Wp, Hp);
+    if (rc) return rc;
+    if (row_stride == dstride) {
+        CK(cudaMemcpyAsync(s.d_bgr, bgr, dstride * Hp, cudaMemcpyHostToDevice, s.stream));
+    } else {
+        CK(cudaMemcpy2DAsync(s.d_bgr, dstride, bgr, row_stride, (size_t)Wp * 3, Hp, cudaMemcpyHostToDevice, s.stream));
+    }
+    return launch_pack(ctx, s, s.d_bgr, dstride);
+}
+
+int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, int Hp, size_t row_stride) {
+    if (!slot_ok(ctx, slot) || !d_bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_dims(ctx, Wp, Hp);
+    if (rc) return rc;
+    if (row_stride < (size_t)Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = prepare_slot(ctx, s, Wp, Hp);
+    if (rc) return rc;
+    return launch_pack(ctx, s, static_cast<const uint8_t *>(d_bgr), row_stride);
+}
+
+int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix, const int32_t *fx) {
+    if (!slot_ok(ctx, src_slot) || !slot_ok(ctx, dst_slot) || src_slot == dst_slot || !ix || !fx)
+        return fail(ctx, P2P_ERR_INVALID, "bad slots or null table");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Slot &a = ctx->slots[src_slot];
+    Slot &d = ctx->slots[dst_slot];
+    if (!a.valid) return fail(ctx, P2P_ERR_STATE, "source slot holds no panorama");
+    for (int u = 0; u < a.Wp; ++u)
+        if (ix[u] < 0 || ix[u] >= a.Wp || fx[u] < 0 || fx[u] > 31) return fail(ctx, P2P_ERR_INVALID, "yaw table entry out of range");
+    int rc = prepare_slot(ctx, d, a.Wp, a.Hp);
+    if (rc) return rc;
+    rc = ensure(ctx, &d.d_tab, &d.tab_cap, (size_t)a.Wp * 2 * sizeof(int32_t));
+    if (rc) return rc;
+    // the table is tiny; the source must be complete before the destination stream reads it
+    CK(cudaStreamSynchronize(a.stream));
+    CK(cudaMemcpyAsync(d.d_tab, ix, (size_t)a.Wp * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.d_tab + a.Wp, fx, (size_t)a.Wp * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaStreamSynchronize(d.stream));  // ix / fx are caller memory (pageable): copy must be done
+    dim3 block(256), grid((a.Wp + 1 + 255) / 256, a.Hp + 1);
+    rotate_kernel<<<grid, block, 0, d.stream>>>(a.d_rgba, d.d_rgba, a.pitch_tex, a.Wp, a.Hp, d.d_tab, d.d_tab + a.Wp);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    d.valid = true;
+    return P2P_OK;
+}
+
+// ---- hot path ------------------------------------------------------------------------------
+int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                      const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device) {
+    if (!ctx) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    int rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, s.Wp);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n_yaw * n_pitch * W * H * 3;
+    uint8_t *d_out = out;
+    if (!out_on_device) {
+        rc = ensure(ctx, &s.d_out, &s.out_cap, bytes);
+        if (rc) return rc;
+        d_out = s.d_out;
+    }
+    rc = launch_project(ctx, s, n_yaw, yaw_shift, n_pitch, pitch, W, H, d_out);
+    if (rc) return rc;
+    if (!out_on_device) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    return P2P_OK;
+}
+
+int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
+                      int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
+                      int W, int H, uint8_t *out_host) {
+    int rc = p2p_upload_pano(ctx, slot, bgr, Wp, Hp, row_stride);
+    if (rc) return rc;
+    return p2p_project_views(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, 0);
+}
+
+int p2p_sync(p2p_ctx *ctx, int slot) {
+    if (!ctx) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (slot < 0) {
+        for (int i = 0; i < ctx->n_slots; ++i) CK(cudaStreamSynchronize(ctx->slots[i].stream));
+        return P2P_OK;
+    }
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    CK(cudaStreamSynchronize(ctx->slots[slot].stream));
+    return P2P_OK;
+}
+
+int p2p_set_stream(p2p_ctx *ctx, int slot, void *cuda_stream) {
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    CK(cudaStreamSynchronize(s.stream));
+    if (s.own_stream && s.stream) CK(cudaStreamDestroy(s.stream));
+    s.stream = static_cast<cudaStream_t>(cuda_stream);
+    s.own_stream = false;
+    return P2P_OK;
+}
+
+// ---- timing --------------------------------------------------------------------------------
+int p2p_event_create(p2p_ctx *ctx, void **event) {
+    if (!ctx || !event) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    *event = e;
+    return P2P_OK;
+}
+
+int p2p_event_destroy(p2p_ctx *ctx, void *event) {
+    if (!ctx || !event) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+    return P2P_OK;
+}
+
+int p2p_event_record(p2p_ctx *ctx, void *event, int slot) {
+    if (!slot_ok(ctx, slot) || !event) return fail(ctx, P2P_ERR_INVALID, "bad slot or event");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(static_cast<cudaEvent_t>(event), ctx->slots[slot].stream));
+    return P2P_OK;
+}
+
+int p2p_event_elapsed_ms(p2p_ctx *ctx, void *start, void *stop, float *ms) {
+    if (!ctx || !start || !stop || !ms) return P2P_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+    CK(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+    return P2P_OK;
+}
+
+int p2p_flush_l2(p2p_ctx *ctx, int slot, size_t bytes) {
+    if (!slot_ok(ctx, slot) || bytes == 0) return fail(ctx, P2P_ERR_INVALID, "bad slot or size");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    bytes = (bytes + 15) & ~(size_t)15;
+    int rc = ensure(ctx, &ctx->d_flush, &ctx->flush_cap, bytes);
+    if (rc) return rc;
+    fill_kernel<<<148 * 8, 256, 0, ctx->slots[slot].stream>>>(ctx->d_flush, bytes / 16, (uint32_t)ctx->launches);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return P2P_OK;
+}
+
+// ---- debug exports -------------------------------------------------------------------------
+int p2p_coords(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
+               float *U_host, float *V_host) {
+    if (!ctx || !pitch || !U_host || !V_host || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_dims(ctx, Wp, Hp);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H;
+    float *d = nullptr;
+    CK(cudaMalloc(&d, n * 2 * sizeof(float)));
+    PitchC k{pitch->f, pitch->c, pitch->s};
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+    cudaStream_t st = ctx->slots[0].stream;
+    coords_kernel<<<grid, block, 0, st>>>(k, W, H, (float)(W / 2.0), (float)(H / 2.0), (float)Wp, (float)Hp,
+                                          (float)(Wp - 1), (float)(Hp - 1), d, d + n);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(U_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(V_host, d + n, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_coords", e);
+    return P2P_OK;
+}
+
+int p2p_sample_with_maps(p2p_ctx *ctx, int slot, int yaw_shift, const float *U_host, const float *V_host,
+                         int W, int H, uint8_t *out_host) {
+    if (!slot_ok(ctx, slot) || !U_host || !V_host || !out_host || W <= 0 || H <= 0)
+        return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    if (yaw_shift < 0 || yaw_shift >= s.Wp) return fail(ctx, P2P_ERR_INVALID, "yaw_shift outside [0, Wp)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)W * H;
+    float *d = nullptr;
+    uint8_t *d_o = nullptr;
+    CK(cudaMalloc(&d, n * 2 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_o, n * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, U_host, n * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, V_host, n * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) {
+        dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+        sample_maps_kernel<<<grid, block, 0, s.stream>>>(s.d_rgba, s.pitch_tex, s.Wp, s.Hp, yaw_shift, d, d + n, W, H, d_o);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_o, n * 3, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d);
+    cudaFree(d_o);
+    if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_sample_with_maps", e);
+    return P2P_OK;
+}
+
+int p2p_download_pano(p2p_ctx *ctx, int slot, uint8_t *bgr_host, size_t row_stride) {
+    if (!slot_ok(ctx, slot) || !bgr_host) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    if (row_stride < (size_t)s.Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    const size_t dstride = (size_t)s.Wp * 3;
+    CK(cudaMalloc(&d, dstride * s.Hp));
+    dim3 block(256), grid((s.Wp + 255) / 256, s.Hp);
+    unpack_kernel<<<grid, block, 0, s.stream>>>(s.d_rgba, s.pitch_tex, s.Wp, s.Hp, d, dstride);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(bgr_host, row_stride, d, dstride, dstride, s.Hp, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_download_pano", e);
+    return P2P_OK;
+}
+
+}  // extern "C"

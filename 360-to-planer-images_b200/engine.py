@@ -1,0 +1,297 @@
+"""Host side of the B200 projection path: a thin, typed wrapper over the C ABI.
+
+``Projector`` owns one ``p2p_ctx`` (one CUDA device, ``n_slots`` panorama slots with their own
+streams).  The host scalars the kernels need are formed here with the reference's own NumPy
+expressions, so they are bit-identical to the reference by construction:
+
+* ``pitch_constants``  - ref ``get_pitch_mapping`` :64, :68 (``np.radians``) and
+  ``precompute_pitch_mapping`` :119 (focal length), :142-149 (``R_pitch`` entries in f32)
+* ``yaw_table``        - one row of ref ``precompute_yaw_mapping`` :85-105, quantised to the
+  1/32-px fixed point ``cv2.remap`` uses; a pure integer roll for every yaw with
+  ``yaw * Wp / 360`` integral
+
+Nothing here computes pixels; without the CUDA library the import fails (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import queue
+import threading
+from contextlib import contextmanager
+
+import numpy as np
+
+from . import _lib
+from ._lib import P2PError, PitchConsts
+
+
+# ------------------------------------------------------------------------------------------
+# host scalars (NumPy, same expressions as the reference)
+# ------------------------------------------------------------------------------------------
+def pitch_constants(W: int, fov_deg, pitch_deg) -> tuple:
+    fov_rad = np.radians(fov_deg)
+    p = np.radians(pitch_deg)
+    f = np.float32((0.5 * W) / np.tan(fov_rad / 2))
+    return float(f), float(np.float32(np.cos(p))), float(np.float32(np.sin(p)))
+
+
+def yaw_table(pano_width: int, yaw_deg):
+    """(ix, fx, shift): quantised yaw column map; ``shift`` is None unless it is a pure roll."""
+    yaw_radians = np.radians(yaw_deg)
+    u = np.arange(pano_width, dtype=np.float32)
+    phi = (2 * np.pi * u / pano_width).astype(np.float32)
+    phi_rotated = (phi + yaw_radians) % (2 * np.pi)
+    U = (phi_rotated * pano_width) / (2 * np.pi)
+    U = np.clip(U, 0, pano_width - 1).astype(np.float32)
+    s = np.rint(U * np.float32(32)).astype(np.int32)
+    ix, fx = s >> 5, s & 31
+    shift = None
+    if not fx.any():
+        s0 = int(ix[0])
+        if np.array_equal(ix, (np.arange(pano_width, dtype=np.int64) + s0) % pano_width):
+            shift = s0
+    return np.ascontiguousarray(ix, np.int32), np.ascontiguousarray(fx, np.int32), shift
+
+
+def _as_u8_image(a, what="panorama") -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError(f"{what} must be uint8 [H, W, 3], got {a.dtype} {a.shape}")
+    if a.strides[2] != 1 or a.strides[1] != 3 or a.strides[0] < a.shape[1] * 3:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a NumPy array (overlapped H2D / D2H)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        lib = _lib.load()
+        self.shape = tuple(int(x) for x in shape)
+        self.nbytes = int(np.prod(self.shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        rc = lib.p2p_host_alloc(C.byref(ptr), self.nbytes)
+        if rc:
+            raise P2PError(rc, "pinned host allocation failed")
+        self._ptr = ptr
+        buf = (C.c_uint8 * self.nbytes).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            _lib.load().p2p_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Projector:
+    """One device context.  Thread-safe; slots are handed out from a pool so concurrent callers
+    (the reference drives this seam from a ThreadPoolExecutor, ref :252-265) never share one."""
+
+    def __init__(self, device: int = 0, n_slots: int = 4):
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.n_slots = int(n_slots)
+        ctx = C.c_void_p()
+        rc = self.lib.p2p_create(self.device, self.n_slots, C.byref(ctx))
+        if rc:
+            raise P2PError(rc, f"p2p_create(device={device}) failed: "
+                               f"{self.lib.p2p_status_string(rc).decode()} (no CUDA device? there is no CPU fallback)")
+        self.ctx = ctx
+        self._pool: queue.Queue = queue.Queue()
+        for i in range(self.n_slots):
+            self._pool.put(i)
+        self._lock = threading.Lock()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.p2p_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc:
+            raise P2PError(rc, self.lib.p2p_last_error(self.ctx).decode(errors="replace"))
+
+    @contextmanager
+    def slots(self, n: int = 1):
+        """Borrow ``n`` slots (blocks until available)."""
+        if n > self.n_slots:
+            raise ValueError(f"need {n} slots, context has {self.n_slots}")
+        with self._lock:  # take all n atomically so two callers can not deadlock on partial sets
+            got = [self._pool.get() for _ in range(n)]
+        try:
+            yield got
+        finally:
+            for s in got:
+                self._pool.put(s)
+
+    def set_option(self, key: int, value: int):
+        self._ck(self.lib.p2p_set_option(self.ctx, key, value))
+
+    def get_option(self, key: int) -> int:
+        v = C.c_int()
+        self._ck(self.lib.p2p_get_option(self.ctx, key, C.byref(v)))
+        return v.value
+
+    @property
+    def launches(self) -> int:
+        return self.get_option(_lib.OPT_COUNT_LAUNCHES)
+
+    def sync(self, slot: int = -1):
+        self._ck(self.lib.p2p_sync(self.ctx, slot))
+
+    # -- raw ABI calls ----------------------------------------------------------------------
+    def upload(self, slot: int, pano: np.ndarray):
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        self._ck(self.lib.p2p_upload_pano(self.ctx, slot, pano.ctypes.data, Wp, Hp, pano.strides[0]))
+        return pano  # caller keeps it alive until the slot is synced
+
+    def upload_device(self, slot: int, dev_ptr: int, Wp: int, Hp: int, row_stride: int):
+        self._ck(self.lib.p2p_upload_pano_device(self.ctx, slot, C.c_void_p(dev_ptr), Wp, Hp, row_stride))
+
+    def rotate(self, src_slot: int, dst_slot: int, ix: np.ndarray, fx: np.ndarray):
+        ix = np.ascontiguousarray(ix, np.int32)
+        fx = np.ascontiguousarray(fx, np.int32)
+        self._ck(self.lib.p2p_rotate_pano(self.ctx, src_slot, dst_slot,
+                                          ix.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          fx.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    @staticmethod
+    def _consts_array(consts):
+        arr = (PitchConsts * len(consts))()
+        for i, (f, c, s) in enumerate(consts):
+            arr[i].f, arr[i].c, arr[i].s = f, c, s
+        return arr
+
+    def project(self, slot: int, shifts, consts, W: int, H: int, out=None, out_device_ptr: int | None = None):
+        """Enqueue n_yaw x n_pitch views.  ``out``: host array [n_yaw, n_pitch, H, W, 3] (created if
+        None) or ``out_device_ptr`` for device-resident results.  Returns ``out`` (valid after sync)."""
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
+        pc = self._consts_array(consts)
+        if out_device_ptr is not None:
+            dst, on_dev = C.c_void_p(out_device_ptr), 1
+        else:
+            if out is None:
+                out = np.empty((n_yaw, n_pitch, H, W, 3), np.uint8)
+            if out.dtype != np.uint8 or not out.flags.c_contiguous or out.size != n_yaw * n_pitch * H * W * 3:
+                raise ValueError("out must be C-contiguous uint8 [n_yaw, n_pitch, H, W, 3]")
+            dst, on_dev = out.ctypes.data, 0
+        self._ck(self.lib.p2p_project_views(self.ctx, slot, n_yaw, shifts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            n_pitch, pc, W, H, dst, on_dev))
+        return out
+
+    def process_image(self, slot: int, pano: np.ndarray, shifts, consts, W: int, H: int, out: np.ndarray):
+        """upload + project + readback in one ABI call (asynchronous; sync the slot before reading)."""
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        pc = self._consts_array(consts)
+        self._ck(self.lib.p2p_process_image(self.ctx, slot, pano.ctypes.data, Wp, Hp, pano.strides[0],
+                                            int(shifts.shape[0]), shifts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            len(consts), pc, W, H, out.ctypes.data))
+        return out
+
+    # -- debug exports ------------------------------------------------------------------------
+    def coords(self, W, H, fov_deg, pitch_deg, Wp, Hp):
+        pc = self._consts_array([pitch_constants(W, fov_deg, pitch_deg)])
+        U = np.empty((H, W), np.float32)
+        V = np.empty((H, W), np.float32)
+        self._ck(self.lib.p2p_coords(self.ctx, pc, W, H, Wp, Hp,
+                                     U.ctypes.data_as(C.POINTER(C.c_float)), V.ctypes.data_as(C.POINTER(C.c_float))))
+        return U, V
+
+    def sample_with_maps(self, slot: int, yaw_shift: int, U: np.ndarray, V: np.ndarray) -> np.ndarray:
+        U = np.ascontiguousarray(U, np.float32)
+        V = np.ascontiguousarray(V, np.float32)
+        H, W = U.shape
+        out = np.empty((H, W, 3), np.uint8)
+        self._ck(self.lib.p2p_sample_with_maps(self.ctx, slot, int(yaw_shift),
+                                               U.ctypes.data_as(C.POINTER(C.c_float)),
+                                               V.ctypes.data_as(C.POINTER(C.c_float)), W, H, out.ctypes.data))
+        return out
+
+    def download_pano(self, slot: int, Wp: int, Hp: int) -> np.ndarray:
+        out = np.empty((Hp, Wp, 3), np.uint8)
+        self._ck(self.lib.p2p_download_pano(self.ctx, slot, out.ctypes.data, out.strides[0]))
+        return out
+
+    # -- events -------------------------------------------------------------------------------
+    def event(self):
+        e = C.c_void_p()
+        self._ck(self.lib.p2p_event_create(self.ctx, C.byref(e)))
+        return e
+
+    def record(self, ev, slot: int):
+        self._ck(self.lib.p2p_event_record(self.ctx, ev, slot))
+
+    def elapsed_ms(self, start, stop) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.p2p_event_elapsed_ms(self.ctx, start, stop, C.byref(ms)))
+        return ms.value
+
+    def set_stream(self, slot: int, stream_ptr: int):
+        self._ck(self.lib.p2p_set_stream(self.ctx, slot, C.c_void_p(stream_ptr)))
+
+    def flush_l2(self, slot: int, nbytes: int):
+        self._ck(self.lib.p2p_flush_l2(self.ctx, slot, nbytes))
+
+    # -- the batched hot path -------------------------------------------------------------------
+    def project_image(self, pano: np.ndarray, yaw_angles, pitch_angles, W: int, H: int, fov_deg=90,
+                      out: np.ndarray | None = None, consts=None, tables=None) -> np.ndarray:
+        """All yaw x pitch views of one panorama: u8 [n_yaw, n_pitch, H, W, 3].
+
+        Replaces the reference's per-image fan-out (ref :252-265): every yaw that is an integer
+        column roll goes into one batched launch; a fractional yaw first materialises the rotated
+        panorama (the reference's yaw remap, ref :191-199) and is projected from that.
+        ``consts`` / ``tables`` let a caller pass memoised host scalars (the mirror module's caches).
+        """
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        yaw_angles = list(yaw_angles)
+        pitch_angles = list(pitch_angles)
+        if consts is None:
+            consts = [pitch_constants(W, fov_deg, p) for p in pitch_angles]
+        if tables is None:
+            tables = [yaw_table(Wp, y) for y in yaw_angles]
+        shape = (len(yaw_angles), len(pitch_angles), H, W, 3)
+        if out is None:
+            out = np.empty(shape, np.uint8)
+        elif out.shape != shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be C-contiguous uint8 {shape}")
+        if not yaw_angles or not pitch_angles:
+            return out
+        roll = [k for k, t in enumerate(tables) if t[2] is not None]
+        frac = [k for k, t in enumerate(tables) if t[2] is None]
+        with self.slots(2 if frac else 1) as got:
+            src = got[0]
+            self.upload(src, pano)
+            tmp = None
+            if roll:
+                dst = out if len(roll) == len(tables) else None
+                tmp = self.project(src, [tables[k][2] for k in roll], consts, W, H, out=dst)
+            for k in frac:
+                self.sync(src)  # the rotate kernel reads the packed source on another stream
+                self.rotate(src, got[1], tables[k][0], tables[k][1])
+                one = self.project(got[1], [0], consts, W, H)
+                self.sync(got[1])
+                out[k] = one[0]
+            self.sync(src)
+            if roll and tmp is not out:
+                for i, k in enumerate(roll):
+                    out[k] = tmp[i]
+        return out

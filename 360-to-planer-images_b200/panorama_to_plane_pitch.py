@@ -1,0 +1,249 @@
+"""Drop-in mirror of the reference's ``app/panorama_to_plane-pitch.py`` for its hot path.
+
+Same entry points, argument meaning, return types, file naming and error behaviour - the
+arithmetic runs on the B200 through ``libp2p_b200.so``:
+
+* ``process_yaw_and_pitchs(pano_image, yaw_angle, pitch_angles, output_width, output_height,
+  fov_deg=90) -> list[np.ndarray]``                                   (ref :181-221)
+* ``process_single_image(...)`` / ``main(...)`` / ``check_pitch``      (ref :227-280, :286-356, :362-376)
+* ``panorama_to_plane(path, FOV, output_size, yaw, pitch) -> np.ndarray`` - the 5-argument front
+  door BASELINE.json names (the reference's README lineage; equals
+  ``process_yaw_and_pitchs(cv2.imread(path), yaw, [pitch], W, H, FOV)[0]``)
+* the CLI with the reference's flags (ref :382-457), plus ``--device``.
+
+The reference's two memo tables survive with the same keys (ref :17-18, :42-73) but hold what
+the GPU path needs: the quantised yaw *column table* instead of a full-size (U, V) map, and the
+three f32 *pitch constants* instead of a full-size map (the map itself is evaluated per pixel
+inside the kernel and never stored).
+
+cv2 is used for file decode / encode only (``imread`` :244, ``imwrite`` :277), as in the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+from . import engine as _engine
+
+VERSION = "0.3.2"  # the reference version this mirrors (ref :20)
+
+# caches, same keys as the reference
+yaw_mapping_cache: dict = {}    # (pano_width, pano_height, yaw_angle) -> (ix, fx, shift)
+pitch_mapping_cache: dict = {}  # (W, H, pitch, pano_width, pano_height, fov) -> (f, c, s)
+
+_projectors: dict = {}
+_projectors_lock = threading.Lock()
+_default_device = 0
+
+
+def get_version():
+    return VERSION
+
+
+def set_device(device: int):
+    """Select the CUDA device the module-level entry points use (default 0)."""
+    global _default_device
+    _default_device = int(device)
+
+
+def get_projector(device: int | None = None) -> _engine.Projector:
+    d = _default_device if device is None else int(device)
+    with _projectors_lock:
+        if d not in _projectors:
+            _projectors[d] = _engine.Projector(d, n_slots=6)
+        return _projectors[d]
+
+
+def get_yaw_mapping(pano_width, pano_height, yaw_angle):
+    """Ref ``get_yaw_mapping`` :42-52, holding the column table (rows of the map are identical)."""
+    key = (pano_width, pano_height, yaw_angle)
+    if key not in yaw_mapping_cache:
+        logging.debug(f"[Yaw] Precomputing yaw mapping for yaw_angle: {yaw_angle} degrees")
+        yaw_mapping_cache[key] = _engine.yaw_table(pano_width, yaw_angle)
+    return yaw_mapping_cache[key]
+
+
+def get_pitch_mapping(output_width, output_height, pitch_angle, pano_width, pano_height, fov_deg=90):
+    """Ref ``get_pitch_mapping`` :55-73, holding the per-pitch constants."""
+    key = (output_width, output_height, pitch_angle, pano_width, pano_height, fov_deg)
+    if key not in pitch_mapping_cache:
+        pitch_mapping_cache[key] = _engine.pitch_constants(output_width, fov_deg, pitch_angle)
+    return pitch_mapping_cache[key]
+
+
+def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
+    """[n_yaw][n_pitch] views through the batched device path, using the module caches."""
+    pano = _engine._as_u8_image(pano_image, "pano_image")
+    Hp, Wp, _ = pano.shape
+    consts = [get_pitch_mapping(output_width, output_height, p, Wp, Hp, fov_deg) for p in pitch_angles]
+    tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
+    return proj.project_image(pano, yaw_angles, pitch_angles, output_width, output_height, fov_deg,
+                              consts=consts, tables=tables)
+
+
+def process_yaw_and_pitchs(pano_image, yaw_angle, pitch_angles, output_width, output_height, fov_deg=90):
+    """Process a single yaw angle and multiple pitch angles, returning all slices (ref :181-221)."""
+    logging.debug(f"[Yaw/Pitch] Starting processing for yaw_angle={yaw_angle}")
+    pitch_angles = list(pitch_angles)
+    if not pitch_angles:
+        # the reference still runs its yaw pass and returns an empty list
+        _ = np.asarray(pano_image).shape[2]
+        return []
+    out = _project(get_projector(), pano_image, [yaw_angle], pitch_angles, output_width, output_height, fov_deg)
+    return [out[0, j] for j in range(len(pitch_angles))]
+
+
+def panorama_to_plane(path, FOV, output_size, yaw, pitch):
+    """One planar view of the panorama file at ``path``: u8 [H, W, 3] in cv2's BGR order.
+
+    ``output_size`` is (width, height).  Raises ``FileNotFoundError`` if the image can not be read.
+    """
+    import cv2
+
+    pano = cv2.imread(str(path))
+    if pano is None:
+        raise FileNotFoundError(f"Failed to read image: {path}")
+    W, H = int(output_size[0]), int(output_size[1])
+    return process_yaw_and_pitchs(pano, yaw, [pitch], W, H, FOV)[0]
+
+
+def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles, output_width,
+                         output_height, num_workers=4, output_format="png", fov_deg=90):
+    """Read one image, project every yaw x pitch view, save the results (ref :227-280).
+
+    The reference submits one thread-pool task per yaw; here all views come from one batched
+    device call and ``num_workers`` threads only run the file encoders.  Output names are the
+    reference's (ref :275).  An unreadable image is logged and skipped (ref :245-247); a failure
+    while saving one yaw's results is logged and the other yaws continue (ref :279-280).
+    """
+    import cv2
+
+    input_image_path = Path(input_image_path)
+    output_dir = Path(output_dir)
+    logging.info(f"Loading image: {input_image_path}")
+    input_image = cv2.imread(str(input_image_path))
+    if input_image is None:
+        logging.error(f"Failed to read image: {input_image_path}")
+        return
+    base_name = input_image_path.stem
+    yaw_angles = list(yaw_angles)
+    pitch_angles = list(pitch_angles)
+    try:
+        views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    except Exception as e:
+        for yaw_angle in yaw_angles:
+            logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
+        return
+
+    def save_yaw(k):
+        yaw_angle = yaw_angles[k]
+        for i in range(len(pitch_angles)):
+            out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angle}"
+                            f"_pitch_{pitch_angles[i]}.{output_format}")
+            output_file = output_dir / out_filename
+            cv2.imwrite(str(output_file), views[k, i])
+            logging.debug(f"Saved {output_file}")
+
+    with ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
+        tasks = [executor.submit(save_yaw, k) for k in range(len(yaw_angles))]
+        for future, yaw_angle in zip(tasks, yaw_angles):
+            try:
+                future.result()
+            except Exception as e:
+                logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
+
+
+def main(input_path, output_path, yaw_angles, pitch_angles, output_width, output_height,
+         num_workers=None, output_format="png", fov_deg=90, enable_file_logging=False):
+    """Process a single image or every image under a folder (ref :286-356)."""
+    if num_workers is None:
+        cpu_cores = os.cpu_count() or 1
+        num_workers = max(1, int(cpu_cores * 0.9))
+        logging.info(f"No num_workers specified. Using {num_workers} (~90% of CPU cores).")
+    else:
+        logging.info(f"Using {num_workers} worker threads.")
+
+    output_dir = Path(output_path)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    logging.info(f"Output directory set to: {output_dir}")
+
+    input_path_obj = Path(input_path)
+    if input_path_obj.is_dir():
+        valid_exts = {".jpg", ".jpeg", ".png"}
+        all_images = [f for f in input_path_obj.rglob("*") if f.suffix.lower() in valid_exts]
+        if not all_images:
+            logging.warning(f"No images found in directory: {input_path_obj}")
+            return
+        logging.info(f"Found {len(all_images)} images in folder: {input_path_obj}")
+    else:
+        all_images = [input_path_obj]
+    for image_file in all_images:
+        process_single_image(
+            input_image_path=image_file, output_dir=output_dir, yaw_angles=yaw_angles,
+            pitch_angles=pitch_angles, output_width=output_width, output_height=output_height,
+            num_workers=num_workers, output_format=output_format, fov_deg=fov_deg,
+        )
+    logging.info("All processing completed.")
+
+
+def check_pitch(value: str) -> int:
+    """Validate the pitch angle is within 1-179 degrees (ref :362-376; CLI only)."""
+    try:
+        pitch = int(value)
+    except ValueError:
+        raise argparse.ArgumentTypeError(f"Pitch angle must be an integer, got '{value}'.")
+    if not (1 <= pitch <= 179):
+        raise argparse.ArgumentTypeError(f"Pitch angle must be between 1 and 179 degrees, got {pitch}.")
+    return pitch
+
+
+def build_parser() -> argparse.ArgumentParser:
+    """The reference's flags (ref :383-455) plus ``--device``."""
+    p = argparse.ArgumentParser(
+        description="Process panorama images or an entire folder of images into planar projections (B200 path)."
+    )
+    p.add_argument("--input_path", type=str, required=True, help="Path to the input panorama image or folder of images")
+    p.add_argument("--output_path", type=str, default="output_images", help="Path to save the output images")
+    p.add_argument("--output_format", type=str, choices=["png", "jpg", "jpeg"], default="png",
+                   help="Output image format (png, jpg, jpeg)")
+    p.add_argument("--FOV", type=int, default=90, help="Field of View in degrees")
+    p.add_argument("--output_width", type=int, default=800, help="Width of the output image in pixels")
+    p.add_argument("--output_height", type=int, default=800, help="Height of the output image in pixels")
+    p.add_argument("--pitch_angles", nargs="+", type=check_pitch, default=[30, 60, 90, 120, 150],
+                   help="List of pitch angles in degrees (1-179). e.g. --pitch_angles 30 60 90")
+    p.add_argument("--yaw_angles", nargs="+", type=int, default=[0, 90, 180, 270],
+                   help="List of yaw angles in degrees (0-360). e.g. --yaw_angles 0 90 180 270")
+    p.add_argument("--num_workers", type=int, default=None,
+                   help="Number of worker threads (file encoders here). If not specified, uses ~90%% of CPU cores.")
+    p.add_argument("--enable_file_logging", action="store_true", help="Enable logging to a file.")
+    p.add_argument("--device", type=int, default=0, help="CUDA device index (extra flag; default 0)")
+    p.add_argument("-v", "--version", action="version", version=f"%(prog)s {get_version()}",
+                   help="Show version information")
+    return p
+
+
+def cli(argv=None):
+    args = build_parser().parse_args(argv)
+    handlers = [logging.StreamHandler()]
+    if args.enable_file_logging:
+        log_file_path = Path.cwd() / "logs" / "app.log"
+        log_file_path.parent.mkdir(parents=True, exist_ok=True)
+        handlers.append(logging.FileHandler(log_file_path, mode="a"))
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s [%(levelname)s] %(message)s", handlers=handlers)
+    set_device(args.device)
+    main(
+        input_path=args.input_path, output_path=args.output_path, yaw_angles=args.yaw_angles,
+        pitch_angles=args.pitch_angles, output_width=args.output_width, output_height=args.output_height,
+        num_workers=args.num_workers, output_format=args.output_format, fov_deg=args.FOV,
+        enable_file_logging=args.enable_file_logging,
+    )
+
+
+if __name__ == "__main__":
+    cli()

@@ -1,0 +1,142 @@
+/*
+ * p2p.h - C ABI of the B200-native panorama -> plane projection library (libp2p_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of Maxiviper117/360-to-planer-images:
+ * the per-view projection in app/panorama_to_plane-pitch.py.  The reference has no FFI seam
+ * of its own (it is a single Python script calling NumPy and cv2.remap), so each entry point
+ * below names the reference lines it replaces; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; all functions return 0 (P2P_OK) or a negative p2p_status;
+ *     p2p_last_error(ctx) returns a human readable message for the last failure on ctx.
+ *   - images are 8-bit, 3 channels, interleaved, channel order preserved (the reference keeps
+ *     cv2's BGR end to end, ref :244; channels are independent in the arithmetic).
+ *   - the caller owns every host buffer; the library owns device memory inside the context.
+ *   - a context belongs to one CUDA device and is thread-safe (calls are serialised on an
+ *     internal mutex and only enqueue work); work of different "slots" runs on different
+ *     CUDA streams so upload / projection / readback of consecutive images overlap.
+ *   - there is no CPU fallback: p2p_create fails if no CUDA device is usable.
+ */
+#ifndef P2P_B200_H
+#define P2P_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2P_ABI_VERSION 1
+
+typedef struct p2p_ctx p2p_ctx;
+
+typedef enum p2p_status {
+    P2P_OK = 0,
+    P2P_ERR_INVALID = -1, /* bad argument (null pointer, non-positive size, bad slot ...) */
+    P2P_ERR_CUDA = -2,    /* a CUDA runtime call failed; see p2p_last_error */
+    P2P_ERR_NOMEM = -3,   /* device or pinned-host allocation failed */
+    P2P_ERR_STATE = -4,   /* slot holds no panorama / size mismatch */
+    P2P_ERR_LIMIT = -5    /* size beyond the limits inherited from cv2.remap (< 32767) */
+} p2p_status;
+
+/* Per-pitch constants of the pitch map, formed on the host exactly as the reference does
+ * (ref precompute_pitch_mapping :119 focal length, :142-149 R_pitch entries, cast to f32). */
+typedef struct p2p_pitch_consts {
+    float f; /* float32(0.5 * W / tan(FOV_rad / 2))           ref :119, :131 */
+    float c; /* float32(cos(pitch_rad))                        ref :145-147   */
+    float s; /* float32(sin(pitch_rad))                        ref :145-147   */
+} p2p_pitch_consts;
+
+/* option keys for p2p_set_option */
+typedef enum p2p_option {
+    P2P_OPT_SAMPLER = 0, /* 0 = global-load gather (default), 1 = texture gather4 point fetch */
+    P2P_OPT_WARP_W = 1,  /* output pixels per warp row: 32 (default), 16 or 8 (2-D warp tiles) */
+    P2P_OPT_YAWS_PER_THREAD = 2, /* 1..4 views sharing one coordinate evaluation (default 4) */
+    P2P_OPT_COUNT_LAUNCHES = 3   /* read-only via p2p_get_option: kernels launched so far */
+} p2p_option;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int p2p_abi_version(void);
+int p2p_device_count(void);
+/* n_slots independent panorama slots (each with its own stream and device buffers). */
+int p2p_create(int device, int n_slots, p2p_ctx **out);
+void p2p_destroy(p2p_ctx *ctx);
+const char *p2p_last_error(p2p_ctx *ctx);
+const char *p2p_status_string(int status);
+int p2p_set_option(p2p_ctx *ctx, int key, int value);
+int p2p_get_option(p2p_ctx *ctx, int key, int *value);
+
+/* ---- host helpers (no GPU work) --------------------------------------------------------- */
+/* libm restatement of the reference's host scalars: np.radians (:64, :68), focal (:119),
+ * cos / sin (:142-149).  The Python host forms them with NumPy instead (identical by
+ * construction); this export is for non-Python callers. */
+int p2p_pitch_constants(double fov_deg, double pitch_deg, int W, p2p_pitch_consts *out);
+/* Quantised yaw column table: (ix, fx) = cv2's 1/32-px fixed point form of one row of the
+ * reference yaw map (precompute_yaw_mapping :85-105; all rows are equal, V = v :102).
+ * Returns in *shift the column roll if the table is a pure integer roll, else -1. */
+int p2p_yaw_table(int Wp, double yaw_deg, int32_t *ix, int32_t *fx, int32_t *shift);
+/* page-locked host memory for overlapped transfers */
+int p2p_host_alloc(void **ptr, size_t bytes);
+int p2p_host_free(void *ptr);
+int p2p_host_register(void *ptr, size_t bytes);
+int p2p_host_unregister(void *ptr);
+
+/* ---- panorama upload (replaces holding the cv2.imread result, ref :244) ------------------ */
+/* Copy a host BGR panorama (row_stride bytes between rows) into `slot` and pack it to the
+ * device layout (RGBA-packed uint32, one duplicated wrap column and clamp row).  Asynchronous
+ * on the slot's stream when `bgr` is page-locked. */
+int p2p_upload_pano(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride);
+/* Same, but `d_bgr` is a device pointer on ctx's device (no PCIe transfer). */
+int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, int Hp, size_t row_stride);
+
+/* Yaw pass for yaws that are not an integer column roll: materialise the rotated panorama
+ * of `src_slot` into `dst_slot` with the Wp-entry table from p2p_yaw_table.  Bit-exact form of
+ * the reference's first cv2.remap (ref :191-199). */
+int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix, const int32_t *fx);
+
+/* ---- the hot path (replaces process_yaw_and_pitchs, ref :181-221, for a whole batch of
+ *      yaws: the ThreadPoolExecutor fan-out of ref :252-265 becomes one launch) ------------- */
+/* Computes n_yaw * n_pitch views of the panorama in `slot`:
+ *   out[(k * n_pitch + j)][v][u][ch], k = yaw index, j = pitch index, u8, W*H*3 bytes per view.
+ * yaw_shift[k] in [0, Wp) is the integer column roll of yaw k (p2p_yaw_table); for other yaws
+ * project from a slot produced by p2p_rotate_pano with shift 0.
+ * out_on_device = 0: `out` is host memory, a device->host copy is enqueued after the kernel
+ *                    (asynchronous if `out` is page-locked); call p2p_sync before reading.
+ * out_on_device = 1: `out` is a device pointer, results stay in HBM. */
+int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                      const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device);
+
+/* upload + project + readback of one image in one call (all asynchronous on the slot stream) */
+int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
+                      int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
+                      int W, int H, uint8_t *out_host);
+
+/* wait for everything enqueued on `slot` (slot < 0: all slots) */
+int p2p_sync(p2p_ctx *ctx, int slot);
+/* run the slot's work on a caller supplied cudaStream_t (e.g. torch's current stream) */
+int p2p_set_stream(p2p_ctx *ctx, int slot, void *cuda_stream);
+
+/* ---- device timing on the launching stream ----------------------------------------------- */
+int p2p_event_create(p2p_ctx *ctx, void **event);
+int p2p_event_destroy(p2p_ctx *ctx, void *event);
+int p2p_event_record(p2p_ctx *ctx, void *event, int slot);
+int p2p_event_elapsed_ms(p2p_ctx *ctx, void *start, void *stop, float *ms); /* syncs on stop */
+/* overwrite `bytes` of scratch device memory on the slot's stream (L2 flush between reps) */
+int p2p_flush_l2(p2p_ctx *ctx, int slot, size_t bytes);
+
+/* ---- stage-isolated debug exports (parity tests) ----------------------------------------- */
+/* coordinates only: the (U, V) f32 maps of ref precompute_pitch_mapping :114-175, to host */
+int p2p_coords(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
+               float *U_host, float *V_host);
+/* sampler only: injected host (U, V) maps, one integer yaw shift; ref :212-218 */
+int p2p_sample_with_maps(p2p_ctx *ctx, int slot, int yaw_shift, const float *U_host,
+                         const float *V_host, int W, int H, uint8_t *out_host);
+/* read back the packed panorama of a slot as BGR (checks upload / rotate) */
+int p2p_download_pano(p2p_ctx *ctx, int slot, uint8_t *bgr_host, size_t row_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2P_B200_H */
