@@ -48,9 +48,11 @@ SIGNATURES = {
     "p2p_upload_pano_device": (_i, [_vp, _i, _vp, _i, _i, _sz]),
     "p2p_rotate_pano": (_i, [_vp, _i, _i, _i32p, _i32p]),
     "p2p_project_views": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _u8p, _i]),
+    "p2p_project_batch": (_i, [_vp, _i, _i32p, _i, _i32p, _i, _pcp, _i, _i, C.POINTER(_vp), _i]),
     "p2p_process_image": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _u8p]),
     "p2p_sync": (_i, [_vp, _i]),
     "p2p_set_stream": (_i, [_vp, _i, _vp]),
+    "p2p_get_stream": (_i, [_vp, _i, C.POINTER(_vp)]),
     "p2p_event_create": (_i, [_vp, C.POINTER(_vp)]),
     "p2p_event_destroy": (_i, [_vp, _vp]),
     "p2p_event_record": (_i, [_vp, _vp, _i]),

@@ -18,6 +18,7 @@ namespace {
 struct Slot {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t owned = nullptr;  // created by us, replaced through p2p_set_stream
     uint8_t *d_bgr = nullptr;  // staging copy of the caller's BGR rows
     size_t bgr_cap = 0;
     uint32_t *d_rgba = nullptr;  // packed panorama
@@ -316,6 +317,7 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.d_out);
         cudaFree(s.d_tab);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+        if (s.owned) cudaStreamDestroy(s.owned);
     }
     cudaFree(ctx->d_flush);
     cudaGetLastError();
@@ -532,6 +534,17 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
     return P2P_OK;
 }
 
+int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
+                      int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
+                      int out_on_device) {
+    if (!ctx || n_images <= 0 || !slots || !outs) return fail(ctx, P2P_ERR_INVALID, "bad batch arguments");
+    for (int i = 0; i < n_images; ++i) {
+        int rc = p2p_project_views(ctx, slots[i], n_yaw, yaw_shift, n_pitch, pitch, W, H, outs[i], out_on_device);
+        if (rc) return rc;
+    }
+    return P2P_OK;
+}
+
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
                       int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
                       int W, int H, uint8_t *out_host) {
@@ -559,9 +572,18 @@ int p2p_set_stream(p2p_ctx *ctx, int slot, void *cuda_stream) {
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
     CK(cudaStreamSynchronize(s.stream));
-    if (s.own_stream && s.stream) CK(cudaStreamDestroy(s.stream));
+    // the slot's own stream is kept (another slot may have borrowed it through p2p_get_stream)
+    // and released by p2p_destroy
+    if (s.own_stream) s.owned = s.stream;
     s.stream = static_cast<cudaStream_t>(cuda_stream);
     s.own_stream = false;
+    return P2P_OK;
+}
+
+int p2p_get_stream(p2p_ctx *ctx, int slot, void **cuda_stream) {
+    if (!slot_ok(ctx, slot) || !cuda_stream) return fail(ctx, P2P_ERR_INVALID, "bad slot or null pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *cuda_stream = ctx->slots[slot].stream;
     return P2P_OK;
 }
 

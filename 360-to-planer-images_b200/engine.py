@@ -195,6 +195,22 @@ class Projector:
                                             n_pitch, pc, W, H, dst, on_dev))
         return out
 
+    def batch_call(self, slots, shifts, consts, W: int, H: int, out_ptrs, on_device: bool = True):
+        """Prebuilt ``p2p_project_batch`` call for resident panoramas: returns a zero-argument
+        callable that enqueues one launch per slot (arguments are marshalled once)."""
+        slots_a = np.ascontiguousarray(slots, np.int32)
+        shifts_a = np.ascontiguousarray(shifts, np.int32)
+        pc = self._consts_array(consts)
+        outs = (C.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        args = (self.ctx, len(slots_a), slots_a.ctypes.data_as(C.POINTER(C.c_int32)), int(shifts_a.shape[0]),
+                shifts_a.ctypes.data_as(C.POINTER(C.c_int32)), len(consts), pc, W, H, outs, 1 if on_device else 0)
+        fn = self.lib.p2p_project_batch
+
+        def call(_keep=(slots_a, shifts_a, pc, outs)):
+            self._ck(fn(*args))
+
+        return call
+
     def process_image(self, slot: int, pano: np.ndarray, shifts, consts, W: int, H: int, out: np.ndarray):
         """upload + project + readback in one ABI call (asynchronous; sync the slot before reading)."""
         pano = _as_u8_image(pano)
@@ -246,6 +262,18 @@ class Projector:
 
     def set_stream(self, slot: int, stream_ptr: int):
         self._ck(self.lib.p2p_set_stream(self.ctx, slot, C.c_void_p(stream_ptr)))
+
+    def get_stream(self, slot: int) -> int:
+        st = C.c_void_p()
+        self._ck(self.lib.p2p_get_stream(self.ctx, slot, C.byref(st)))
+        return st.value or 0
+
+    def share_stream(self, slots, from_slot: int = 0):
+        """Run several slots on one stream (serialised launches, e.g. for event timing)."""
+        st = self.get_stream(from_slot)
+        for s in slots:
+            if s != from_slot:
+                self.set_stream(s, st)
 
     def flush_l2(self, slot: int, nbytes: int):
         self._ck(self.lib.p2p_flush_l2(self.ctx, slot, nbytes))

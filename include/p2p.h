@@ -108,6 +108,13 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
 int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                       const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device);
 
+/* The same views for a batch of panoramas that are already resident (one launch per image,
+ * each on its slot's stream): slots[i] -> outs[i].  One host call per batch keeps the launch
+ * queue full when a launch is only tens of microseconds (BASELINE configs[2]). */
+int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
+                      int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
+                      int out_on_device);
+
 /* upload + project + readback of one image in one call (all asynchronous on the slot stream) */
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
                       int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
@@ -117,6 +124,8 @@ int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp
 int p2p_sync(p2p_ctx *ctx, int slot);
 /* run the slot's work on a caller supplied cudaStream_t (e.g. torch's current stream) */
 int p2p_set_stream(p2p_ctx *ctx, int slot, void *cuda_stream);
+/* the cudaStream_t a slot currently runs on (e.g. to put several slots on one stream) */
+int p2p_get_stream(p2p_ctx *ctx, int slot, void **cuda_stream);
 
 /* ---- device timing on the launching stream ----------------------------------------------- */
 int p2p_event_create(p2p_ctx *ctx, void **event);

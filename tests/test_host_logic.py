@@ -1,0 +1,150 @@
+"""CPU tests of the host side: scalars, yaw tables, C helpers, CLI surface, ABI exports."""
+import ctypes as C
+import logging
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import fixedpoint as fp
+from oracle import ref_port
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = (ROOT / "include" / "p2p.h").read_text()
+    declared = set(re.findall(r"\b(p2p_[a-z0-9_]+)\s*\(", header))
+    declared -= {"p2p_ctx"}
+    assert len(declared) >= 25
+    lib = pkg._lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/p2p.h but not exported"
+    assert declared == set(pkg._lib.SIGNATURES), "ctypes table and header disagree"
+    assert lib.p2p_abi_version() == 1
+    assert lib.p2p_status_string(0) == b"ok"
+
+
+def test_create_fails_loudly_without_device(pkg):
+    lib = pkg._lib.load()
+    if lib.p2p_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    ctx = C.c_void_p()
+    assert lib.p2p_create(0, 2, C.byref(ctx)) == -2
+    assert not ctx.value
+    with pytest.raises(pkg.P2PError):
+        pkg.Projector(0)
+    with pytest.raises(pkg.P2PError):  # the drop-in entry point has no CPU path either
+        pkg.process_yaw_and_pitchs(np.zeros((8, 16, 3), np.uint8), 0, [90], 4, 4, 90)
+
+
+def test_pitch_constants_match_reference_expressions(pkg):
+    lib = pkg._lib.load()
+    mism = 0
+    for W in (640, 1920, 800, 3840, 2048, 333):
+        for fov in (30, 60, 90, 100, 120, 150, 179):
+            for pitch in range(0, 181):
+                want = ref_port.pitch_scalars(W, fov, pitch)
+                got = pkg.pitch_constants(W, fov, pitch)
+                assert tuple(np.float32(x) for x in got) == tuple(want)
+                pc = pkg.PitchConsts()
+                assert lib.p2p_pitch_constants(float(fov), float(pitch), W, C.byref(pc)) == 0
+                mism += (np.float32(pc.f), np.float32(pc.c), np.float32(pc.s)) != tuple(want)
+    # the libm export is for non-Python callers; it must agree with NumPy on this grid
+    assert mism == 0
+
+
+def test_yaw_table_host_and_c_helper_match_oracle(pkg):
+    lib = pkg._lib.load()
+    for Wp in (1000, 1024, 2048, 4096, 8192, 16384, 360, 1023):
+        for yaw in (0, 90, 180, 270, 360, 30, 1, 359, 77, 45, -90, 450, 123):
+            ix_o, fx_o = fp.yaw_column_table(Wp, yaw)
+            ix, fx, shift = pkg.yaw_table(Wp, yaw)
+            assert np.array_equal(ix, ix_o) and np.array_equal(fx, fx_o)
+            assert shift == fp.yaw_table_is_roll(ix_o, fx_o)
+            cix = np.empty(Wp, np.int32)
+            cfx = np.empty(Wp, np.int32)
+            cs = C.c_int32(-7)
+            rc = lib.p2p_yaw_table(Wp, float(yaw), cix.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   cfx.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(cs))
+            assert rc == 0
+            assert np.array_equal(cix, ix_o) and np.array_equal(cfx, fx_o), (Wp, yaw)
+            assert cs.value == (-1 if shift is None else shift)
+
+
+def test_baseline_yaws_are_integer_rolls(pkg):
+    for Wp in (2048, 8192, 16384):
+        for yaw, frac in ((0, 0), (90, 1), (180, 2), (270, 3)):
+            assert pkg.yaw_table(Wp, yaw)[2] == frac * Wp // 4
+
+
+def test_cli_flags_and_defaults_match_reference(pkg):
+    ap = pkg.panorama_to_plane_pitch.build_parser()
+    a = ap.parse_args(["--input_path", "x"])
+    assert (a.output_path, a.output_format, a.FOV, a.output_width, a.output_height) == ("output_images", "png", 90, 800, 800)
+    assert a.pitch_angles == [30, 60, 90, 120, 150] and a.yaw_angles == [0, 90, 180, 270]
+    assert a.num_workers is None and a.enable_file_logging is False
+    a = ap.parse_args("--input_path p --FOV 120 --output_width 1920 --output_height 1080 "
+                      "--pitch_angles 30 60 90 --yaw_angles 0 90 180 270 --output_format jpg --num_workers 3".split())
+    assert (a.FOV, a.output_width, a.output_height, a.output_format, a.num_workers) == (120, 1920, 1080, "jpg", 3)
+    with pytest.raises(SystemExit):
+        ap.parse_args(["--input_path", "x", "--pitch_angles", "0"])
+    with pytest.raises(SystemExit):
+        ap.parse_args(["--input_path", "x", "--pitch_angles", "180"])
+    with pytest.raises(SystemExit):
+        ap.parse_args(["--input_path", "x", "--output_format", "bmp"])
+    assert pkg.check_pitch("1") == 1 and pkg.check_pitch("179") == 179
+    import argparse
+
+    with pytest.raises(argparse.ArgumentTypeError):
+        pkg.check_pitch("abc")
+    assert pkg.get_version() == "0.3.2"
+
+
+def test_unreadable_image_is_logged_and_skipped(pkg, tmp_path, caplog):
+    bad = tmp_path / "not_an_image.png"
+    bad.write_bytes(b"nope")
+    with caplog.at_level(logging.ERROR):
+        assert pkg.process_single_image(bad, tmp_path, [0], [90], 8, 8) is None
+    assert any("Failed to read image" in r.message for r in caplog.records)
+    with pytest.raises(FileNotFoundError):
+        pkg.panorama_to_plane(bad, 90, (8, 8), 0, 90)
+
+
+def test_empty_directory_warns(pkg, tmp_path, caplog):
+    with caplog.at_level(logging.WARNING):
+        pkg.main(str(tmp_path), str(tmp_path / "out"), [0], [90], 8, 8, num_workers=1)
+    assert any("No images found" in r.message for r in caplog.records)
+    assert (tmp_path / "out").is_dir()
+
+
+def test_image_argument_validation(pkg):
+    from p2p_b200 import engine
+
+    with pytest.raises(ValueError):
+        engine._as_u8_image(np.zeros((4, 4), np.uint8))
+    with pytest.raises(ValueError):
+        engine._as_u8_image(np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(ValueError):
+        engine._as_u8_image(np.zeros((4, 4, 4), np.uint8))
+    a = np.zeros((4, 8, 3), np.uint8)[:, ::2]  # non-unit pixel stride -> copied
+    assert engine._as_u8_image(a).flags.c_contiguous
+    b = np.zeros((4, 8, 3), np.uint8)[:, :5]   # row-strided view is accepted as is
+    assert engine._as_u8_image(b) is b or engine._as_u8_image(b).base is b.base
+
+
+def test_sharding(pkg):
+    from p2p_b200 import shard
+
+    for n, world in ((256, 8), (5, 2), (3, 4), (0, 2)):
+        seen = sorted(i for r in range(world) for i in shard.shard_images(n, r, world))
+        assert seen == list(range(n))
+    for (ny, npitch, world) in ((4, 3, 1), (4, 3, 2), (4, 3, 4), (4, 3, 8), (1, 1, 2)):
+        allv = [v for r in range(world) for v in shard.shard_views(ny, npitch, r, world)]
+        assert sorted(allv) == sorted((k, j) for k in range(ny) for j in range(npitch))
+        sizes = [len(shard.shard_views(ny, npitch, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard.group_by_pitch([(0, 1), (1, 1), (0, 2)]) == {1: [0, 1], 2: [0]}
+    with pytest.raises(ValueError):
+        shard.shard_images(4, 2, 2)

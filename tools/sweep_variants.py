@@ -1,0 +1,77 @@
+"""Resident-throughput sweep over the kernel variants (run on the GPU box).
+
+    python tools/sweep_variants.py [--batch 16] [--steps 5] > gpurun_out/sweep.jsonl
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as g  # noqa: E402
+from oracle import synth  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 16, 8])
+    ap.add_argument("--nys", type=int, nargs="+", default=[4, 2, 1])
+    args = ap.parse_args()
+    import torch
+
+    g.build()
+    pkg = g.load_package()
+    L = pkg._lib
+    dev = torch.device("cuda", 0)
+    proj = pkg.Projector(0, n_slots=args.batch)
+    slots = list(range(args.batch))
+    proj.share_stream(slots, 0)
+    base = synth.noise(bench.WP, bench.HP, 0)
+    d_stage = torch.from_numpy(base).to(dev)
+    for i in slots:
+        st = torch.roll(d_stage, shifts=131 * i, dims=1).contiguous()
+        torch.cuda.synchronize()
+        proj.upload_device(i, st.data_ptr(), bench.WP, bench.HP, bench.WP * 3)
+        proj.sync(i)
+    d_out = torch.empty((args.batch, bench.N_VIEWS, bench.H, bench.W, 3), dtype=torch.uint8, device=dev)
+    outs = [d_out[i].data_ptr() for i in slots]
+    consts = [pkg.pitch_constants(bench.W, bench.FOV, p) for p in bench.PITCHES]
+    shifts = [pkg.yaw_table(bench.WP, y)[2] for y in bench.YAWS]
+    step = proj.batch_call(slots, shifts, consts, bench.W, bench.H, outs)
+    ev0, ev1 = proj.event(), proj.event()
+    ref = None
+    for sampler in args.samplers:
+        for ww in args.warp_ws:
+            for ny in args.nys:
+                proj.set_option(L.OPT_SAMPLER, sampler)
+                proj.set_option(L.OPT_WARP_W, ww)
+                proj.set_option(L.OPT_YAWS_PER_THREAD, ny)
+                for _ in range(3):
+                    step()
+                proj.sync(0)
+                proj.record(ev0, 0)
+                for _ in range(args.steps):
+                    step()
+                proj.record(ev1, 0)
+                proj.sync(0)
+                ms = proj.elapsed_ms(ev0, ev1) / (args.steps * args.batch)
+                torch.cuda.synchronize()
+                chk = int(d_out[0].to(torch.int64).sum().item())
+                ref = chk if ref is None else ref
+                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "launch_us": ms * 1e3,
+                                  "gpix_s": bench.PX_PER_IMAGE / (ms * 1e-3) / 1e9,
+                                  "roofline_frac": bench.B_ALG_PER_IMAGE / (ms * 1e-3) / 1e9 / bench.read_peaks()[0],
+                                  "same_output": chk == ref}), flush=True)
+    proj.close()
+
+
+if __name__ == "__main__":
+    main()
