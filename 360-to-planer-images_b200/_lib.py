@@ -58,12 +58,13 @@ SIGNATURES = {
     "p2p_event_record": (_i, [_vp, _vp, _i]),
     "p2p_event_elapsed_ms": (_i, [_vp, _vp, _vp, _f32p]),
     "p2p_flush_l2": (_i, [_vp, _i, _sz]),
+    "p2p_selftest": (_i, [_vp, _pcp, _i, _i, _i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "p2p_coords": (_i, [_vp, _pcp, _i, _i, _i, _i, _f32p, _f32p]),
     "p2p_sample_with_maps": (_i, [_vp, _i, _i, _f32p, _f32p, _i, _i, _u8p]),
     "p2p_download_pano": (_i, [_vp, _i, _u8p, _sz]),
 }
 
-OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES = 0, 1, 2, 3
+OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH = 0, 1, 2, 3, 4
 
 _lib = None
 

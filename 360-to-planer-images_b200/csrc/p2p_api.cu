@@ -46,6 +46,7 @@ struct p2p_ctx {
     int opt_sampler = 0;
     int opt_warp_w = 32;
     int opt_ny = 4;
+    int opt_nb = 1;
     long long launches = 0;
     uint4 *d_flush = nullptr;
     size_t flush_cap = 0;
@@ -157,71 +158,89 @@ int ensure_texture(p2p_ctx *ctx, Slot &s) {
 
 typedef void (*proj_fn)(const ProjParams);
 
-template <int WARP_W, int SAMPLER>
+template <int WARP_W, int NB, int SAMPLER, bool QUAD>
 proj_fn pick_ny(int ny) {
     switch (ny) {
-        case 1: return project_kernel<WARP_W, 1, SAMPLER>;
-        case 2: return project_kernel<WARP_W, 2, SAMPLER>;
-        case 3: return project_kernel<WARP_W, 3, SAMPLER>;
-        default: return project_kernel<WARP_W, 4, SAMPLER>;
+        case 1: return project_kernel<WARP_W, 1, NB, SAMPLER, QUAD>;
+        case 2: return project_kernel<WARP_W, 2, NB, SAMPLER, QUAD>;
+        case 3: return project_kernel<WARP_W, 3, NB, SAMPLER, QUAD>;
+        default: return project_kernel<WARP_W, 4, NB, SAMPLER, QUAD>;
     }
 }
 
-template <int SAMPLER>
+template <int NB, int SAMPLER>
 proj_fn pick_w(int warp_w, int ny) {
-    switch (warp_w) {
-        case 8: return pick_ny<8, SAMPLER>(ny);
-        case 16: return pick_ny<16, SAMPLER>(ny);
-        default: return pick_ny<32, SAMPLER>(ny);
+    return (warp_w == 8) ? pick_ny<8, NB, SAMPLER, true>(ny) : pick_ny<32, NB, SAMPLER, true>(ny);
+}
+
+// the packed-store variants; outputs with W % 4 != 0 (or unaligned) use one generic byte-store kernel
+template <int SAMPLER>
+proj_fn pick_kernel(bool quad, int nb, int warp_w, int ny) {
+    if (!quad) return pick_ny<32, 1, SAMPLER, false>(ny);
+    switch (nb) {
+        case 4: return pick_w<4, SAMPLER>(warp_w, ny);
+        case 2: return pick_w<2, SAMPLER>(warp_w, ny);
+        default: return pick_w<1, SAMPLER>(warp_w, ny);
     }
 }
 
-int launch_project(p2p_ctx *ctx, Slot &s, int n_yaw, const int32_t *yaw_shift, int n_pitch,
-                   const p2p_pitch_consts *pitch, int W, int H, uint8_t *d_out) {
+// One or several (nb = 1, 2, 4) same-sized resident panoramas -> their view batches.  All launches
+// go to the stream of the first slot.
+int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                   const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *d_out) {
+    Slot &s = *sl[0];
     if (ctx->opt_sampler == 1) {
-        int rc = ensure_texture(ctx, s);
-        if (rc) return rc;
+        for (int b = 0; b < nb; ++b) {
+            int rc = ensure_texture(ctx, *sl[b]);
+            if (rc) return rc;
+        }
     }
-    // chunk over yaws / pitches so any list length works
-    for (int y0 = 0; y0 < n_yaw; y0 += kMaxYawPerLaunch) {
-        const int ny_l = (n_yaw - y0 < kMaxYawPerLaunch) ? n_yaw - y0 : kMaxYawPerLaunch;
+    const int ny_max = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
+    ProjParams P;
+    memset(&P, 0, sizeof(P));
+    bool aligned = true;
+    for (int b = 0; b < nb; ++b) {
+        P.pano[b] = sl[b]->d_rgba;
+        P.tex[b] = sl[b]->tex;
+        P.out[b] = d_out[b];
+        aligned = aligned && ((reinterpret_cast<uintptr_t>(d_out[b]) & 3) == 0);
+    }
+    P.view_stride = (unsigned long long)W * H * 3;
+    P.yaw_stride = P.view_stride * (unsigned long long)n_pitch;
+    P.pitch_tex = s.pitch_tex;
+    P.Wp = s.Wp;
+    P.Hp = s.Hp;
+    P.W = W;
+    P.H = H;
+    P.halfW = (float)(W / 2.0);
+    P.halfH = (float)(H / 2.0);
+    P.Wp_f = (float)s.Wp;
+    P.Hp_f = (float)s.Hp;
+    P.Umax = (float)(s.Wp - 1);
+    P.Vmax = (float)(s.Hp - 1);
+    const bool quad = ((W & 3) == 0) && aligned;
+    if (!quad && nb > 1) return fail(ctx, P2P_ERR_INVALID, "multi-image launches need W % 4 == 0 and aligned outputs");
+    // chunk over yaws (<= 4 share one coordinate evaluation) and pitches (grid.z) so any list length works
+    for (int y0 = 0; y0 < n_yaw; y0 += ny_max) {
+        const int ny_l = (n_yaw - y0 < ny_max) ? n_yaw - y0 : ny_max;
+        for (int k = 0; k < 4; ++k) {
+            P.shift[k] = (k < ny_l) ? yaw_shift[y0 + k] : 0;
+            P.shift_p1_f[k] = (float)(P.shift[k] + 1);
+        }
+        P.yaw_off = y0;
         for (int p0 = 0; p0 < n_pitch; p0 += kMaxPitchPerLaunch) {
             const int np_l = (n_pitch - p0 < kMaxPitchPerLaunch) ? n_pitch - p0 : kMaxPitchPerLaunch;
-            ProjParams P;
-            memset(&P, 0, sizeof(P));
-            P.pano = s.d_rgba;
-            P.tex = s.tex;
-            P.view_stride = (unsigned long long)W * H * 3;
-            P.pitch_tex = s.pitch_tex;
-            P.Wp = s.Wp;
-            P.Hp = s.Hp;
-            P.W = W;
-            P.H = H;
-            P.n_yaw = ny_l;
             P.n_pitch = np_l;
-            P.halfW = (float)(W / 2.0);
-            P.halfH = (float)(H / 2.0);
-            P.Wp_f = (float)s.Wp;
-            P.Hp_f = (float)s.Hp;
-            P.Umax = (float)(s.Wp - 1);
-            P.Vmax = (float)(s.Hp - 1);
-            for (int k = 0; k < ny_l; ++k) P.shift[k] = yaw_shift[y0 + k];
+            P.pitch_off = p0;
             for (int j = 0; j < np_l; ++j) {
                 P.pc[j].f = pitch[p0 + j].f;
                 P.pc[j].c = pitch[p0 + j].c;
                 P.pc[j].s = pitch[p0 + j].s;
             }
-            P.out = d_out;
-            P.yaw_off = y0;
-            P.pitch_off = p0;
-            P.n_pitch_total = n_pitch;
-            P.quad_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0);
-            const int ny_thread = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
-            const int groups = (ny_l + ny_thread - 1) / ny_thread;
-            dim3 grid((W + 31) / 32, (H + 7) / 8, groups * np_l);
-            if (grid.y > 65535 || grid.z > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
-            proj_fn fn = (ctx->opt_sampler == 1) ? pick_w<1>(ctx->opt_warp_w, ny_thread)
-                                                 : pick_w<0>(ctx->opt_warp_w, ny_thread);
+            dim3 grid((W + 31) / 32, (H + 7) / 8, np_l);
+            if (grid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+            proj_fn fn = (ctx->opt_sampler == 1) ? pick_kernel<1>(quad, nb, ctx->opt_warp_w, ny_l)
+                                                 : pick_kernel<0>(quad, nb, ctx->opt_warp_w, ny_l);
             fn<<<grid, kThreads, 0, s.stream>>>(P);
             ctx->launches++;
             CK(cudaGetLastError());
@@ -336,12 +355,16 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             ctx->opt_sampler = value;
             return P2P_OK;
         case P2P_OPT_WARP_W:
-            if (value != 8 && value != 16 && value != 32) return fail(ctx, P2P_ERR_INVALID, "warp_w must be 8, 16 or 32");
+            if (value != 8 && value != 32) return fail(ctx, P2P_ERR_INVALID, "warp_w must be 8 or 32");
             ctx->opt_warp_w = value;
             return P2P_OK;
         case P2P_OPT_YAWS_PER_THREAD:
             if (value < 1 || value > 4) return fail(ctx, P2P_ERR_INVALID, "yaws per thread must be 1..4");
             ctx->opt_ny = value;
+            return P2P_OK;
+        case P2P_OPT_IMAGES_PER_LAUNCH:
+            if (value != 1 && value != 2 && value != 4) return fail(ctx, P2P_ERR_INVALID, "images per launch must be 1, 2 or 4");
+            ctx->opt_nb = value;
             return P2P_OK;
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -356,6 +379,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_WARP_W: *value = ctx->opt_warp_w; return P2P_OK;
         case P2P_OPT_YAWS_PER_THREAD: *value = ctx->opt_ny; return P2P_OK;
         case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
+        case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
 }
@@ -528,7 +552,9 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
         if (rc) return rc;
         d_out = s.d_out;
     }
-    rc = launch_project(ctx, s, n_yaw, yaw_shift, n_pitch, pitch, W, H, d_out);
+    Slot *sl[1] = {&s};
+    uint8_t *outs[1] = {d_out};
+    rc = launch_project(ctx, sl, 1, n_yaw, yaw_shift, n_pitch, pitch, W, H, outs);
     if (rc) return rc;
     if (!out_on_device) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
     return P2P_OK;
@@ -538,9 +564,48 @@ int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_ya
                       int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
                       int out_on_device) {
     if (!ctx || n_images <= 0 || !slots || !outs) return fail(ctx, P2P_ERR_INVALID, "bad batch arguments");
-    for (int i = 0; i < n_images; ++i) {
-        int rc = p2p_project_views(ctx, slots[i], n_yaw, yaw_shift, n_pitch, pitch, W, H, outs[i], out_on_device);
-        if (rc) return rc;
+    int nb = 1;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        nb = ctx->opt_nb;
+    }
+    int i = 0;
+    while (i < n_images) {
+        // images that share one launch must be resident, equally sized and write to device memory
+        int g = 1;
+        if (out_on_device && nb > 1 && i + nb <= n_images && (W & 3) == 0) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            bool ok = true;
+            for (int b = 0; b < nb && ok; ++b) {
+                ok = slot_ok(ctx, slots[i + b]) && ctx->slots[slots[i + b]].valid && outs[i + b] &&
+                     (reinterpret_cast<uintptr_t>(outs[i + b]) & 3) == 0 &&
+                     ctx->slots[slots[i + b]].Wp == ctx->slots[slots[i]].Wp &&
+                     ctx->slots[slots[i + b]].Hp == ctx->slots[slots[i]].Hp;
+                for (int c = 0; c < b && ok; ++c) ok = slots[i + c] != slots[i + b];
+            }
+            if (ok) g = nb;
+        }
+        if (g == 1) {
+            int rc = p2p_project_views(ctx, slots[i], n_yaw, yaw_shift, n_pitch, pitch, W, H, outs[i], out_on_device);
+            if (rc) return rc;
+        } else {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            int rc = check_project_args(ctx, slots[i], n_yaw, yaw_shift, n_pitch, pitch, W, H, outs[i],
+                                        ctx->slots[slots[i]].Wp);
+            if (rc) return rc;
+            CK(cudaSetDevice(ctx->device));
+            Slot *sl[kMaxImagesPerLaunch];
+            uint8_t *o[kMaxImagesPerLaunch];
+            for (int b = 0; b < g; ++b) {
+                sl[b] = &ctx->slots[slots[i + b]];
+                o[b] = outs[i + b];
+                // the launch runs on the first slot's stream: the others must have finished uploading
+                if (b > 0 && sl[b]->stream != sl[0]->stream) CK(cudaStreamSynchronize(sl[b]->stream));
+            }
+            rc = launch_project(ctx, sl, g, n_yaw, yaw_shift, n_pitch, pitch, W, H, o);
+            if (rc) return rc;
+        }
+        i += g;
     }
     return P2P_OK;
 }
@@ -636,6 +701,37 @@ int p2p_flush_l2(p2p_ctx *ctx, int slot, size_t bytes) {
 }
 
 // ---- debug exports -------------------------------------------------------------------------
+int p2p_selftest(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int exhaustive_div,
+                 unsigned long long *ray_mismatches, unsigned long long *div_mismatches) {
+    if (!ctx || !pitch || W <= 0 || H <= 0 || !ray_mismatches || !div_mismatches)
+        return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaStream_t st = ctx->slots[0].stream;
+    cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        PitchC k{pitch->f, pitch->c, pitch->s};
+        dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+        selftest_ray_kernel<<<grid, block, 0, st>>>(k, W, H, (float)(W / 2.0), (float)(H / 2.0), d);
+        ctx->launches++;
+        if (exhaustive_div) {
+            selftest_constdiv_kernel<<<148 * 16, 256, 0, st>>>(d);
+            ctx->launches++;
+        }
+        e = cudaGetLastError();
+    }
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_selftest", e);
+    *ray_mismatches = h[0];
+    *div_mismatches = h[1];
+    return P2P_OK;
+}
+
 int p2p_coords(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
                float *U_host, float *V_host) {
     if (!ctx || !pitch || !U_host || !V_host || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "bad argument");

@@ -231,6 +231,13 @@ class Projector:
                                      U.ctypes.data_as(C.POINTER(C.c_float)), V.ctypes.data_as(C.POINTER(C.c_float))))
         return U, V
 
+    def selftest(self, W, H, fov_deg, pitch_deg, exhaustive_div=False):
+        """(ray_mismatches, div_mismatches) of the fast IEEE sequences vs the generic intrinsics."""
+        pc = self._consts_array([pitch_constants(W, fov_deg, pitch_deg)])
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self._ck(self.lib.p2p_selftest(self.ctx, pc, W, H, 1 if exhaustive_div else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def sample_with_maps(self, slot: int, yaw_shift: int, U: np.ndarray, V: np.ndarray) -> np.ndarray:
         U = np.ascontiguousarray(U, np.float32)
         V = np.ascontiguousarray(V, np.float32)

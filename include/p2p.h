@@ -52,9 +52,11 @@ typedef struct p2p_pitch_consts {
 /* option keys for p2p_set_option */
 typedef enum p2p_option {
     P2P_OPT_SAMPLER = 0, /* 0 = global-load gather (default), 1 = texture gather4 point fetch */
-    P2P_OPT_WARP_W = 1,  /* output pixels per warp row: 32 (default), 16 or 8 (2-D warp tiles) */
+    P2P_OPT_WARP_W = 1,  /* output pixels per warp row: 32 (default) or 8 (8 x 4 warp tiles) */
     P2P_OPT_YAWS_PER_THREAD = 2, /* 1..4 views sharing one coordinate evaluation (default 4) */
-    P2P_OPT_COUNT_LAUNCHES = 3   /* read-only via p2p_get_option: kernels launched so far */
+    P2P_OPT_COUNT_LAUNCHES = 3,  /* read-only via p2p_get_option: kernels launched so far */
+    P2P_OPT_IMAGES_PER_LAUNCH = 4 /* 1 (default), 2 or 4 resident panoramas share one launch (and one
+                                     coordinate evaluation) in p2p_project_batch */
 } p2p_option;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
@@ -136,6 +138,12 @@ int p2p_event_elapsed_ms(p2p_ctx *ctx, void *start, void *stop, float *ms); /* s
 int p2p_flush_l2(p2p_ctx *ctx, int slot, size_t bytes);
 
 /* ---- stage-isolated debug exports (parity tests) ----------------------------------------- */
+/* device self-test of the range-check-free sqrt / division sequences against the generic IEEE
+ * intrinsics: number of pixels of a W x H view whose rotated ray differs in any bit, and (if
+ * exhaustive_div) number of floats in {0} U [2^-64, 2^24) whose division by 2pi / pi differs (the
+ * kernel's numerators never leave that set). Both must be 0. */
+int p2p_selftest(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int exhaustive_div,
+                 unsigned long long *ray_mismatches, unsigned long long *div_mismatches);
 /* coordinates only: the (U, V) f32 maps of ref precompute_pitch_mapping :114-175, to host */
 int p2p_coords(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
                float *U_host, float *V_host);

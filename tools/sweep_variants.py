@@ -22,8 +22,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1])
-    ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 16, 8])
-    ap.add_argument("--nys", type=int, nargs="+", default=[4, 2, 1])
+    ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 8])
+    ap.add_argument("--nys", type=int, nargs="+", default=[4])
+    ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
     args = ap.parse_args()
     import torch
 
@@ -50,10 +51,12 @@ def main():
     ref = None
     for sampler in args.samplers:
         for ww in args.warp_ws:
-            for ny in args.nys:
+          for ny in args.nys:
+            for nb in args.nbs:
                 proj.set_option(L.OPT_SAMPLER, sampler)
                 proj.set_option(L.OPT_WARP_W, ww)
                 proj.set_option(L.OPT_YAWS_PER_THREAD, ny)
+                proj.set_option(L.OPT_IMAGES_PER_LAUNCH, nb)
                 for _ in range(3):
                     step()
                 proj.sync(0)
@@ -66,7 +69,7 @@ def main():
                 torch.cuda.synchronize()
                 chk = int(d_out[0].to(torch.int64).sum().item())
                 ref = chk if ref is None else ref
-                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "launch_us": ms * 1e3,
+                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "image_us": ms * 1e3,
                                   "gpix_s": bench.PX_PER_IMAGE / (ms * 1e-3) / 1e9,
                                   "roofline_frac": bench.B_ALG_PER_IMAGE / (ms * 1e-3) / 1e9 / bench.read_peaks()[0],
                                   "same_output": chk == ref}), flush=True)
