@@ -43,10 +43,11 @@ struct p2p_ctx {
     Slot *slots = nullptr;
     std::mutex mu;
     std::string err;
-    int opt_sampler = 0;
+    int opt_sampler = 1;
     int opt_warp_w = 32;
     int opt_ny = 4;
     int opt_nb = 1;
+    int opt_mirror = 1;
     long long launches = 0;
     uint4 *d_flush = nullptr;
     size_t flush_cap = 0;
@@ -124,7 +125,7 @@ int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride) {
 // (re)build the gather texture of a slot from its packed panorama
 int ensure_texture(p2p_ctx *ctx, Slot &s) {
     if (s.tex_current) return P2P_OK;
-    const int aw = s.Wp + 1, ah = s.Hp + 1;
+    const int aw = s.Wp, ah = s.Hp;  // wrap in x / clamp in y replace the duplicated column and row
     if (!s.arr || s.arrW != aw || s.arrH != ah) {
         if (s.tex) {
             CK(cudaDestroyTextureObject(s.tex));
@@ -144,10 +145,11 @@ int ensure_texture(p2p_ctx *ctx, Slot &s) {
         rd.res.array.array = s.arr;
         cudaTextureDesc td;
         memset(&td, 0, sizeof(td));
-        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.addressMode[0] = cudaAddressModeWrap;
+        td.addressMode[1] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModePoint;
         td.readMode = cudaReadModeElementType;
-        td.normalizedCoords = 0;
+        td.normalizedCoords = 1;
         CK(cudaCreateTextureObject(&s.tex, &rd, &td, nullptr));
     }
     CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.d_rgba, (size_t)s.pitch_tex * 4, (size_t)aw * 4, ah,
@@ -189,13 +191,16 @@ proj_fn pick_kernel(bool quad, int nb, int warp_w, int ny) {
 int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                    const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *d_out) {
     Slot &s = *sl[0];
-    if (ctx->opt_sampler == 1) {
+    if (ctx->opt_sampler != 0) {
         for (int b = 0; b < nb; ++b) {
             int rc = ensure_texture(ctx, *sl[b]);
             if (rc) return rc;
         }
     }
-    const int ny_max = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
+    int ny_max = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
+    // the kernel adds k * yaw_stride as a 32-bit offset: fall back to fewer yaws per launch for huge outputs
+    const unsigned long long ys = (unsigned long long)W * H * 3 * (unsigned long long)n_pitch;
+    while (ny_max > 1 && (unsigned long long)(ny_max - 1) * ys >= (1ull << 32)) --ny_max;
     ProjParams P;
     memset(&P, 0, sizeof(P));
     bool aligned = true;
@@ -207,6 +212,7 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
     }
     P.view_stride = (unsigned long long)W * H * 3;
     P.yaw_stride = P.view_stride * (unsigned long long)n_pitch;
+    P.yaw_stride32 = (ny_max > 1) ? (unsigned)P.yaw_stride : 0u;
     P.pitch_tex = s.pitch_tex;
     P.Wp = s.Wp;
     P.Hp = s.Hp;
@@ -218,6 +224,8 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
     P.Hp_f = (float)s.Hp;
     P.Umax = (float)(s.Wp - 1);
     P.Vmax = (float)(s.Hp - 1);
+    P.inv_Wp = (float)(1.0 / (double)s.Wp);
+    P.inv_Hp = (float)(1.0 / (double)s.Hp);
     const bool quad = ((W & 3) == 0) && aligned;
     if (!quad && nb > 1) return fail(ctx, P2P_ERR_INVALID, "multi-image launches need W % 4 == 0 and aligned outputs");
     // chunk over yaws (<= 4 share one coordinate evaluation) and pitches (grid.z) so any list length works
@@ -225,7 +233,7 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
         const int ny_l = (n_yaw - y0 < ny_max) ? n_yaw - y0 : ny_max;
         for (int k = 0; k < 4; ++k) {
             P.shift[k] = (k < ny_l) ? yaw_shift[y0 + k] : 0;
-            P.shift_p1_f[k] = (float)(P.shift[k] + 1);
+            P.shift_n[k] = (float)((double)P.shift[k] / (double)s.Wp);
         }
         P.yaw_off = y0;
         for (int p0 = 0; p0 < n_pitch; p0 += kMaxPitchPerLaunch) {
@@ -237,10 +245,25 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
                 P.pc[j].c = pitch[p0 + j].c;
                 P.pc[j].s = pitch[p0 + j].s;
             }
+            // mirror-symmetric kernel: texture sampler, one image per launch, vector-store friendly sizes
+            if (ctx->opt_mirror && ctx->opt_sampler == 1 && nb == 1 && quad && (W & 7) == 0) {
+                dim3 mgrid((W / 2 + 1 + 31) / 32, (H + 7) / 8, np_l);
+                if (mgrid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+                switch (ny_l) {
+                    case 1: project_mirror_kernel<1><<<mgrid, kThreads, 0, s.stream>>>(P); break;
+                    case 2: project_mirror_kernel<2><<<mgrid, kThreads, 0, s.stream>>>(P); break;
+                    case 3: project_mirror_kernel<3><<<mgrid, kThreads, 0, s.stream>>>(P); break;
+                    default: project_mirror_kernel<4><<<mgrid, kThreads, 0, s.stream>>>(P); break;
+                }
+                ctx->launches++;
+                CK(cudaGetLastError());
+                continue;
+            }
             dim3 grid((W + 31) / 32, (H + 7) / 8, np_l);
             if (grid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
-            proj_fn fn = (ctx->opt_sampler == 1) ? pick_kernel<1>(quad, nb, ctx->opt_warp_w, ny_l)
-                                                 : pick_kernel<0>(quad, nb, ctx->opt_warp_w, ny_l);
+            proj_fn fn = (ctx->opt_sampler == 1)   ? pick_kernel<1>(quad, nb, ctx->opt_warp_w, ny_l)
+                         : (ctx->opt_sampler == 2) ? pick_kernel<2>(quad, nb, ctx->opt_warp_w, ny_l)
+                                                   : pick_kernel<0>(quad, nb, ctx->opt_warp_w, ny_l);
             fn<<<grid, kThreads, 0, s.stream>>>(P);
             ctx->launches++;
             CK(cudaGetLastError());
@@ -351,7 +374,7 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     switch (key) {
         case P2P_OPT_SAMPLER:
-            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "sampler must be 0 or 1");
+            if (value < 0 || value > 2) return fail(ctx, P2P_ERR_INVALID, "sampler must be 0, 1 or 2");
             ctx->opt_sampler = value;
             return P2P_OK;
         case P2P_OPT_WARP_W:
@@ -365,6 +388,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
         case P2P_OPT_IMAGES_PER_LAUNCH:
             if (value != 1 && value != 2 && value != 4) return fail(ctx, P2P_ERR_INVALID, "images per launch must be 1, 2 or 4");
             ctx->opt_nb = value;
+            return P2P_OK;
+        case P2P_OPT_MIRROR:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "mirror must be 0 or 1");
+            ctx->opt_mirror = value;
             return P2P_OK;
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -380,6 +407,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_YAWS_PER_THREAD: *value = ctx->opt_ny; return P2P_OK;
         case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
         case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
+        case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
 }

@@ -250,6 +250,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         proj.set_option(L.OPT_WARP_W, args.warp_w)
     if args.ny is not None:
         proj.set_option(L.OPT_YAWS_PER_THREAD, args.ny)
+    if args.nb is not None:
+        proj.set_option(L.OPT_IMAGES_PER_LAUNCH, args.nb)
 
     consts = [pkg.pitch_constants(W, FOV, p) for p in PITCHES]
     shifts = [pkg.yaw_table(WP, y)[2] for y in YAWS]
@@ -349,6 +351,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             "config": workload_config({
                 "sampler": proj.get_option(L.OPT_SAMPLER), "warp_w": proj.get_option(L.OPT_WARP_W),
                 "yaws_per_thread": proj.get_option(L.OPT_YAWS_PER_THREAD),
+                "images_per_launch": proj.get_option(L.OPT_IMAGES_PER_LAUNCH),
                 "distinct_seeds_per_gpu": n_distinct,
             }),
             "roofline": {
@@ -381,6 +384,7 @@ def main():
     ap.add_argument("--sampler", type=int, default=None)
     ap.add_argument("--warp-w", type=int, default=None)
     ap.add_argument("--ny", type=int, default=None)
+    ap.add_argument("--nb", type=int, default=None, help="resident panoramas per launch (1, 2, 4)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct noise seeds per GPU (others are rolled copies)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap on end-to-end steps (each moves 5.6 GB over PCIe)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

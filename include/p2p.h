@@ -51,12 +51,16 @@ typedef struct p2p_pitch_consts {
 
 /* option keys for p2p_set_option */
 typedef enum p2p_option {
-    P2P_OPT_SAMPLER = 0, /* 0 = global-load gather (default), 1 = texture gather4 point fetch */
+    P2P_OPT_SAMPLER = 0, /* 0 = global-load gather, 1 = texture gather4 point fetch (default), 2 = both,
+                            alternating between the yaws of a launch */
     P2P_OPT_WARP_W = 1,  /* output pixels per warp row: 32 (default) or 8 (8 x 4 warp tiles) */
     P2P_OPT_YAWS_PER_THREAD = 2, /* 1..4 views sharing one coordinate evaluation (default 4) */
     P2P_OPT_COUNT_LAUNCHES = 3,  /* read-only via p2p_get_option: kernels launched so far */
-    P2P_OPT_IMAGES_PER_LAUNCH = 4 /* 1 (default), 2 or 4 resident panoramas share one launch (and one
+    P2P_OPT_IMAGES_PER_LAUNCH = 4, /* 1 (default), 2 or 4 resident panoramas share one launch (and one
                                      coordinate evaluation) in p2p_project_batch */
+    P2P_OPT_MIRROR = 5            /* 1 (default): with the texture sampler and W % 8 == 0, the pixel pair
+                                     (W/2 + t, W/2 - t) shares one coordinate evaluation; 0: every pixel
+                                     evaluates its own */
 } p2p_option;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -234,9 +234,10 @@ def test_kernel_variants_identical(pkg, proj):
     Wp, Hp, W, H, fov = 2048, 1024, 480, 272, 120
     pano = synth.noise(Wp, Hp, 4)
     yaws, pitches = [0, 90, 180, 270, 45 * 0], [30, 60, 90]
+    proj.set_option(L.OPT_MIRROR, 0)
     base = proj.project_image(pano, yaws, pitches, W, H, fov).copy()
     try:
-        for sampler in (0, 1):
+        for sampler in (0, 1, 2):
             for warp_w in (32, 8):
                 for ny in (1, 2, 3, 4):
                     proj.set_option(L.OPT_SAMPLER, sampler)
@@ -246,15 +247,49 @@ def test_kernel_variants_identical(pkg, proj):
                     assert np.array_equal(got, base), (sampler, warp_w, ny)
         # odd output sizes take the byte-store path
         odd = None
-        for sampler in (0, 1):
+        for sampler in (0, 1, 2):
             proj.set_option(L.OPT_SAMPLER, sampler)
             got = proj.project_image(pano, [0, 90], [60], 333, 201, 100)
             odd = got.copy() if odd is None else odd
             assert np.array_equal(got, odd)
     finally:
-        proj.set_option(L.OPT_SAMPLER, 0)
+        proj.set_option(L.OPT_SAMPLER, 1)
         proj.set_option(L.OPT_WARP_W, 32)
         proj.set_option(L.OPT_YAWS_PER_THREAD, 4)
+        proj.set_option(L.OPT_MIRROR, 1)
+
+
+def test_mirror_kernel_against_per_pixel_kernel_and_oracle(pkg, proj):
+    """The mirror-symmetric kernel (default) derives the left-half azimuth as pi - a.  Its direct
+    half must equal the per-pixel kernel bit for bit; the derived half may differ from it only
+    where a last-ulp azimuth difference flips a 1/32-px bin, and must meet the same gates against
+    the oracle as every other path."""
+    L = pkg._lib
+    for (Wp, Hp, W, H, fov, yaws, pitches) in [
+        (2048, 1024, 480, 272, 120, [0, 90, 180, 270], [30, 60, 90]),
+        (2048, 1024, 64, 40, 90, [0], [90]),            # single tile
+        (2048, 1024, 72, 9, 90, [180], [45]),           # W % 8 == 0 but not % 16
+        (2048, 1024, 160, 7, 100, [90, 270, 45], [1, 179, 120]),  # partial row tile, 3 yaws (one fractional)
+        (4096, 2048, 2048, 2048, 90, [0, 90], [0, 180]),  # pole faces
+    ]:
+        noise = synth.noise(Wp, Hp, 9)
+        smooth = synth.smooth(Wp, Hp, 9)
+        try:
+            proj.set_option(L.OPT_MIRROR, 0)
+            ref_n = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+        finally:
+            proj.set_option(L.OPT_MIRROR, 1)
+        got_n = proj.project_image(noise, yaws, pitches, W, H, fov)
+        assert np.array_equal(got_n[..., W // 2:, :], ref_n[..., W // 2:, :]), "direct half differs"
+        left = exact_fraction(got_n[..., :W // 2, :], ref_n[..., :W // 2, :])
+        assert left >= 0.97, left
+        got_s = proj.project_image(smooth, yaws, pitches, W, H, fov)
+        for i, y in enumerate(yaws):
+            for j, p in enumerate(pitches):
+                want = fp.project_view_single_pass(noise, y, p, W, H, fov)
+                assert exact_fraction(got_n[i, j], want) >= NOISE_EXACT_MIN, (Wp, W, y, p)
+                want_s = fp.project_view_single_pass(smooth, y, p, W, H, fov)
+                assert np.abs(got_s[i, j].astype(np.int16) - want_s.astype(np.int16)).max() <= 1, (Wp, W, y, p)
 
 
 def test_fast_ieee_sequences_match_intrinsics(proj):
@@ -276,6 +311,7 @@ def test_multi_image_launch_matches_single(pkg, proj):
     yaws, pitches = [0, 90, 180, 270], [30, 60, 90]
     n = 4
     panos = [synth.noise(Wp, Hp, 20 + i) for i in range(n)]
+    proj.set_option(L.OPT_MIRROR, 0)
     want = [proj.project_image(p, yaws, pitches, W, H, fov) for p in panos]
     consts = [pkg.pitch_constants(W, fov, p) for p in pitches]
     shifts = [pkg.yaw_table(Wp, y)[2] for y in yaws]
@@ -285,7 +321,7 @@ def test_multi_image_launch_matches_single(pkg, proj):
             proj.upload(s, p)
             proj.sync(s)
         try:
-            for sampler in (0, 1):
+            for sampler in (0, 1, 2):
                 for nb in (1, 2, 4):
                     proj.set_option(L.OPT_SAMPLER, sampler)
                     proj.set_option(L.OPT_IMAGES_PER_LAUNCH, nb)
@@ -297,8 +333,9 @@ def test_multi_image_launch_matches_single(pkg, proj):
                     for i in range(n):
                         assert np.array_equal(res[i], want[i]), (sampler, nb, i)
         finally:
-            proj.set_option(L.OPT_SAMPLER, 0)
+            proj.set_option(L.OPT_SAMPLER, 1)
             proj.set_option(L.OPT_IMAGES_PER_LAUNCH, 1)
+            proj.set_option(L.OPT_MIRROR, 1)
 
 
 def test_many_yaws_and_pitches_chunking(proj):

@@ -21,10 +21,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1, 2])
     ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 8])
     ap.add_argument("--nys", type=int, nargs="+", default=[4])
     ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
+    ap.add_argument("--mirrors", type=int, nargs="+", default=[0, 1])
     args = ap.parse_args()
     import torch
 
@@ -52,7 +53,11 @@ def main():
     for sampler in args.samplers:
         for ww in args.warp_ws:
           for ny in args.nys:
-            for nb in args.nbs:
+           for nb in args.nbs:
+            for mirror in args.mirrors:
+                if mirror and (sampler != 1 or nb != 1):
+                    continue
+                proj.set_option(L.OPT_MIRROR, mirror)
                 proj.set_option(L.OPT_SAMPLER, sampler)
                 proj.set_option(L.OPT_WARP_W, ww)
                 proj.set_option(L.OPT_YAWS_PER_THREAD, ny)
@@ -68,8 +73,8 @@ def main():
                 ms = proj.elapsed_ms(ev0, ev1) / (args.steps * args.batch)
                 torch.cuda.synchronize()
                 chk = int(d_out[0].to(torch.int64).sum().item())
-                ref = chk if ref is None else ref
-                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "image_us": ms * 1e3,
+                ref = chk if ref is None else ref  # (the mirror kernel legitimately differs in a few pixels)
+                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "mirror": mirror, "image_us": ms * 1e3,
                                   "gpix_s": bench.PX_PER_IMAGE / (ms * 1e-3) / 1e9,
                                   "roofline_frac": bench.B_ALG_PER_IMAGE / (ms * 1e-3) / 1e9 / bench.read_peaks()[0],
                                   "same_output": chk == ref}), flush=True)
