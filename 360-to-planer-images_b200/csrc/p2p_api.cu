@@ -393,6 +393,7 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "mirror must be 0 or 1");
             ctx->opt_mirror = value;
             return P2P_OK;
+
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
@@ -408,6 +409,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
         case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
+
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
 }

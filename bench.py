@@ -221,25 +221,12 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     g.build()
     pkg = g.load_package()
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+    from p2p_b200 import distrib
 
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    ranks = distrib.Ranks("nccl", device=dev)  # no-op when WORLD_SIZE == 1
+    barrier, max_over_ranks = ranks.barrier, ranks.max
 
     n_e2e_slots = 4
     proj = pkg.Projector(local_rank, n_slots=BATCH + n_e2e_slots)
@@ -371,8 +358,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     for b in pin_in + pin_out:
         b.free()
     proj.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def main():

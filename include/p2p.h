@@ -61,6 +61,7 @@ typedef enum p2p_option {
     P2P_OPT_MIRROR = 5            /* 1 (default): with the texture sampler and W % 8 == 0, the pixel pair
                                      (W/2 + t, W/2 - t) shares one coordinate evaluation; 0: every pixel
                                      evaluates its own */
+
 } p2p_option;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -26,9 +26,12 @@ def main():
     ap.add_argument("--nys", type=int, nargs="+", default=[4])
     ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
     ap.add_argument("--mirrors", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--fov", type=int, default=None, help="override the FOV (locality experiments)")
     args = ap.parse_args()
     import torch
 
+    if args.fov is not None:
+        bench.FOV = args.fov
     g.build()
     pkg = g.load_package()
     L = pkg._lib
