@@ -19,6 +19,8 @@ class Ranks:
             import torch.distributed as dist
 
             if not dist.is_initialized():
+                # keep stdout clean for the one JSON line: NCCL's banner / debug output goes to stderr
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
                 kw = {}
                 if backend == "nccl" and device is not None:
                     kw["device_id"] = device
