@@ -24,6 +24,7 @@ from .panorama_to_plane_pitch import (  # noqa: E402
     main,
     panorama_to_plane,
     pitch_mapping_cache,
+    process_image_batch,
     process_single_image,
     process_yaw_and_pitchs,
     set_device,
@@ -32,6 +33,6 @@ from .panorama_to_plane_pitch import (  # noqa: E402
 from ._lib import P2PError, PitchConsts  # noqa: E402
 
 __all__ = [
-    "panorama_to_plane", "process_yaw_and_pitchs", "process_single_image", "main", "check_pitch",
+    "panorama_to_plane", "process_yaw_and_pitchs", "process_single_image", "process_image_batch", "main", "check_pitch",
     "get_version", "cli", "Projector", "PinnedBuffer", "pitch_constants", "yaw_table", "P2PError",
 ]

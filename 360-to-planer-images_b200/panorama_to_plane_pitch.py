@@ -141,17 +141,9 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
             logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
         return
 
-    def save_yaw(k):
-        yaw_angle = yaw_angles[k]
-        for i in range(len(pitch_angles)):
-            out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angle}"
-                            f"_pitch_{pitch_angles[i]}.{output_format}")
-            output_file = output_dir / out_filename
-            cv2.imwrite(str(output_file), views[k, i])
-            logging.debug(f"Saved {output_file}")
-
     with ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
-        tasks = [executor.submit(save_yaw, k) for k in range(len(yaw_angles))]
+        tasks = _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width,
+                            output_height, output_format, executor)
         for future, yaw_angle in zip(tasks, yaw_angles):
             try:
                 future.result()
@@ -159,8 +151,132 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
                 logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
 
 
+def _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
+                output_format, executor):
+    """Submit one encode task per yaw (reference file names, ref :275); returns the futures."""
+
+    def save_yaw(k):
+        for i in range(len(pitch_angles)):
+            out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angles[k]}"
+                            f"_pitch_{pitch_angles[i]}.{output_format}")
+            cv2.imwrite(str(output_dir / out_filename), views[k, i])
+            logging.debug(f"Saved {output_dir / out_filename}")
+
+    return [executor.submit(save_yaw, k) for k in range(len(yaw_angles))]
+
+
+def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, output_width, output_height,
+                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=3):
+    """Directory front end (ref ``main`` :320-341 processes the files one after the other).
+
+    Same files and names out as calling ``process_single_image`` per file, but pipelined: decoder
+    threads read ahead, every image is uploaded / projected / read back asynchronously on its own
+    slot (stream), and encoder threads write the previous images while the next ones are in flight.
+    ``devices`` shards the files round-robin over several GPUs (one pipeline per device, no data
+    exchange).  Images that need a fractional yaw take the synchronous path.
+    """
+    import cv2
+
+    image_files = [Path(f) for f in image_files]
+    output_dir = Path(output_dir)
+    yaw_angles, pitch_angles = list(yaw_angles), list(pitch_angles)
+    devices = [_default_device] if not devices else [int(d) for d in devices]
+    num_workers = max(1, int(num_workers))
+    W, H = int(output_width), int(output_height)
+
+    def run_device(dev, files):
+        from collections import deque
+
+        proj = get_projector(dev)
+        n_in = max(1, min(int(inflight), proj.n_slots - 1))
+        out_bufs = [_engine.PinnedBuffer((len(yaw_angles), len(pitch_angles), H, W, 3)) for _ in range(n_in)]
+        free_bufs = deque(range(n_in))
+        pending = deque()  # (slot_ctx, slot, buf_index, pano, base_name)
+        with ThreadPoolExecutor(max_workers=num_workers) as readers, \
+                ThreadPoolExecutor(max_workers=num_workers) as writers:
+            ahead = deque()
+            it = iter(files)
+
+            def refill():
+                while len(ahead) < n_in + 1:
+                    f = next(it, None)
+                    if f is None:
+                        return
+                    logging.info(f"Loading image: {f}")
+                    ahead.append((f, readers.submit(cv2.imread, str(f))))
+
+            def retire():
+                cm, slot, bi, _pano, base, futs_in = pending.popleft()
+                try:
+                    proj.sync(slot)
+                    futs = _save_views(cv2, out_bufs[bi].array, base, output_dir, yaw_angles, pitch_angles, W, H,
+                                       output_format, writers)
+                    for fut, yaw in zip(futs, yaw_angles):
+                        try:
+                            fut.result()  # the pinned buffer is reused afterwards
+                        except Exception as e:
+                            logging.error(f"Error processing yaw_angle {yaw}: {e}")
+                except Exception as e:
+                    for yaw in yaw_angles:
+                        logging.error(f"Error processing yaw_angle {yaw}: {e}")
+                finally:
+                    cm.__exit__(None, None, None)
+                    free_bufs.append(bi)
+
+            refill()
+            while ahead:
+                f, fut = ahead.popleft()
+                refill()
+                pano = fut.result()
+                if pano is None:
+                    logging.error(f"Failed to read image: {f}")
+                    continue
+                try:
+                    pano = _engine._as_u8_image(pano, "input image")
+                    Hp, Wp, _ = pano.shape
+                    consts = [get_pitch_mapping(W, H, p, Wp, Hp, fov_deg) for p in pitch_angles]
+                    tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
+                    if any(t[2] is None for t in tables):  # fractional yaw: synchronous two-stage path
+                        views = proj.project_image(pano, yaw_angles, pitch_angles, W, H, fov_deg,
+                                                   consts=consts, tables=tables)
+                        for fut2, yaw in zip(_save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles,
+                                                         W, H, output_format, writers), yaw_angles):
+                            try:
+                                fut2.result()
+                            except Exception as e:
+                                logging.error(f"Error processing yaw_angle {yaw}: {e}")
+                        continue
+                    while not free_bufs:
+                        retire()
+                    bi = free_bufs.popleft()
+                    cm = proj.slots(1)
+                    (slot,) = cm.__enter__()
+                    proj.process_image(slot, pano, [t[2] for t in tables], consts, W, H, out_bufs[bi].array)
+                    pending.append((cm, slot, bi, pano, f.stem, None))
+                except Exception as e:
+                    for yaw in yaw_angles:
+                        logging.error(f"Error processing yaw_angle {yaw}: {e}")
+            while pending:
+                retire()
+        for b in out_bufs:
+            b.free()
+
+    if not yaw_angles or not pitch_angles:
+        return
+    if len(devices) == 1:
+        run_device(devices[0], image_files)
+    else:
+        from . import shard
+
+        with ThreadPoolExecutor(max_workers=len(devices)) as ex:
+            futs = [ex.submit(run_device, d, [image_files[i] for i in shard.shard_images(len(image_files), r, len(devices))])
+                    for r, d in enumerate(devices)]
+            for fu in futs:
+                fu.result()
+
+
 def main(input_path, output_path, yaw_angles, pitch_angles, output_width, output_height,
-         num_workers=None, output_format="png", fov_deg=90, enable_file_logging=False):
+         num_workers=None, output_format="png", fov_deg=90, enable_file_logging=False, devices=None):
     """Process a single image or every image under a folder (ref :286-356)."""
     if num_workers is None:
         cpu_cores = os.cpu_count() or 1
@@ -183,12 +299,15 @@ def main(input_path, output_path, yaw_angles, pitch_angles, output_width, output
         logging.info(f"Found {len(all_images)} images in folder: {input_path_obj}")
     else:
         all_images = [input_path_obj]
-    for image_file in all_images:
+    if len(all_images) == 1 and not devices:
         process_single_image(
-            input_image_path=image_file, output_dir=output_dir, yaw_angles=yaw_angles,
+            input_image_path=all_images[0], output_dir=output_dir, yaw_angles=yaw_angles,
             pitch_angles=pitch_angles, output_width=output_width, output_height=output_height,
             num_workers=num_workers, output_format=output_format, fov_deg=fov_deg,
         )
+    else:
+        process_image_batch(all_images, output_dir, yaw_angles, pitch_angles, output_width, output_height,
+                            num_workers=num_workers, output_format=output_format, fov_deg=fov_deg, devices=devices)
     logging.info("All processing completed.")
 
 
@@ -223,6 +342,8 @@ def build_parser() -> argparse.ArgumentParser:
                    help="Number of worker threads (file encoders here). If not specified, uses ~90%% of CPU cores.")
     p.add_argument("--enable_file_logging", action="store_true", help="Enable logging to a file.")
     p.add_argument("--device", type=int, default=0, help="CUDA device index (extra flag; default 0)")
+    p.add_argument("--devices", type=int, nargs="+", default=None,
+                   help="several CUDA devices: the files of a folder are sharded round-robin (extra flag)")
     p.add_argument("-v", "--version", action="version", version=f"%(prog)s {get_version()}",
                    help="Show version information")
     return p
@@ -241,7 +362,7 @@ def cli(argv=None):
         input_path=args.input_path, output_path=args.output_path, yaw_angles=args.yaw_angles,
         pitch_angles=args.pitch_angles, output_width=args.output_width, output_height=args.output_height,
         num_workers=args.num_workers, output_format=args.output_format, fov_deg=args.FOV,
-        enable_file_logging=args.enable_file_logging,
+        enable_file_logging=args.enable_file_logging, devices=args.devices,
     )
 
 

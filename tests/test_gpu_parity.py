@@ -465,6 +465,42 @@ def test_dropin_files_and_front_door(pkg, tmp_path):
     assert np.array_equal(one, got)
 
 
+def test_directory_pipeline_matches_single_image_path(pkg, tmp_path, caplog):
+    """``main`` on a folder runs the pipelined front end (decode ahead, async slots, encoder threads):
+    same files, names and pixels as ``process_single_image`` per file; unreadable files are logged."""
+    import logging
+
+    cv2 = pytest.importorskip("cv2")
+    src = tmp_path / "in"
+    (src / "sub").mkdir(parents=True)
+    sizes = [(1024, 512), (1024, 512), (2048, 1024), (1000, 500), (1024, 512)]
+    for i, (Wp, Hp) in enumerate(sizes):
+        name = src / ("sub" if i % 2 else "") / f"p{i}.{'jpg' if i == 3 else 'png'}"
+        assert cv2.imwrite(str(name), synth.smooth(Wp, Hp, i))
+    (src / "broken.png").write_bytes(b"not an image")
+    (src / "notes.txt").write_text("ignored")
+    W, H, fov, yaws, pitches = 200, 120, 100, [0, 90, 30], [60, 120]   # yaw 30 is fractional on Wp = 1000 / 1024
+    out_a, out_b = tmp_path / "a", tmp_path / "b"
+    with caplog.at_level(logging.ERROR):
+        pkg.main(str(src), str(out_a), yaws, pitches, W, H, num_workers=3, fov_deg=fov)
+    assert any("Failed to read image" in r.message and "broken.png" in r.message for r in caplog.records)
+    out_b.mkdir()
+    files = [f for f in src.rglob("*") if f.suffix.lower() in {".jpg", ".jpeg", ".png"} and f.name != "broken.png"]
+    for f in files:
+        pkg.process_single_image(f, out_b, yaws, pitches, W, H, num_workers=2, fov_deg=fov)
+    names_a, names_b = sorted(p.name for p in out_a.iterdir()), sorted(p.name for p in out_b.iterdir())
+    assert names_a == names_b and len(names_a) == len(files) * len(yaws) * len(pitches)
+    for n in names_a:
+        assert np.array_equal(cv2.imread(str(out_a / n)), cv2.imread(str(out_b / n))), n
+    # the CLI front door with the reference's flags
+    out_c = tmp_path / "c"
+    pkg.cli(["--input_path", str(src / "p0.png"), "--output_path", str(out_c), "--FOV", str(fov), "--output_width",
+             str(W), "--output_height", str(H), "--yaw_angles", "0", "90", "--pitch_angles", "60", "--num_workers", "2"])
+    assert sorted(p.name for p in out_c.iterdir()) == [f"p0_{W}x{H}_yaw_0_pitch_60.png", f"p0_{W}x{H}_yaw_90_pitch_60.png"]
+    assert np.array_equal(cv2.imread(str(out_c / f"p0_{W}x{H}_yaw_90_pitch_60.png")),
+                          cv2.imread(str(out_a / f"p0_{W}x{H}_yaw_90_pitch_60.png")))
+
+
 # ------------------------------------------------------------------------------------------
 # error behaviour of the C ABI
 # ------------------------------------------------------------------------------------------
