@@ -48,6 +48,7 @@ struct p2p_ctx {
     int opt_ny = 4;
     int opt_nb = 1;
     int opt_mirror = 1;
+    int opt_interp = 0;
     long long launches = 0;
     uint4 *d_flush = nullptr;
     size_t flush_cap = 0;
@@ -191,7 +192,7 @@ proj_fn pick_kernel(bool quad, int nb, int warp_w, int ny) {
 int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                    const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *d_out) {
     Slot &s = *sl[0];
-    if (ctx->opt_sampler != 0) {
+    if (ctx->opt_sampler != 0 && ctx->opt_interp == 0) {
         for (int b = 0; b < nb; ++b) {
             int rc = ensure_texture(ctx, *sl[b]);
             if (rc) return rc;
@@ -244,6 +245,20 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
                 P.pc[j].f = pitch[p0 + j].f;
                 P.pc[j].c = pitch[p0 + j].c;
                 P.pc[j].s = pitch[p0 + j].s;
+            }
+            if (ctx->opt_interp == 1) {  // exact-bilinear mode (scipy map_coordinates order=1 arithmetic)
+                if (nb != 1) return fail(ctx, P2P_ERR_INVALID, "exact interpolation mode renders one image per launch");
+                dim3 egrid((W + 31) / 32, (H + 7) / 8, np_l);
+                if (egrid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+                switch (ny_l) {
+                    case 1: project_exact_kernel<1><<<egrid, kThreads, 0, s.stream>>>(P); break;
+                    case 2: project_exact_kernel<2><<<egrid, kThreads, 0, s.stream>>>(P); break;
+                    case 3: project_exact_kernel<3><<<egrid, kThreads, 0, s.stream>>>(P); break;
+                    default: project_exact_kernel<4><<<egrid, kThreads, 0, s.stream>>>(P); break;
+                }
+                ctx->launches++;
+                CK(cudaGetLastError());
+                continue;
             }
             // mirror-symmetric kernel: texture sampler, one image per launch, vector-store friendly sizes
             if (ctx->opt_mirror && ctx->opt_sampler == 1 && nb == 1 && quad && (W & 7) == 0) {
@@ -393,6 +408,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "mirror must be 0 or 1");
             ctx->opt_mirror = value;
             return P2P_OK;
+        case P2P_OPT_INTERP:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "interp must be 0 (cv2 fixed point) or 1 (exact bilinear)");
+            ctx->opt_interp = value;
+            return P2P_OK;
 
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -409,6 +428,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
         case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
+        case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
 
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
@@ -545,6 +565,8 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
     Slot &a = ctx->slots[src_slot];
     Slot &d = ctx->slots[dst_slot];
     if (!a.valid) return fail(ctx, P2P_ERR_STATE, "source slot holds no panorama");
+    if (ctx->opt_interp != 0)
+        return fail(ctx, P2P_ERR_INVALID, "fractional yaws are only defined for the cv2 fixed-point interpolation mode");
     for (int u = 0; u < a.Wp; ++u)
         if (ix[u] < 0 || ix[u] >= a.Wp || fx[u] < 0 || fx[u] > 31) return fail(ctx, P2P_ERR_INVALID, "yaw table entry out of range");
     int rc = prepare_slot(ctx, d, a.Wp, a.Hp);
@@ -805,7 +827,8 @@ int p2p_sample_with_maps(p2p_ctx *ctx, int slot, int yaw_shift, const float *U_h
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, V_host, n * sizeof(float), cudaMemcpyHostToDevice, s.stream);
     if (e == cudaSuccess) {
         dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
-        sample_maps_kernel<<<grid, block, 0, s.stream>>>(s.d_rgba, s.pitch_tex, s.Wp, s.Hp, yaw_shift, d, d + n, W, H, d_o);
+        sample_maps_kernel<<<grid, block, 0, s.stream>>>(s.d_rgba, s.pitch_tex, s.Wp, s.Hp, yaw_shift, d, d + n, W, H, d_o,
+                                                        ctx->opt_interp);
         ctx->launches++;
         e = cudaGetLastError();
     }

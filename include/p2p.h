@@ -61,6 +61,10 @@ typedef enum p2p_option {
     P2P_OPT_MIRROR = 5            /* 1 (default): with the texture sampler and W % 8 == 0, the pixel pair
                                      (W/2 + t, W/2 - t) shares one coordinate evaluation; 0: every pixel
                                      evaluates its own */
+    ,P2P_OPT_INTERP = 6            /* 0 (default): cv2.remap fixed-point bilinear, the reference's arithmetic
+                                     (ref :192-199, :212-218); 1: exact bilinear - un-quantised fractions with the
+                                     arithmetic of scipy.ndimage.map_coordinates(order=1) (double precision, round
+                                     half up); integer-roll yaws only */
 
 } p2p_option;
 

@@ -292,6 +292,55 @@ def test_mirror_kernel_against_per_pixel_kernel_and_oracle(pkg, proj):
                 assert np.abs(got_s[i, j].astype(np.int16) - want_s.astype(np.int16)).max() <= 1, (Wp, W, y, p)
 
 
+def test_exact_bilinear_mode_against_scipy(pkg):
+    """Optional interpolation mode 1: bit-exact against scipy.ndimage.map_coordinates
+    (order=1) with injected maps; end to end <= 1 LSB against scipy on the reference's maps."""
+    pytest.importorskip("scipy")
+    from oracle import exact_bilinear as eb
+
+    L = pkg._lib
+    p = pkg.Projector(0, n_slots=2)
+    try:
+        p.set_option(L.OPT_INTERP, 1)
+        rng = np.random.default_rng(8)
+        Wp, Hp, W, H = 257, 129, 333, 201
+        pano = synth.noise(Wp, Hp, 3)
+        U = rng.uniform(0, Wp - 1, (H, W)).astype(np.float32)
+        V = rng.uniform(0, Hp - 1, (H, W)).astype(np.float32)
+        U[0, :] = Wp - 1
+        V[1, :] = Hp - 1
+        U[2, :8] = np.arange(8) + 0.5   # exact halves: round half up
+        V[2, :8] = np.arange(8) + 0.5
+        U[3, 5] = np.nan
+        with p.slots(1) as (s,):
+            p.upload(s, pano)
+            for shift in (0, 7, Wp - 1):
+                assert np.array_equal(p.sample_with_maps(s, shift, U, V), eb.sample_view_exact(pano, U, V, shift)), shift
+        # end to end on the scaled README example
+        Wp, Hp, W, H, fov = 1024, 512, 240, 136, 120
+        yaws, pitches = [0, 90, 180, 270, 90], [30, 60, 90]
+        for kind in ("noise", "smooth"):
+            pano = synth.make(kind, Wp, Hp, 0)
+            out = p.project_image(pano, yaws, pitches, W, H, fov)
+            for i, y in enumerate(yaws):
+                for j, pt in enumerate(pitches):
+                    want = eb.project_view_exact(pano, y, pt, W, H, fov)
+                    if kind == "smooth":
+                        assert np.abs(out[i, j].astype(np.int16) - want.astype(np.int16)).max() <= 1
+                    else:
+                        assert exact_fraction(out[i, j], want) >= 0.97
+        with pytest.raises(pkg.P2PError):   # fractional yaws are only defined for the cv2 mode
+            p.project_image(pano, [30], [90], W, H, fov)
+        # and the default mode is untouched: it differs from the exact mode (5-bit fractions) on noise
+        exact_view = p.project_image(pano, [0], [90], W, H, fov)[0, 0].copy()
+        p.set_option(L.OPT_INTERP, 0)
+        cv2_view = p.project_image(pano, [0], [90], W, H, fov)[0, 0]
+        assert np.array_equal(cv2_view, fp.sample_view(pano, *p.coords(W, H, fov, 90, Wp, Hp), yaw_shift=0))
+        assert not np.array_equal(cv2_view, exact_view)
+    finally:
+        p.close()
+
+
 def test_fast_ieee_sequences_match_intrinsics(proj):
     """The range-check-free sqrt / shared-reciprocal division / constant division used by the hot
     kernel are bit-identical to __fsqrt_rn / __fdiv_rn: every pixel of the BASELINE view shapes,

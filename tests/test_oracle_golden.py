@@ -157,3 +157,36 @@ def test_full_size_c5_pole_face_hash(manifest):
     for k in (1, 5):  # the seam face and a pole face
         y, p = faces[k]
         assert sha(fp.project_view_single_pass(pano, y, p, 2048, 2048, 90)) == want[k]
+
+
+def test_exact_bilinear_oracle_arithmetic_model():
+    """The optional exact-bilinear mode is pinned against scipy.ndimage.map_coordinates(order=1); this
+    checks the arithmetic the CUDA kernel implements (double precision, weights 1 - frac and
+    1 - (1 - frac), C-order taps, row weight then column weight, +0.5 and truncation) against scipy."""
+    pytest.importorskip("scipy")
+    from oracle import exact_bilinear as eb
+
+    rng = np.random.default_rng(0)
+    Wp, Hp, W, H = 257, 129, 300, 200
+    pano = synth.noise(Wp, Hp, 1)
+    U = rng.uniform(0, Wp - 1, (H, W)).astype(np.float32)
+    V = rng.uniform(0, Hp - 1, (H, W)).astype(np.float32)
+    U[0, :] = Wp - 1
+    V[1, :] = Hp - 1
+    U[2, :8] = np.arange(8) + 0.5
+    V[2, :8] = np.arange(8) + 0.5
+    want = eb.sample_view_exact(pano, U, V, 5)
+    r = np.roll(pano, -5, axis=1).astype(np.float64)
+    xf, yf = np.floor(U), np.floor(V)
+    ix, iy = xf.astype(int), yf.astype(int)
+    fx, fy = (U - xf).astype(np.float64), (V - yf).astype(np.float64)
+    wy0 = 1 - fy
+    wy1 = 1 - wy0
+    wx0 = 1 - fx
+    wx1 = 1 - wx0
+    ix1, iy1 = np.minimum(ix + 1, Wp - 1), np.minimum(iy + 1, Hp - 1)
+    acc = np.zeros((H, W, 3))
+    for yy, xx, wy, wx in ((iy, ix, wy0, wx0), (iy, ix1, wy0, wx1), (iy1, ix, wy1, wx0), (iy1, ix1, wy1, wx1)):
+        acc = acc + (r[yy, xx] * wy[..., None]) * wx[..., None]
+    got = np.minimum(np.where(acc > 0, acc + 0.5, 0), 255).astype(np.uint8)
+    assert np.array_equal(got, want)
