@@ -334,6 +334,7 @@ def test_exact_bilinear_mode_against_scipy(pkg):
         # and the default mode is untouched: it differs from the exact mode (5-bit fractions) on noise
         exact_view = p.project_image(pano, [0], [90], W, H, fov)[0, 0].copy()
         p.set_option(L.OPT_INTERP, 0)
+        p.set_option(L.OPT_MIRROR, 0)  # per-pixel kernel = the coordinates p2p_coords reports
         cv2_view = p.project_image(pano, [0], [90], W, H, fov)[0, 0]
         assert np.array_equal(cv2_view, fp.sample_view(pano, *p.coords(W, H, fov, 90, Wp, Hp), yaw_shift=0))
         assert not np.array_equal(cv2_view, exact_view)
