@@ -339,13 +339,16 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                 "sampler": proj.get_option(L.OPT_SAMPLER), "warp_w": proj.get_option(L.OPT_WARP_W),
                 "yaws_per_thread": proj.get_option(L.OPT_YAWS_PER_THREAD),
                 "images_per_launch": proj.get_option(L.OPT_IMAGES_PER_LAUNCH),
+                "mirror_pairs": proj.get_option(L.OPT_MIRROR),
                 "distinct_seeds_per_gpu": n_distinct,
             }),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": read_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": B_ALG_PER_IMAGE, "launch_ms": launch_ms,
-                "kernel": "p2p::project_kernel (one launch = one image = 12 views)",
+                "kernel": ("p2p::project_mirror_kernel<4>" if (proj.get_option(L.OPT_MIRROR) and proj.get_option(L.OPT_SAMPLER) == 1
+                                                              and proj.get_option(L.OPT_IMAGES_PER_LAUNCH) == 1)
+                           else "p2p::project_kernel") + " (one launch = one image = 12 views)",
             },
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * H2D_PER_IMAGE,
