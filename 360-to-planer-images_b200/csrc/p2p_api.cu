@@ -276,9 +276,8 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
             }
             dim3 grid((W + 31) / 32, (H + 7) / 8, np_l);
             if (grid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
-            proj_fn fn = (ctx->opt_sampler == 1)   ? pick_kernel<1>(quad, nb, ctx->opt_warp_w, ny_l)
-                         : (ctx->opt_sampler == 2) ? pick_kernel<2>(quad, nb, ctx->opt_warp_w, ny_l)
-                                                   : pick_kernel<0>(quad, nb, ctx->opt_warp_w, ny_l);
+            proj_fn fn = (ctx->opt_sampler == 1) ? pick_kernel<1>(quad, nb, ctx->opt_warp_w, ny_l)
+                                                 : pick_kernel<0>(quad, nb, ctx->opt_warp_w, ny_l);
             fn<<<grid, kThreads, 0, s.stream>>>(P);
             ctx->launches++;
             CK(cudaGetLastError());
@@ -389,7 +388,7 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     switch (key) {
         case P2P_OPT_SAMPLER:
-            if (value < 0 || value > 2) return fail(ctx, P2P_ERR_INVALID, "sampler must be 0, 1 or 2");
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "sampler must be 0 or 1");
             ctx->opt_sampler = value;
             return P2P_OK;
         case P2P_OPT_WARP_W:

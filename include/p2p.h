@@ -51,8 +51,7 @@ typedef struct p2p_pitch_consts {
 
 /* option keys for p2p_set_option */
 typedef enum p2p_option {
-    P2P_OPT_SAMPLER = 0, /* 0 = global-load gather, 1 = texture gather4 point fetch (default), 2 = both,
-                            alternating between the yaws of a launch */
+    P2P_OPT_SAMPLER = 0, /* 0 = global-load gather, 1 = texture gather4 point fetch (default) */
     P2P_OPT_WARP_W = 1,  /* output pixels per warp row: 32 (default) or 8 (8 x 4 warp tiles) */
     P2P_OPT_YAWS_PER_THREAD = 2, /* 1..4 views sharing one coordinate evaluation (default 4) */
     P2P_OPT_COUNT_LAUNCHES = 3,  /* read-only via p2p_get_option: kernels launched so far */

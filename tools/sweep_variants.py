@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1, 2])
+    ap.add_argument("--samplers", type=int, nargs="+", default=[0, 1])
     ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 8])
     ap.add_argument("--nys", type=int, nargs="+", default=[4])
     ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
