@@ -567,6 +567,13 @@ def test_abi_error_codes(pkg, proj):
         with pytest.raises(pkg.P2PError) as e:
             proj.project(s, [0], consts, 40000, 8)
         assert e.value.code == -5
+    # limits inherited from cv2.remap: every dimension < 32767
+    with proj.slots(1) as (s,):
+        with pytest.raises(pkg.P2PError) as e:
+            proj.upload(s, np.zeros((1, 32767, 3), np.uint8))
+        assert e.value.code == -5
+        proj.upload(s, np.zeros((1, 32766, 3), np.uint8))  # the largest legal width
+        proj.sync(s)
     fresh = pkg.Projector(0, n_slots=1)
     try:
         with pytest.raises(pkg.P2PError) as e:
