@@ -207,7 +207,7 @@ def run_reference_arm(args, rank: int):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -357,14 +357,33 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             "gpu_launches": launches * world,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for b in pin_in + pin_out:
         b.free()
     proj.close()
     ranks.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the one JSON line on the real stdout (library chatter such as NCCL's version banner has
+    been redirected to stderr by ``main``)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # stdout carries exactly one JSON line: everything else any library prints to fd 1 goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -389,6 +408,7 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__, *sys.argv[1:]]
+        os.dup2(_REAL_STDOUT, 1)  # the torchrun children write their own single line
         raise SystemExit(subprocess.call(cmd))
     run_b200_arm(args, rank, local_rank, world)
 
