@@ -28,6 +28,7 @@ struct Slot {
     cudaArray_t arr = nullptr;  // gather-enabled array (sampler 1)
     int arrW = 0, arrH = 0;
     cudaTextureObject_t tex = 0;
+    cudaSurfaceObject_t surf = 0;  // the same array, written directly by the pack kernel
     bool tex_current = false;
     uint8_t *d_out = nullptr;  // device outputs when the caller wants them on the host
     size_t out_cap = 0;
@@ -112,32 +113,46 @@ int prepare_slot(p2p_ctx *ctx, Slot &s, int Wp, int Hp) {
     return P2P_OK;
 }
 
+int ensure_array(p2p_ctx *ctx, Slot &s);
+
 int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride) {
     const int groups = s.Wp / 4 + 1;
     dim3 block(256), grid((groups + 255) / 256, s.Hp + 1);
     const int aligned4 = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 3) == 0);
-    pack_kernel<<<grid, block, 0, s.stream>>>(d_src, stride, s.d_rgba, s.pitch_tex, s.Wp, s.Hp, aligned4);
+    // with the texture sampler the pack kernel also writes the gather array through a surface,
+    // so no device-to-device copy is needed before the projection
+    cudaSurfaceObject_t surf = 0;
+    if (ctx->opt_sampler == 1) {
+        int rc = ensure_array(ctx, s);
+        if (rc) return rc;
+        surf = s.surf;
+    }
+    pack_kernel<<<grid, block, 0, s.stream>>>(d_src, stride, s.d_rgba, s.pitch_tex, s.Wp, s.Hp, aligned4, surf);
     ctx->launches++;
     CK(cudaGetLastError());
     s.valid = true;
+    s.tex_current = (surf != 0);
     return P2P_OK;
 }
 
-// (re)build the gather texture of a slot from its packed panorama
-int ensure_texture(p2p_ctx *ctx, Slot &s) {
-    if (s.tex_current) return P2P_OK;
+// gather-enabled array of a slot (texture for the sampler, surface for the pack kernel)
+int ensure_array(p2p_ctx *ctx, Slot &s) {
     const int aw = s.Wp, ah = s.Hp;  // wrap in x / clamp in y replace the duplicated column and row
     if (!s.arr || s.arrW != aw || s.arrH != ah) {
         if (s.tex) {
             CK(cudaDestroyTextureObject(s.tex));
             s.tex = 0;
         }
+        if (s.surf) {
+            CK(cudaDestroySurfaceObject(s.surf));
+            s.surf = 0;
+        }
         if (s.arr) {
             CK(cudaFreeArray(s.arr));
             s.arr = nullptr;
         }
         cudaChannelFormatDesc fd = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindUnsigned);
-        CK(cudaMallocArray(&s.arr, &fd, aw, ah, cudaArrayTextureGather));
+        CK(cudaMallocArray(&s.arr, &fd, aw, ah, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
         s.arrW = aw;
         s.arrH = ah;
         cudaResourceDesc rd;
@@ -152,8 +167,18 @@ int ensure_texture(p2p_ctx *ctx, Slot &s) {
         td.readMode = cudaReadModeElementType;
         td.normalizedCoords = 1;
         CK(cudaCreateTextureObject(&s.tex, &rd, &td, nullptr));
+        CK(cudaCreateSurfaceObject(&s.surf, &rd));
     }
-    CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.d_rgba, (size_t)s.pitch_tex * 4, (size_t)aw * 4, ah,
+    return P2P_OK;
+}
+
+// make the texture of a slot current: normally the pack kernel has written the array already; a
+// panorama produced by the rotate kernel (linear buffer only) is copied into it
+int ensure_texture(p2p_ctx *ctx, Slot &s) {
+    if (s.tex_current) return P2P_OK;
+    int rc = ensure_array(ctx, s);
+    if (rc) return rc;
+    CK(cudaMemcpy2DToArrayAsync(s.arr, 0, 0, s.d_rgba, (size_t)s.pitch_tex * 4, (size_t)s.Wp * 4, s.Hp,
                                 cudaMemcpyDeviceToDevice, s.stream));
     s.tex_current = true;
     return P2P_OK;
@@ -367,6 +392,7 @@ void p2p_destroy(p2p_ctx *ctx) {
     for (int i = 0; i < ctx->n_slots; ++i) {
         Slot &s = ctx->slots[i];
         if (s.tex) cudaDestroyTextureObject(s.tex);
+        if (s.surf) cudaDestroySurfaceObject(s.surf);
         if (s.arr) cudaFreeArray(s.arr);
         cudaFree(s.d_bgr);
         cudaFree(s.d_rgba);
