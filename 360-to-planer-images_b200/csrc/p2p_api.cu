@@ -603,11 +603,18 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
     CK(cudaMemcpyAsync(d.d_tab, ix, (size_t)a.Wp * 4, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.d_tab + a.Wp, fx, (size_t)a.Wp * 4, cudaMemcpyHostToDevice, d.stream));
     CK(cudaStreamSynchronize(d.stream));  // ix / fx are caller memory (pageable): copy must be done
+    cudaSurfaceObject_t surf = 0;
+    if (ctx->opt_sampler == 1) {
+        rc = ensure_array(ctx, d);
+        if (rc) return rc;
+        surf = d.surf;
+    }
     dim3 block(256), grid((a.Wp + 1 + 255) / 256, a.Hp + 1);
-    rotate_kernel<<<grid, block, 0, d.stream>>>(a.d_rgba, d.d_rgba, a.pitch_tex, a.Wp, a.Hp, d.d_tab, d.d_tab + a.Wp);
+    rotate_kernel<<<grid, block, 0, d.stream>>>(a.d_rgba, d.d_rgba, a.pitch_tex, a.Wp, a.Hp, d.d_tab, d.d_tab + a.Wp, surf);
     ctx->launches++;
     CK(cudaGetLastError());
     d.valid = true;
+    d.tex_current = (surf != 0);
     return P2P_OK;
 }
 
