@@ -551,6 +551,26 @@ def test_directory_pipeline_matches_single_image_path(pkg, tmp_path, caplog):
                           cv2.imread(str(out_a / f"p0_{W}x{H}_yaw_90_pitch_60.png")))
 
 
+def test_integration_md_stub_runs(pkg):
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would paste in) is
+    executed verbatim against the built library and must reproduce the packaged drop-in."""
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    text = (root / "INTEGRATION.md").read_text()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "def process_yaw_and_pitchs" in b and "C.CDLL" in b)
+    stub = stub.replace('C.CDLL("libp2p_b200.so")', f'C.CDLL(r"{pkg._lib.LIB_PATH}")')
+    ns = {}
+    exec(compile(stub, "INTEGRATION.md", "exec"), ns)
+    pano = synth.smooth(1000, 500, 3)
+    for yaw in (90, 30):  # integer roll and fractional yaw
+        got = ns["process_yaw_and_pitchs"](pano, yaw, [60, 120], 200, 120, 100)
+        want = pkg.process_yaw_and_pitchs(pano, yaw, [60, 120], 200, 120, 100)
+        assert len(got) == 2 and all(np.array_equal(a, b) for a, b in zip(got, want)), yaw
+
+
 # ------------------------------------------------------------------------------------------
 # error behaviour of the C ABI
 # ------------------------------------------------------------------------------------------
