@@ -64,7 +64,7 @@ SIGNATURES = {
     "p2p_download_pano": (_i, [_vp, _i, _u8p, _sz]),
 }
 
-OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH, OPT_MIRROR, OPT_INTERP = 0, 1, 2, 3, 4, 5, 6
+OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH, OPT_MIRROR, OPT_INTERP, OPT_TRIG = 0, 1, 2, 3, 4, 5, 6, 7
 
 _lib = None
 

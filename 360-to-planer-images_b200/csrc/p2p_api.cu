@@ -49,6 +49,7 @@ struct p2p_ctx {
     int opt_ny = 4;
     int opt_nb = 1;
     int opt_mirror = 1;
+    int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
     long long launches = 0;
     uint4 *d_flush = nullptr;
@@ -252,6 +253,7 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
     P.Vmax = (float)(s.Hp - 1);
     P.inv_Wp = (float)(1.0 / (double)s.Wp);
     P.inv_Hp = (float)(1.0 / (double)s.Hp);
+    P.numpy_trig = (ctx->opt_trig == 0);
     const bool quad = ((W & 3) == 0) && aligned;
     if (!quad && nb > 1) return fail(ctx, P2P_ERR_INVALID, "multi-image launches need W % 4 == 0 and aligned outputs");
     // chunk over yaws (<= 4 share one coordinate evaluation) and pitches (grid.z) so any list length works
@@ -437,6 +439,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "interp must be 0 (cv2 fixed point) or 1 (exact bilinear)");
             ctx->opt_interp = value;
             return P2P_OK;
+        case P2P_OPT_TRIG:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "trig must be 0 (NumPy-exact) or 1 (minimax)");
+            ctx->opt_trig = value;
+            return P2P_OK;
 
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -454,6 +460,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
         case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
+        case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
 
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
@@ -830,7 +837,7 @@ int p2p_coords(p2p_ctx *ctx, const p2p_pitch_consts *pitch, int W, int H, int Wp
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
     cudaStream_t st = ctx->slots[0].stream;
     coords_kernel<<<grid, block, 0, st>>>(k, W, H, (float)(W / 2.0), (float)(H / 2.0), (float)Wp, (float)Hp,
-                                          (float)(Wp - 1), (float)(Hp - 1), d, d + n);
+                                          (float)(Wp - 1), (float)(Hp - 1), d, d + n, ctx->opt_trig == 0);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(U_host, d, n * sizeof(float), cudaMemcpyDeviceToHost, st);

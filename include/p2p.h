@@ -64,6 +64,9 @@ typedef enum p2p_option {
                                      (ref :192-199, :212-218); 1: exact bilinear - un-quantised fractions with the
                                      arithmetic of scipy.ndimage.map_coordinates(order=1) (double precision, round
                                      half up); integer-roll yaws only */
+    ,P2P_OPT_TRIG = 7              /* 0 (default): f32 arccos / arctan2 exactly as NumPy evaluates them on AVX-512
+                                     hosts (Intel SVML, ref :162-164) - coordinates and pixels then match the
+                                     reference bit for bit there; 1: table-free minimax fits (<= 1.2 ulp) */
 
 } p2p_option;
 

@@ -123,7 +123,30 @@ def _coord_report(U, V, Ur, Vr):
 
 
 @pytest.mark.parametrize("name", ["c2_small.npz", "c5_small.npz"])
-def test_g2_coordinates_within_fp32_tolerance(proj, golden_dir, name):
+def test_g2_coordinates_bit_exact_with_numpy_exact_trig(proj, golden_dir, name):
+    """Default mode: arccos / arctan2 as NumPy evaluates them on the AVX-512 host that produced the
+    golden maps -> every U and V of the reference's pitch maps is reproduced bit for bit."""
+    g = load(golden_dir, name)
+    Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
+    pitches = g["pitches"] if "pitches" in g.files else g["map_pitches"]
+    for j, p in enumerate(pitches):
+        U, V = proj.coords(W, H, fov, int(p), Wp, Hp)
+        assert np.array_equal(U.view(np.uint32), g["U"][j].view(np.uint32)), int(p)
+        nan = np.isnan(g["V"][j])
+        assert np.array_equal(np.isnan(V), nan)
+        assert np.array_equal(V.view(np.uint32)[~nan], g["V"][j].view(np.uint32)[~nan]), int(p)
+
+
+@pytest.fixture()
+def minimax_trig(pkg, proj):
+    """Switch the shared context to the table-free minimax acos / atan2 for one test."""
+    proj.set_option(pkg._lib.OPT_TRIG, 1)
+    yield
+    proj.set_option(pkg._lib.OPT_TRIG, 0)
+
+
+@pytest.mark.parametrize("name", ["c2_small.npz", "c5_small.npz"])
+def test_g2_coordinates_within_fp32_tolerance(proj, golden_dir, name, minimax_trig):
     g = load(golden_dir, name)
     Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
     pitches = g["pitches"] if "pitches" in g.files else g["map_pitches"]
@@ -159,7 +182,62 @@ def test_g2_nan_pixel_set_equality(proj, golden_dir):
 # ------------------------------------------------------------------------------------------
 # G3 end to end
 # ------------------------------------------------------------------------------------------
-def test_g3_c1_reference_case(proj, golden_dir):
+def test_g3_bit_exact_against_every_golden_output(pkg, proj, golden_dir):
+    """Default mode (NumPy-exact trig, mirror kernel): every stored output of the unmodified reference -
+    C1 full size, the scaled README example on noise and on the smooth panorama, cube faces with pole
+    pitches, fractional yaws, the NaN-pixel case - is reproduced bit for bit, by both projection kernels."""
+    L = pkg._lib
+    for mirror in (1, 0):
+        proj.set_option(L.OPT_MIRROR, mirror)
+        try:
+            g = load(golden_dir, "c1.npz")
+            out = proj.project_image(synth.noise(int(g["Wp"]), int(g["Hp"]), 0), [0], [90], int(g["W"]), int(g["H"]), int(g["fov"]))
+            assert np.array_equal(out, g["out"])
+            g = load(golden_dir, "c2_small.npz")
+            Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
+            yaws, pitches = [int(y) for y in g["yaws"]], [int(p) for p in g["pitches"]]
+            for kind in ("noise", "smooth"):
+                out = proj.project_image(synth.make(kind, Wp, Hp, 0), yaws, pitches, W, H, fov)
+                assert np.array_equal(out, g[f"out_{kind}"]), (mirror, kind)
+            g = load(golden_dir, "c5_small.npz")
+            Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
+            pano = synth.noise(Wp, Hp, 0)
+            for k, (yaw, pitch) in enumerate(g["views"]):
+                assert np.array_equal(proj.project_image(pano, [int(yaw)], [int(pitch)], W, H, fov)[0, 0], g["out"][k]), (mirror, int(yaw), int(pitch))
+            g = load(golden_dir, "frac_yaw.npz")
+            Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
+            out = proj.project_image(synth.noise(Wp, Hp, 0), [int(y) for y in g["yaws"]], [int(p) for p in g["pitches"]], W, H, fov)
+            assert np.array_equal(out, g["out"]), mirror
+            g = load(golden_dir, "nan_case.npz")
+            Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
+            out = proj.project_image(synth.smooth(Wp, Hp, 0), [0], [int(p) for p in g["pitches"]], W, H, fov)
+            assert np.array_equal(out, g["out"]), mirror
+        finally:
+            proj.set_option(L.OPT_MIRROR, 1)
+
+
+def test_g3_full_size_hashes_of_the_reference(proj, golden_dir):
+    """BASELINE configs at full size against the sha256 of the unmodified reference's outputs:
+    all 12 views of the README example (C2), the six cube faces (C5) and four 16K views (C4)."""
+    import hashlib
+
+    m = json.loads((golden_dir / "manifest.json").read_text())["hashes"]
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    pano = synth.noise(8192, 4096, 0)
+    out = proj.project_image(pano, [0, 90, 180, 270], [30, 60, 90], 1920, 1080, 120)
+    assert [[sha(out[i, j]) for j in range(3)] for i in range(4)] == m["c2_noise"]
+    faces = [(0, 90), (90, 90), (180, 90), (270, 90), (0, 0), (0, 180)]
+    assert [sha(proj.project_image(pano, [y], [p], 2048, 2048, 90)[0, 0]) for y, p in faces] == m["c5_noise"]
+    del pano, out
+    pano = synth.noise(16384, 8192, 0)
+    out = proj.project_image(pano, [0, 90], [30, 60, 90], 3840, 2160, 100)
+    assert [sha(out[0, j]) for j in range(3)] == m["c4_noise_yaw0"]
+    assert sha(out[1, 1]) == m["c4_noise_yaw90_pitch60"]
+
+def test_g3_c1_reference_case(proj, golden_dir, minimax_trig):
     g = load(golden_dir, "c1.npz")
     pano = synth.noise(int(g["Wp"]), int(g["Hp"]), 0)
     out = proj.project_image(pano, [0], [90], int(g["W"]), int(g["H"]), int(g["fov"]))
@@ -168,7 +246,7 @@ def test_g3_c1_reference_case(proj, golden_dir):
     assert frac >= NOISE_EXACT_MIN
 
 
-def test_g3_c2_small_smooth_le_1lsb_and_noise_fraction(proj, golden_dir):
+def test_g3_c2_small_smooth_le_1lsb_and_noise_fraction(proj, golden_dir, minimax_trig):
     g = load(golden_dir, "c2_small.npz")
     Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
     yaws, pitches = [int(y) for y in g["yaws"]], [int(p) for p in g["pitches"]]
@@ -183,7 +261,7 @@ def test_g3_c2_small_smooth_le_1lsb_and_noise_fraction(proj, golden_dir):
     assert min(min(r) for r in fr) >= NOISE_EXACT_MIN
 
 
-def test_g3_cube_faces(proj, golden_dir):
+def test_g3_cube_faces(proj, golden_dir, minimax_trig):
     g = load(golden_dir, "c5_small.npz")
     Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
     pano = synth.noise(Wp, Hp, 0)
@@ -192,7 +270,7 @@ def test_g3_cube_faces(proj, golden_dir):
         assert exact_fraction(out, g["out"][k]) >= NOISE_EXACT_MIN, (int(yaw), int(pitch))
 
 
-def test_g3_nan_pixel_is_black(proj, golden_dir):
+def test_g3_nan_pixel_is_black(proj, golden_dir, minimax_trig):
     g = load(golden_dir, "nan_case.npz")
     Wp, Hp, W, H, fov = (int(g[k]) for k in ("Wp", "Hp", "W", "H", "fov"))
     pano = synth.smooth(Wp, Hp, 0)
@@ -280,9 +358,18 @@ def test_mirror_kernel_against_per_pixel_kernel_and_oracle(pkg, proj):
         finally:
             proj.set_option(L.OPT_MIRROR, 1)
         got_n = proj.project_image(noise, yaws, pitches, W, H, fov)
-        assert np.array_equal(got_n[..., W // 2:, :], ref_n[..., W // 2:, :]), "direct half differs"
-        left = exact_fraction(got_n[..., :W // 2, :], ref_n[..., :W // 2, :])
-        assert left >= 0.97, left
+        # NumPy-exact trig: the pair shares SVML's sign-independent atan2 core, both halves are identical
+        assert np.array_equal(got_n, ref_n), "mirror kernel differs from the per-pixel kernel"
+        try:  # minimax trig: the derived half may flip a 1/32-px bin where the azimuths differ in the last ulp
+            proj.set_option(L.OPT_TRIG, 1)
+            got_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+            proj.set_option(L.OPT_MIRROR, 0)
+            ref_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+        finally:
+            proj.set_option(L.OPT_MIRROR, 1)
+            proj.set_option(L.OPT_TRIG, 0)
+        assert np.array_equal(got_m[..., W // 2:, :], ref_m[..., W // 2:, :]), "direct half differs"
+        assert exact_fraction(got_m[..., :W // 2, :], ref_m[..., :W // 2, :]) >= 0.97
         got_s = proj.project_image(smooth, yaws, pitches, W, H, fov)
         for i, y in enumerate(yaws):
             for j, p in enumerate(pitches):

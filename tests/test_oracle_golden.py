@@ -190,3 +190,27 @@ def test_exact_bilinear_oracle_arithmetic_model():
         acc = acc + (r[yy, xx] * wy[..., None]) * wx[..., None]
     got = np.minimum(np.where(acc > 0, acc + 0.5, 0), 255).astype(np.uint8)
     assert np.array_equal(got, want)
+
+
+def test_svml_model_reproduces_numpy_arccos_arctan2():
+    """NumPy evaluates f32 arccos / arctan2 with Intel SVML on AVX-512 hosts; the operation-by-operation
+    model (which the CUDA kernels restate) must agree bit for bit, including +-1, +-0, |x| > 1 and NaN."""
+    from oracle import svml_model as sm
+
+    if not sm.host_numpy_uses_svml():
+        pytest.skip("this host's NumPy does not take the AVX-512 SVML path")
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.uniform(-1, 1, 1_500_000), 1 - np.logspace(-7.5, -1, 100_000),
+                        -1 + np.logspace(-7.5, -1, 100_000),
+                        [1, -1, 0, -0.0, 0.5, -0.5, 0.25, 1.0000001, -1.0000001, np.nan]]).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        want = np.arccos(z)
+    got = sm.acos(z)
+    assert np.array_equal(want.view(np.uint32)[~np.isnan(want)], got.view(np.uint32)[~np.isnan(want)])
+    assert np.array_equal(np.isnan(want), np.isnan(got))
+    y = np.concatenate([rng.uniform(-1, 1, 1_500_000), rng.uniform(-1e-6, 1e-6, 100_000),
+                        [0, 0, -0.0, 0.3, -0.3, 0, -0.0]]).astype(np.float32)
+    x = np.concatenate([rng.uniform(-1, 1, 1_500_000), rng.uniform(-1, 1, 100_000),
+                        [0, -0.0, 0.0, 0, -0.0, 0.5, -0.5]]).astype(np.float32)
+    assert np.array_equal(np.arctan2(y, x).view(np.uint32), sm.atan2(y, x).view(np.uint32))
+    # and the golden maps of the reference follow from it (rotated ray from the scalar model)
