@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import fixedpoint as fp
-from oracle import ref_port, synth
+from oracle import ref_port, svml_model, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,9 @@ def test_random_configs_against_oracle(proj, case):
                 if shift is not None:
                     assert np.array_equal(proj.sample_with_maps(s, shift, U, V),
                                           fp.sample_view(noise, U, V, yaw_shift=shift)), (case, y, p)
+    # When this host's NumPy evaluates arccos / arctan2 with SVML (AVX-512), the default device path is
+    # bit-identical to the oracle; otherwise the reference itself differs in the last ulp on this host.
+    strict = svml_model.host_numpy_uses_svml()
     total = exact = 0
     for i, y in enumerate(yaws):
         for j, p in enumerate(pitches):
@@ -54,6 +57,8 @@ def test_random_configs_against_oracle(proj, case):
             U, _ = ref_port.pitch_mapping(W, H, fov, p, Wp, Hp)
             seam = (U <= 1.0) | (U >= Wp - 2.0) | np.isnan(U)
             assert d[~seam].max(initial=0) <= 1, (case, y, p, int(d[~seam].max(initial=0)))
+            if strict:
+                assert np.array_equal(got_n[i, j], want_n) and np.array_equal(got_s[i, j], want_s), (case, y, p)
             same = (got_n[i, j] == want_n).all(axis=-1)
             total += same.size
             exact += int(same.sum())
