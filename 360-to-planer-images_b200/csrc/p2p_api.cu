@@ -291,11 +291,20 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
             if (ctx->opt_mirror && ctx->opt_sampler == 1 && nb == 1 && quad && (W & 7) == 0) {
                 dim3 mgrid((W / 2 + 1 + 31) / 32, (H + kMirRows - 1) / kMirRows, np_l);
                 if (mgrid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
-                switch (ny_l) {
-                    case 1: project_mirror_kernel<1><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
-                    case 2: project_mirror_kernel<2><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
-                    case 3: project_mirror_kernel<3><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
-                    default: project_mirror_kernel<4><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                if (P.numpy_trig) {
+                    switch (ny_l) {
+                        case 1: project_mirror_kernel<1, true><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        case 2: project_mirror_kernel<2, true><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        case 3: project_mirror_kernel<3, true><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        default: project_mirror_kernel<4, true><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                    }
+                } else {
+                    switch (ny_l) {
+                        case 1: project_mirror_kernel<1, false><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        case 2: project_mirror_kernel<2, false><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        case 3: project_mirror_kernel<3, false><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                        default: project_mirror_kernel<4, false><<<mgrid, kMirThreads, 0, s.stream>>>(P); break;
+                    }
                 }
                 ctx->launches++;
                 CK(cudaGetLastError());
