@@ -658,6 +658,35 @@ def test_integration_md_stub_runs(pkg):
         assert len(got) == 2 and all(np.array_equal(a, b) for a, b in zip(got, want)), yaw
 
 
+def test_plain_c_consumer_matches_python_host(pkg, tmp_path):
+    """tests/c_abi_smoke.c (C99, no Python, host scalars from the library's own C helpers) renders the same
+    pixels as the Python host."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "c_abi_smoke"
+    libdir = pkg._lib.LIB_PATH.parent
+    subprocess.run([gcc, "-std=c99", "-O1", f"-I{root / 'include'}", str(root / "tests" / "c_abi_smoke.c"), "-o", str(exe),
+                    f"-L{libdir}", "-lp2p_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    Wp, Hp, W, H, fov = 1024, 512, 200, 120, 100
+    out_file = tmp_path / "out.bin"
+    run = subprocess.run([str(exe), str(Wp), str(Hp), str(W), str(H), str(fov), str(out_file)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    s, vals = 12345, np.empty(Wp * Hp * 3, np.uint8)
+    for i in range(vals.size):  # same LCG as the C program
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+        vals[i] = s >> 24
+    pano = vals.reshape(Hp, Wp, 3)
+    got = np.fromfile(out_file, np.uint8).reshape(3, 2, H, W, 3)
+    want = pkg.Projector(0, n_slots=1).project_image(pano, [0, 90, 270], [60, 120], W, H, fov)
+    assert np.array_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------------
 # error behaviour of the C ABI
 # ------------------------------------------------------------------------------------------

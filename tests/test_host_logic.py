@@ -148,3 +148,24 @@ def test_sharding(pkg):
     assert shard.group_by_pitch([(0, 1), (1, 1), (0, 2)]) == {1: [0, 1], 2: [0]}
     with pytest.raises(ValueError):
         shard.shard_images(4, 2, 2)
+
+
+def test_header_is_plain_c_and_links(pkg, tmp_path):
+    """include/p2p.h must be consumable from C (C99, -pedantic) and the library must link from C."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = ROOT / "tests" / "c_abi_smoke.c"
+    exe = tmp_path / "c_abi_smoke"
+    libdir = pkg._lib.LIB_PATH.parent
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+           f"-L{libdir}", "-lp2p_b200", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    if pkg._lib.load().p2p_device_count() == 0:
+        # no GPU here: the program must fail loudly at p2p_create, not crash
+        run = subprocess.run([str(exe), "64", "32", "16", "8", "90", str(tmp_path / "o.bin")], capture_output=True, text=True)
+        assert run.returncode == 2 and "p2p_create" in run.stderr
