@@ -50,6 +50,7 @@ SIGNATURES = {
     "p2p_project_views": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _u8p, _i]),
     "p2p_project_batch": (_i, [_vp, _i, _i32p, _i, _i32p, _i, _pcp, _i, _i, C.POINTER(_vp), _i]),
     "p2p_process_image": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _u8p]),
+    "p2p_view_row_range": (_i, [_vp, _i, _pcp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "p2p_sync": (_i, [_vp, _i]),
     "p2p_set_stream": (_i, [_vp, _i, _vp]),
     "p2p_get_stream": (_i, [_vp, _i, C.POINTER(_vp)]),
@@ -65,6 +66,7 @@ SIGNATURES = {
 }
 
 OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH, OPT_MIRROR, OPT_INTERP, OPT_TRIG = 0, 1, 2, 3, 4, 5, 6, 7
+OPT_PARTIAL_UPLOAD = 8
 
 _lib = None
 

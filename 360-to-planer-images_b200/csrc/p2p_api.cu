@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 using namespace p2p;
 
@@ -25,6 +26,7 @@ struct Slot {
     size_t rgba_cap = 0;
     int Wp = 0, Hp = 0, pitch_tex = 0;
     bool valid = false;
+    int row0 = 0, row1 = 0;  // packed rows row0 .. row1 (<= Hp, the clamp row) hold data; a full upload has 0 .. Hp
     cudaArray_t arr = nullptr;  // gather-enabled array (sampler 1)
     int arrW = 0, arrH = 0;
     cudaTextureObject_t tex = 0;
@@ -34,6 +36,14 @@ struct Slot {
     size_t out_cap = 0;
     int32_t *d_tab = nullptr;  // yaw table (ix | fx), 2 * Wp
     size_t tab_cap = 0;
+};
+
+// memoised tap-row range of one view geometry (no yaw, no image: the key of the reference's pitch map cache)
+struct RowRange {
+    bool valid = false;
+    int W = 0, H = 0, Wp = 0, Hp = 0, trig = 0;
+    std::vector<p2p_pitch_consts> pc;
+    int lo = 0, hi = 0;  // min / max tap row iy over all pixels (the sampler reads rows iy and iy + 1)
 };
 
 }  // namespace
@@ -51,6 +61,9 @@ struct p2p_ctx {
     int opt_mirror = 1;
     int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
+    int opt_partial = 1;       // p2p_process_image transfers only the panorama rows its views can touch
+    RowRange rows;
+    int *d_range = nullptr;
     long long launches = 0;
     uint4 *d_flush = nullptr;
     size_t flush_cap = 0;
@@ -116,9 +129,10 @@ int prepare_slot(p2p_ctx *ctx, Slot &s, int Wp, int Hp) {
 
 int ensure_array(p2p_ctx *ctx, Slot &s);
 
-int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride) {
+// pack panorama rows y0 .. y1 (y1 <= Hp: row Hp is the clamp row) of the staging image into the device layout
+int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride, int y0, int y1) {
     const int groups = s.Wp / 4 + 1;
-    dim3 block(256), grid((groups + 255) / 256, s.Hp + 1);
+    dim3 block(256), grid((groups + 255) / 256, y1 - y0 + 1);
     const int aligned4 = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_src) & 3) == 0);
     // with the texture sampler the pack kernel also writes the gather array through a surface,
     // so no device-to-device copy is needed before the projection
@@ -128,11 +142,59 @@ int launch_pack(p2p_ctx *ctx, Slot &s, const uint8_t *d_src, size_t stride) {
         if (rc) return rc;
         surf = s.surf;
     }
-    pack_kernel<<<grid, block, 0, s.stream>>>(d_src, stride, s.d_rgba, s.pitch_tex, s.Wp, s.Hp, aligned4, surf);
+    pack_kernel<<<grid, block, 0, s.stream>>>(d_src, stride, s.d_rgba, s.pitch_tex, s.Wp, s.Hp, aligned4, surf, y0);
     ctx->launches++;
     CK(cudaGetLastError());
     s.valid = true;
+    s.row0 = y0;
+    s.row1 = y1;
     s.tex_current = (surf != 0);
+    return P2P_OK;
+}
+
+bool slot_is_partial(const Slot &s) { return s.row0 > 0 || s.row1 < s.Hp; }
+
+// Tap-row range of a view set on a Wp x Hp panorama: the sampler reads rows lo .. hi + 1.  Evaluated once per
+// geometry on `st` (one small kernel + an 8-byte readback) and memoised in the context.
+int view_row_range(p2p_ctx *ctx, cudaStream_t st, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
+                   int Wp, int Hp, int *lo, int *hi) {
+    RowRange &r = ctx->rows;
+    bool hit = r.valid && r.W == W && r.H == H && r.Wp == Wp && r.Hp == Hp && r.trig == ctx->opt_trig &&
+               (int)r.pc.size() == n_pitch;
+    for (int j = 0; hit && j < n_pitch; ++j) hit = memcmp(&r.pc[j], &pitch[j], sizeof(p2p_pitch_consts)) == 0;
+    if (!hit) {
+        if ((H + 7) / 8 > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+        if (!ctx->d_range) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_range), 2 * sizeof(int)));
+        const int init[2] = {INT_MAX, INT_MIN};
+        CK(cudaMemcpyAsync(ctx->d_range, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        RowRangeParams P;
+        memset(&P, 0, sizeof(P));
+        P.W = W;
+        P.H = H;
+        P.halfW = (float)(W / 2.0);
+        P.halfH = (float)(H / 2.0);
+        P.Hp_f = (float)Hp;
+        P.Vmax = (float)(Hp - 1);
+        P.numpy_trig = (ctx->opt_trig == 0);
+        for (int p0 = 0; p0 < n_pitch; p0 += kMaxPitchPerLaunch) {
+            const int np_l = (n_pitch - p0 < kMaxPitchPerLaunch) ? n_pitch - p0 : kMaxPitchPerLaunch;
+            for (int j = 0; j < np_l; ++j) P.pc[j] = PitchC{pitch[p0 + j].f, pitch[p0 + j].c, pitch[p0 + j].s};
+            tap_rows_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, np_l), 256, 0, st>>>(P, ctx->d_range);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        int got[2] = {0, 0};
+        CK(cudaMemcpyAsync(got, ctx->d_range, sizeof(got), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (got[0] > got[1]) got[0] = got[1] = 0;  // every pixel NaN: nothing is read
+        r.W = W; r.H = H; r.Wp = Wp; r.Hp = Hp; r.trig = ctx->opt_trig;
+        r.pc.assign(pitch, pitch + n_pitch);
+        r.lo = got[0];
+        r.hi = got[1];
+        r.valid = true;
+    }
+    *lo = r.lo;
+    *hi = r.hi;
     return P2P_OK;
 }
 
@@ -218,6 +280,17 @@ proj_fn pick_kernel(bool quad, int nb, int warp_w, int ny) {
 int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                    const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *d_out) {
     Slot &s = *sl[0];
+    for (int b = 0; b < nb; ++b) {
+        // a slot filled by p2p_process_image holds only the rows its own views touch
+        if (!slot_is_partial(*sl[b])) continue;
+        if (ctx->opt_interp != 0)
+            return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama: exact interpolation needs a full upload");
+        int lo = 0, hi = 0;
+        int rc = view_row_range(ctx, sl[b]->stream, n_pitch, pitch, W, H, sl[b]->Wp, sl[b]->Hp, &lo, &hi);
+        if (rc) return rc;
+        if (lo < sl[b]->row0 || hi + 1 > sl[b]->row1)
+            return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama that does not cover these views: upload it again");
+    }
     if (ctx->opt_sampler != 0 && ctx->opt_interp == 0) {
         for (int b = 0; b < nb; ++b) {
             int rc = ensure_texture(ctx, *sl[b]);
@@ -334,6 +407,55 @@ int check_project_args(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shi
     return P2P_OK;
 }
 
+// host BGR rows y0 .. min(y1, Hp - 1) -> staging -> packed rows y0 .. y1 (y1 == Hp adds the clamp row); caller holds the lock
+int upload_rows(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int y0, int y1) {
+    int rc = check_dims(ctx, Wp, Hp);
+    if (rc) return rc;
+    if (row_stride < (size_t)Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    // tight device staging copy (row stride rounded to 4 bytes so the packer can use word loads)
+    const size_t dstride = ((size_t)Wp * 3 + 3) & ~(size_t)3;
+    rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, dstride * Hp);
+    if (rc) return rc;
+    rc = prepare_slot(ctx, s, Wp, Hp);
+    if (rc) return rc;
+    const int ys1 = (y1 < Hp) ? y1 : Hp - 1;
+    const size_t nrows = (size_t)(ys1 - y0 + 1);
+    if (row_stride == dstride) {
+        CK(cudaMemcpyAsync(s.d_bgr + (size_t)y0 * dstride, bgr + (size_t)y0 * row_stride, dstride * nrows,
+                           cudaMemcpyHostToDevice, s.stream));
+    } else {
+        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)y0 * dstride, dstride, bgr + (size_t)y0 * row_stride, row_stride,
+                             (size_t)Wp * 3, nrows, cudaMemcpyHostToDevice, s.stream));
+    }
+    return launch_pack(ctx, s, s.d_bgr, dstride, y0, y1);
+}
+
+// p2p_project_views with the context lock held
+int project_views_locked(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                         const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device) {
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    int rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, s.Wp);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n_yaw * n_pitch * W * H * 3;
+    uint8_t *d_out = out;
+    if (!out_on_device) {
+        rc = ensure(ctx, &s.d_out, &s.out_cap, bytes);
+        if (rc) return rc;
+        d_out = s.d_out;
+    }
+    Slot *sl[1] = {&s};
+    uint8_t *outs[1] = {d_out};
+    rc = launch_project(ctx, sl, 1, n_yaw, yaw_shift, n_pitch, pitch, W, H, outs);
+    if (rc) return rc;
+    if (!out_on_device) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    return P2P_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -413,6 +535,7 @@ void p2p_destroy(p2p_ctx *ctx) {
         if (s.owned) cudaStreamDestroy(s.owned);
     }
     cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_range);
     cudaGetLastError();
     delete[] ctx->slots;
     delete ctx;
@@ -452,6 +575,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "trig must be 0 (NumPy-exact) or 1 (minimax)");
             ctx->opt_trig = value;
             return P2P_OK;
+        case P2P_OPT_PARTIAL_UPLOAD:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "partial_upload must be 0 or 1");
+            ctx->opt_partial = value;
+            return P2P_OK;
 
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -470,6 +597,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
         case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
         case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
+        case P2P_OPT_PARTIAL_UPLOAD: *value = ctx->opt_partial; return P2P_OK;
 
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }
@@ -566,23 +694,7 @@ int p2p_host_unregister(void *ptr) {
 int p2p_upload_pano(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride) {
     if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    int rc = check_dims(ctx, Wp, Hp);
-    if (rc) return rc;
-    if (row_stride < (size_t)Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
-    CK(cudaSetDevice(ctx->device));
-    Slot &s = ctx->slots[slot];
-    // tight device staging copy (row stride rounded to 4 bytes so the packer can use word loads)
-    const size_t dstride = ((size_t)Wp * 3 + 3) & ~(size_t)3;
-    rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, dstride * Hp);
-    if (rc) return rc;
-    rc = prepare_slot(ctx, s, Wp, Hp);
-    if (rc) return rc;
-    if (row_stride == dstride) {
-        CK(cudaMemcpyAsync(s.d_bgr, bgr, dstride * Hp, cudaMemcpyHostToDevice, s.stream));
-    } else {
-        CK(cudaMemcpy2DAsync(s.d_bgr, dstride, bgr, row_stride, (size_t)Wp * 3, Hp, cudaMemcpyHostToDevice, s.stream));
-    }
-    return launch_pack(ctx, s, s.d_bgr, dstride);
+    return upload_rows(ctx, slot, bgr, Wp, Hp, row_stride, 0, Hp);
 }
 
 int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, int Hp, size_t row_stride) {
@@ -595,7 +707,7 @@ int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, in
     Slot &s = ctx->slots[slot];
     rc = prepare_slot(ctx, s, Wp, Hp);
     if (rc) return rc;
-    return launch_pack(ctx, s, static_cast<const uint8_t *>(d_bgr), row_stride);
+    return launch_pack(ctx, s, static_cast<const uint8_t *>(d_bgr), row_stride, 0, Hp);
 }
 
 int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix, const int32_t *fx) {
@@ -606,6 +718,7 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
     Slot &a = ctx->slots[src_slot];
     Slot &d = ctx->slots[dst_slot];
     if (!a.valid) return fail(ctx, P2P_ERR_STATE, "source slot holds no panorama");
+    if (slot_is_partial(a)) return fail(ctx, P2P_ERR_STATE, "source slot holds a partial panorama (p2p_process_image)");
     if (ctx->opt_interp != 0)
         return fail(ctx, P2P_ERR_INVALID, "fractional yaws are only defined for the cv2 fixed-point interpolation mode");
     for (int u = 0; u < a.Wp; ++u)
@@ -630,6 +743,8 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
     ctx->launches++;
     CK(cudaGetLastError());
     d.valid = true;
+    d.row0 = 0;
+    d.row1 = a.Hp;
     d.tex_current = (surf != 0);
     return P2P_OK;
 }
@@ -639,25 +754,7 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
                       const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device) {
     if (!ctx) return P2P_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
-    Slot &s = ctx->slots[slot];
-    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
-    int rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, s.Wp);
-    if (rc) return rc;
-    CK(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)n_yaw * n_pitch * W * H * 3;
-    uint8_t *d_out = out;
-    if (!out_on_device) {
-        rc = ensure(ctx, &s.d_out, &s.out_cap, bytes);
-        if (rc) return rc;
-        d_out = s.d_out;
-    }
-    Slot *sl[1] = {&s};
-    uint8_t *outs[1] = {d_out};
-    rc = launch_project(ctx, sl, 1, n_yaw, yaw_shift, n_pitch, pitch, W, H, outs);
-    if (rc) return rc;
-    if (!out_on_device) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
-    return P2P_OK;
+    return project_views_locked(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, out_on_device);
 }
 
 int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
@@ -713,9 +810,41 @@ int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_ya
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
                       int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
                       int W, int H, uint8_t *out_host) {
-    int rc = p2p_upload_pano(ctx, slot, bgr, Wp, Hp, row_stride);
+    if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
+    if (n_pitch <= 0 || !pitch || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_dims(ctx, Wp, Hp);
     if (rc) return rc;
-    return p2p_project_views(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, 0);
+    // the views are known before the transfer: move only the panorama rows they can touch (the pitch map does
+    // not depend on the yaw or the image, so the range is memoised per geometry like the reference's map cache)
+    int y0 = 0, y1 = Hp;
+    if (ctx->opt_partial && ctx->opt_interp == 0) {
+        CK(cudaSetDevice(ctx->device));
+        int lo = 0, hi = 0;
+        rc = view_row_range(ctx, ctx->slots[slot].stream, n_pitch, pitch, W, H, Wp, Hp, &lo, &hi);
+        if (rc) return rc;
+        y0 = lo;
+        y1 = hi + 1;  // second tap row; Hp = the clamp row (a copy of row Hp - 1)
+    }
+    rc = upload_rows(ctx, slot, bgr, Wp, Hp, row_stride, y0, y1);
+    if (rc) return rc;
+    return project_views_locked(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, 0);
+}
+
+int p2p_view_row_range(p2p_ctx *ctx, int n_pitch, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
+                       int *first_row, int *last_row) {
+    if (!ctx || n_pitch <= 0 || !pitch || W <= 0 || H <= 0 || !first_row || !last_row)
+        return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_dims(ctx, Wp, Hp);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int lo = 0, hi = 0;
+    rc = view_row_range(ctx, ctx->slots[0].stream, n_pitch, pitch, W, H, Wp, Hp, &lo, &hi);
+    if (rc) return rc;
+    *first_row = lo;
+    *last_row = (hi + 1 < Hp) ? hi + 1 : Hp - 1;
+    return P2P_OK;
 }
 
 int p2p_sync(p2p_ctx *ctx, int slot) {
@@ -893,6 +1022,7 @@ int p2p_download_pano(p2p_ctx *ctx, int slot, uint8_t *bgr_host, size_t row_stri
     std::lock_guard<std::mutex> lk(ctx->mu);
     Slot &s = ctx->slots[slot];
     if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    if (slot_is_partial(s)) return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama (p2p_process_image)");
     if (row_stride < (size_t)s.Wp * 3) return fail(ctx, P2P_ERR_INVALID, "row_stride smaller than Wp * 3");
     CK(cudaSetDevice(ctx->device));
     uint8_t *d = nullptr;

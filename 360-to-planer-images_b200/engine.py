@@ -222,6 +222,14 @@ class Projector:
                                             len(consts), pc, W, H, out.ctypes.data))
         return out
 
+    def view_row_range(self, consts, W: int, H: int, Wp: int, Hp: int) -> tuple:
+        """(first, last) panorama row (inclusive) the sampler reads for these pitch constants: what
+        ``process_image`` transfers over PCIe (any yaw, any image; memoised per geometry)."""
+        pc = self._consts_array(consts)
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.p2p_view_row_range(self.ctx, len(consts), pc, W, H, Wp, Hp, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- debug exports ------------------------------------------------------------------------
     def coords(self, W, H, fov_deg, pitch_deg, Wp, Hp):
         pc = self._consts_array([pitch_constants(W, fov_deg, pitch_deg)])

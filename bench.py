@@ -15,8 +15,8 @@ collective - torch.distributed only provides the barrier and the max-over-ranks 
 value    device-resident throughput: the packed panoramas already sit in HBM, outputs stay in HBM,
          one CUDA-event pair on the launching stream around exactly K steps, max over ranks.
 e2e      the same metric through the public API with HOST buffers: every image is uploaded from
-         pinned memory (100.7 MB), projected and read back (74.6 MB) inside the timed region,
-         pipelined over the context's slots (streams).
+         pinned memory (the rows its views can touch: 75 of 100.7 MB), projected and read back
+         (74.6 MB) inside the timed region, pipelined over the context's slots (streams).
 roofline HBM: algorithmic bytes per launch (3 * sum(W*H) + 3 * N_T = 141,009,384 B for
          one 12-view image) / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline  oracle/ref_port.py (NumPy + cv2.remap restatement of the reference, same thread
@@ -300,6 +300,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             proj.sync(s)  # the slot's previous image (and its readback) is complete
             proj.process_image(s, pin_in[i % n_host].array, shifts, consts, W, H, pin_out[i % n_e2e_slots].array)
 
+    # the library transfers only the panorama rows these views can touch (p2p_view_row_range)
+    row_first, row_last = proj.view_row_range(consts, W, H, WP, HP)
+    h2d_per_image = (row_last - row_first + 1) * WP * 3 if proj.get_option(L.OPT_PARTIAL_UPLOAD) else H2D_PER_IMAGE
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(2):
         e2e_step()
@@ -351,9 +354,12 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                            else "p2p::project_kernel") + " (one launch = one image = 12 views)",
             },
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * H2D_PER_IMAGE,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * h2d_per_image,
                     "d2h_bytes_per_step": BATCH * D2H_PER_IMAGE, "steps": e2e_steps,
-                    "ms_per_step": e2e_s / e2e_steps * 1e3, "pipeline_slots": n_e2e_slots},
+                    "ms_per_step": e2e_s / e2e_steps * 1e3, "pipeline_slots": n_e2e_slots,
+                    "h2d_rows": [row_first, row_last],
+                    "h2d_note": f"rows {row_first}..{row_last} of {HP}: the only panorama rows the 12 views read "
+                                f"({h2d_per_image} of {H2D_PER_IMAGE} bytes per image)"},
             "gpu_launches": launches * world,
             "clocks": clocks,
         }

@@ -67,6 +67,8 @@ typedef enum p2p_option {
     ,P2P_OPT_TRIG = 7              /* 0 (default): f32 arccos / arctan2 exactly as NumPy evaluates them on AVX-512
                                      hosts (Intel SVML, ref :162-164) - coordinates and pixels then match the
                                      reference bit for bit there; 1: table-free minimax fits (<= 1.2 ulp) */
+    ,P2P_OPT_PARTIAL_UPLOAD = 8    /* 1 (default): p2p_process_image copies only the panorama rows its views can
+                                     touch (p2p_view_row_range) over PCIe; 0: always the whole panorama */
 
 } p2p_option;
 
@@ -128,10 +130,19 @@ int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_ya
                       int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
                       int out_on_device);
 
-/* upload + project + readback of one image in one call (all asynchronous on the slot stream) */
+/* upload + project + readback of one image in one call (all asynchronous on the slot stream).
+ * Because the views are known before the transfer, only the panorama rows they can touch are copied to the
+ * device (P2P_OPT_PARTIAL_UPLOAD); the slot then holds a partial panorama: projecting other views from it
+ * returns P2P_ERR_STATE, upload it again instead. */
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
                       int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
                       int W, int H, uint8_t *out_host);
+
+/* First and last panorama row (inclusive) the 4-tap sampler reads for these pitches - every yaw, any image: the
+ * pitch map has no yaw and no image in it (the key of the reference's pitch_mapping_cache, ref :55-73).  Evaluated
+ * on the device with the projection kernel's own arithmetic (exact), memoised per geometry in the context. */
+int p2p_view_row_range(p2p_ctx *ctx, int n_pitch, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
+                       int *first_row, int *last_row);
 
 /* wait for everything enqueued on `slot` (slot < 0: all slots) */
 int p2p_sync(p2p_ctx *ctx, int slot);
