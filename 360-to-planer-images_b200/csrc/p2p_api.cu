@@ -2,6 +2,7 @@
 // Host logic only: contexts, panorama slots (stream + device buffers), launches, transfers.
 #include "p2p.h"
 #include "p2p_kernels.cuh"
+#include "p2p_jpeg_host.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -36,6 +37,22 @@ struct Slot {
     size_t out_cap = 0;
     int32_t *d_tab = nullptr;  // yaw table (ix | fx), 2 * Wp
     size_t tab_cap = 0;
+    // JPEG encoder scratch (p2p_encode_jpeg): coefficients, per-block bits / offsets, bit string, stuffed files
+    int16_t *j_coef = nullptr;
+    size_t j_coef_cap = 0;
+    uint32_t *j_bits = nullptr;   // [2][n * n_blocks]: code bits, exclusive offsets
+    size_t j_bits_cap = 0;
+    uint32_t *j_stream = nullptr;
+    size_t j_stream_cap = 0;
+    uint32_t *j_cnt = nullptr;    // [2][n * chunks]: 0xFF counts, exclusive offsets
+    size_t j_cnt_cap = 0;
+    uint8_t *j_out = nullptr;
+    size_t j_out_cap = 0;
+    unsigned long long *j_tot = nullptr;  // [3][n]: total bits, total 0xFF, n_chunks (as u32 pairs)
+    size_t j_tot_cap = 0;
+    unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
+    unsigned long long *j_sizes_d = nullptr;
+    int j_sizes_n = 0;
 };
 
 // memoised tap-row range of one view geometry (no yaw, no image: the key of the reference's pitch map cache)
@@ -62,6 +79,9 @@ struct p2p_ctx {
     int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
     int opt_partial = 1;       // p2p_process_image transfers only the panorama rows its views can touch
+    p2pjpeg::Tables *d_jtab = nullptr;  // JPEG tables + header of (jW, jH, jQ)
+    int jW = 0, jH = 0, jQ = 0;
+    int *j_err_h = nullptr, *j_err_d = nullptr;  // mapped: set by the encoder kernels when a file does not fit
     RowRange rows;
     int *d_range = nullptr;
     long long launches = 0;
@@ -456,6 +476,87 @@ int project_views_locked(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_s
     return P2P_OK;
 }
 
+// ---- JPEG encoder (p2p_jpeg.cuh) ---------------------------------------------------------------
+// enqueue the encoder for n device images on the slot's stream; the files land in s.j_out, the sizes in s.j_sizes_h
+int enqueue_jpeg(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H, int quality, p2pjpeg::Geometry &G) {
+    using namespace p2pjpeg;
+    if (W >= 65536 || H >= 65536) return fail(ctx, P2P_ERR_LIMIT, "JPEG dimensions must be < 65536");
+    G = make_geometry(W, H);
+    if ((size_t)G.n_blocks * 64ull * 27ull >= (1ull << 32)) return fail(ctx, P2P_ERR_LIMIT, "image too large for the JPEG encoder");
+    if (!ctx->d_jtab) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_jtab), sizeof(Tables)));
+    if (!ctx->j_err_h) {
+        CK(cudaHostAlloc(reinterpret_cast<void **>(&ctx->j_err_h), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        *ctx->j_err_h = 0;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->j_err_d), ctx->j_err_h, 0));
+    }
+    if (ctx->jW != W || ctx->jH != H || ctx->jQ != quality) {
+        // other streams may still read the old tables: rare (a new output size or quality), wait for everything
+        for (int i = 0; i < ctx->n_slots; ++i) CK(cudaStreamSynchronize(ctx->slots[i].stream));
+        Tables T;
+        build_tables(W, H, quality, T);
+        CK(cudaMemcpy(ctx->d_jtab, &T, sizeof(T), cudaMemcpyHostToDevice));
+        ctx->jW = W; ctx->jH = H; ctx->jQ = quality;
+    }
+    const size_t nb = (size_t)n * G.n_blocks, chunks = G.cap_bits_words / 4;
+    int rc = ensure(ctx, &s.j_coef, &s.j_coef_cap, nb * 64 * sizeof(int16_t));
+    if (!rc) rc = ensure(ctx, &s.j_bits, &s.j_bits_cap, 2 * nb * sizeof(uint32_t));
+    if (!rc) rc = ensure(ctx, &s.j_stream, &s.j_stream_cap, (size_t)n * G.cap_bits_words * sizeof(uint32_t));
+    if (!rc) rc = ensure(ctx, &s.j_cnt, &s.j_cnt_cap, 2 * (size_t)n * chunks * sizeof(uint32_t));
+    if (!rc) rc = ensure(ctx, &s.j_out, &s.j_out_cap, (size_t)n * G.cap_out);
+    if (!rc) rc = ensure(ctx, &s.j_tot, &s.j_tot_cap, 3 * (size_t)n * sizeof(unsigned long long));
+    if (rc) return rc;
+    if (s.j_sizes_n < n) {
+        if (s.j_sizes_h) CK(cudaFreeHost(s.j_sizes_h));
+        s.j_sizes_h = nullptr;
+        CK(cudaHostAlloc(reinterpret_cast<void **>(&s.j_sizes_h), (size_t)n * sizeof(unsigned long long),
+                         cudaHostAllocMapped | cudaHostAllocPortable));
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.j_sizes_d), s.j_sizes_h, 0));
+        s.j_sizes_n = n;
+    }
+    uint32_t *bits = s.j_bits, *offs = s.j_bits + nb;
+    uint32_t *cnt = s.j_cnt, *ffoff = s.j_cnt + (size_t)n * chunks;
+    unsigned long long *tot_bits = s.j_tot, *tot_ff = s.j_tot + n;
+    uint32_t *n_chunks = reinterpret_cast<uint32_t *>(s.j_tot + 2 * (size_t)n);
+    cudaStream_t st = s.stream;
+    CK(cudaMemsetAsync(s.j_stream, 0, (size_t)n * G.cap_bits_words * sizeof(uint32_t), st));
+    jpeg_dct_kernel<<<dim3((G.n_mcu + kMcuPerCta - 1) / kMcuPerCta, n), 64 * kMcuPerCta, 0, st>>>(d_bgr, s.j_coef, ctx->d_jtab, G);
+    jpeg_size_kernel<<<dim3((G.n_blocks + 255) / 256, n), 256, 0, st>>>(s.j_coef, bits, ctx->d_jtab, G);
+    jpeg_scan_kernel<<<n, 1024, 0, st>>>(bits, offs, nullptr, (uint32_t)G.n_blocks, (size_t)G.n_blocks, tot_bits);
+    jpeg_emit_kernel<<<dim3((G.n_blocks + 255) / 256, n), 256, 0, st>>>(s.j_coef, offs, s.j_stream, ctx->d_jtab, G, tot_bits,
+                                                                        ctx->j_err_d);
+    const unsigned cgrid = (unsigned)((chunks + 255) / 256);
+    jpeg_ffcount_kernel<<<dim3(cgrid, n), 256, 0, st>>>(s.j_stream, cnt, n_chunks, G, tot_bits);
+    jpeg_scan_kernel<<<n, 1024, 0, st>>>(cnt, ffoff, n_chunks, 0u, chunks, tot_ff);
+    jpeg_stuff_kernel<<<dim3(cgrid, n), 256, 0, st>>>(s.j_stream, ffoff, s.j_out, G, ctx->d_jtab, tot_bits, tot_ff, ctx->j_err_d);
+    jpeg_finish_kernel<<<n, 256, 0, st>>>(s.j_out, G, ctx->d_jtab, tot_bits, tot_ff, s.j_sizes_d);
+    ctx->launches += 8;
+    CK(cudaGetLastError());
+    return P2P_OK;
+}
+
+// wait for the slot's encoder and copy the files out (called WITHOUT the context lock: only stream calls)
+int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) return P2P_ERR_CUDA;
+    int rc = P2P_OK;
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long sz = s.j_sizes_h[i];
+        sizes[i] = (size_t)sz;
+        if (sz == 0 || sz > out_stride) {
+            rc = P2P_ERR_LIMIT;
+            sizes[i] = 0;
+            continue;
+        }
+        e = cudaMemcpyAsync(out_host + (size_t)i * out_stride, s.j_out + (size_t)i * G.cap_out, (size_t)sz,
+                            cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) return P2P_ERR_CUDA;
+    }
+    e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) return P2P_ERR_CUDA;
+    (void)ctx;
+    return rc;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -531,11 +632,20 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.d_rgba);
         cudaFree(s.d_out);
         cudaFree(s.d_tab);
+        cudaFree(s.j_coef);
+        cudaFree(s.j_bits);
+        cudaFree(s.j_stream);
+        cudaFree(s.j_cnt);
+        cudaFree(s.j_out);
+        cudaFree(s.j_tot);
+        if (s.j_sizes_h) cudaFreeHost(s.j_sizes_h);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);
     }
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_range);
+    cudaFree(ctx->d_jtab);
+    if (ctx->j_err_h) cudaFreeHost(ctx->j_err_h);
     cudaGetLastError();
     delete[] ctx->slots;
     delete ctx;
@@ -844,6 +954,63 @@ int p2p_view_row_range(p2p_ctx *ctx, int n_pitch, const p2p_pitch_consts *pitch,
     if (rc) return rc;
     *first_row = lo;
     *last_row = (hi + 1 < Hp) ? hi + 1 : Hp - 1;
+    return P2P_OK;
+}
+
+// ---- JPEG files of the views (the encode side of cv2.imwrite, ref :277) -------------------------------
+int p2p_encode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H, int quality,
+                    uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    if (!slot_ok(ctx, slot) || !bgr || n_images <= 0 || W <= 0 || H <= 0 || !out_host || !sizes)
+        return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    p2pjpeg::Geometry G;
+    Slot &s = ctx->slots[slot];
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        const uint8_t *d_src = bgr;
+        if (!on_device) {
+            const size_t bytes = (size_t)n_images * W * H * 3;
+            int rc = ensure(ctx, &s.d_out, &s.out_cap, bytes);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(s.d_out, bgr, bytes, cudaMemcpyHostToDevice, s.stream));
+            d_src = s.d_out;
+        }
+        int rc = enqueue_jpeg(ctx, s, d_src, n_images, W, H, quality, G);
+        if (rc) return rc;
+    }
+    cudaSetDevice(ctx->device);
+    int rc = collect_jpeg(ctx, s, n_images, G, out_host, out_stride, sizes);
+    if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a JPEG file does not fit its output buffer (out_stride) or the encoder's capacity");
+    if (rc) return fail(ctx, rc, "JPEG encoder: CUDA error");
+    return P2P_OK;
+}
+
+int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                           const p2p_pitch_consts *pitch, int W, int H, int quality, uint8_t *out_host,
+                           size_t out_stride, size_t *sizes) {
+    if (!slot_ok(ctx, slot) || !out_host || !sizes) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    p2pjpeg::Geometry G;
+    Slot &s = ctx->slots[slot];
+    const int n = n_yaw * n_pitch;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+        int rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, s.Wp);
+        if (rc) return rc;
+        CK(cudaSetDevice(ctx->device));
+        rc = ensure(ctx, &s.d_out, &s.out_cap, (size_t)n * W * H * 3);
+        if (rc) return rc;
+        Slot *sl[1] = {&s};
+        uint8_t *outs[1] = {s.d_out};
+        rc = launch_project(ctx, sl, 1, n_yaw, yaw_shift, n_pitch, pitch, W, H, outs);
+        if (rc) return rc;
+        rc = enqueue_jpeg(ctx, s, s.d_out, n, W, H, quality, G);
+        if (rc) return rc;
+    }
+    cudaSetDevice(ctx->device);
+    int rc = collect_jpeg(ctx, s, n, G, out_host, out_stride, sizes);
+    if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a JPEG file does not fit its output buffer (out_stride) or the encoder's capacity");
+    if (rc) return fail(ctx, rc, "JPEG encoder: CUDA error");
     return P2P_OK;
 }
 

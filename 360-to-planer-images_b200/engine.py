@@ -222,6 +222,43 @@ class Projector:
                                             len(consts), pc, W, H, out.ctypes.data))
         return out
 
+    # -- JPEG files (the encode side of cv2.imwrite, ref :277) ---------------------------------
+    def encode_jpeg(self, images: np.ndarray, quality: int = 95, slot: int | None = None) -> list:
+        """JPEG files (bytes) of ``images`` u8 [n, H, W, 3] (BGR), encoded on the GPU; byte-identical to
+        ``cv2.imencode('.jpg', image)`` at OpenCV's defaults."""
+        images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim == 3:
+            images = images[None]
+        n, H, W, ch = images.shape
+        if ch != 3:
+            raise ValueError("images must be [n, H, W, 3]")
+        buf = np.empty((n, W * H * 3 + 4096), np.uint8)
+        sizes = (C.c_size_t * n)()
+
+        def run(s):
+            self._ck(self.lib.p2p_encode_jpeg(self.ctx, s, images.ctypes.data, 0, n, W, H, int(quality),
+                                              buf.ctypes.data, buf.strides[0], sizes))
+
+        if slot is None:
+            with self.slots(1) as (s,):
+                run(s)
+        else:
+            run(slot)
+        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+
+    def project_jpeg(self, slot: int, shifts, consts, W: int, H: int, quality: int = 95) -> list:
+        """The n_yaw x n_pitch views of the panorama in ``slot`` as JPEG files (bytes, yaw-major): projection and
+        encoder both run on the device, only the files cross PCIe."""
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
+        n = n_yaw * n_pitch
+        pc = self._consts_array(consts)
+        buf = np.empty((n, W * H * 3 + 4096), np.uint8)
+        sizes = (C.c_size_t * n)()
+        self._ck(self.lib.p2p_project_views_jpeg(self.ctx, slot, n_yaw, shifts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 n_pitch, pc, W, H, int(quality), buf.ctypes.data, buf.strides[0], sizes))
+        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+
     def view_row_range(self, consts, W: int, H: int, Wp: int, Hp: int) -> tuple:
         """(first, last) panorama row (inclusive) the sampler reads for these pitch constants: what
         ``process_image`` transfers over PCIe (any yaw, any image; memoised per geometry)."""

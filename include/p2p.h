@@ -144,6 +144,22 @@ int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp
 int p2p_view_row_range(p2p_ctx *ctx, int n_pitch, const p2p_pitch_consts *pitch, int W, int H, int Wp, int Hp,
                        int *first_row, int *last_row);
 
+/* ---- JPEG files of the views (replaces cv2.imwrite(<name>.jpg, view), ref :277, for --output_format
+ *      jpg | jpeg, ref :400-405) ------------------------------------------------------------------------ */
+/* Baseline JPEG files of n_images images (BGR u8, H x W x 3, tightly packed; `bgr` is host memory when
+ * on_device = 0, a device pointer on ctx's device when 1), encoded on the GPU.  With quality = 95 the files are
+ * byte-identical to what cv2.imwrite / cv2.imencode('.jpg') produce with OpenCV's defaults (libjpeg-turbo:
+ * 4:2:0, integer "islow" DCT, Annex K Huffman tables, JFIF header).  File i is written to
+ * out_host + i * out_stride, its length to sizes[i].  Synchronous (returns when the files are in out_host).
+ * P2P_ERR_LIMIT if a file does not fit out_stride bytes (W * H * 3 + 2048 always suffices). */
+int p2p_encode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H,
+                    int quality, uint8_t *out_host, size_t out_stride, size_t *sizes);
+/* p2p_project_views followed by p2p_encode_jpeg without the pixels leaving the device: view (k, j) becomes
+ * file k * n_pitch + j. */
+int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
+                           const p2p_pitch_consts *pitch, int W, int H, int quality, uint8_t *out_host,
+                           size_t out_stride, size_t *sizes);
+
 /* wait for everything enqueued on `slot` (slot < 0: all slots) */
 int p2p_sync(p2p_ctx *ctx, int slot);
 /* run the slot's work on a caller supplied cudaStream_t (e.g. torch's current stream) */

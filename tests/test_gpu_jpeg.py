@@ -1,0 +1,72 @@
+"""GPU JPEG encoder (csrc/p2p_jpeg.cuh) through the C ABI: the files must be byte-identical to what the reference's
+``cv2.imwrite(<name>.jpg, view)`` (ref :277) writes - checked against the real ``cv2.imencode`` and against the oracle."""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import jpeg_model as jm
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_jpeg(img, quality=None):
+    params = [] if quality is None else [cv2.IMWRITE_JPEG_QUALITY, quality]
+    return cv2.imencode(".jpg", img, params)[1].tobytes()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (8, 8), (16, 16), (17, 33), (53, 37), (56, 40), (240, 136), (640, 480), (1000, 333)])
+@pytest.mark.parametrize("kind", ["noise", "smooth"])
+def test_encode_equals_cv2(proj, w, h, kind):
+    rng = np.random.default_rng(w * 131 + h)
+    if kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    else:
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.stack([(127 + 120 * np.sin(xx / 9.0 + c) * np.cos(yy / 6.0)).astype(np.uint8) for c in range(3)], -1)
+    got = proj.encode_jpeg(img)[0]
+    assert got == ref_jpeg(img)
+    if w * h <= 240 * 136:
+        assert got == jm.encode(img)
+
+
+def test_encode_batch_and_extremes(proj):
+    rng = np.random.default_rng(5)
+    imgs = np.stack([rng.integers(0, 256, (72, 104, 3), dtype=np.uint8), np.full((72, 104, 3), 255, np.uint8),
+                     np.zeros((72, 104, 3), np.uint8), synth.smooth(104, 72, 4),
+                     (rng.integers(0, 2, (72, 104, 3)) * 255).astype(np.uint8)])   # saturated noise: long codes, many 0xFF
+    files = proj.encode_jpeg(imgs)
+    for f, img in zip(files, imgs):
+        assert f == ref_jpeg(img)
+
+
+@pytest.mark.parametrize("quality", [1, 50, 75, 100])
+def test_encode_quality(proj, quality):
+    img = synth.smooth(200, 120, 6)
+    assert proj.encode_jpeg(img, quality=quality)[0] == ref_jpeg(img, quality)
+
+
+def test_full_size_view_equals_cv2(proj):
+    img = synth.smooth(1920, 1080, 3)
+    assert proj.encode_jpeg(img)[0] == ref_jpeg(img)
+    img = synth.noise(1920, 1080, 3)
+    assert proj.encode_jpeg(img)[0] == ref_jpeg(img)
+
+
+def test_project_views_jpeg_equals_imwrite_of_the_views(pkg, proj, tmp_path):
+    Wp, Hp, W, H, fov = 1024, 512, 240, 136, 120
+    yaws, pitches = [0, 90, 180, 270], [30, 60, 90]
+    pano = synth.smooth(Wp, Hp, 0)
+    shifts = [pkg.yaw_table(Wp, y)[2] for y in yaws]
+    consts = [pkg.pitch_constants(W, fov, p) for p in pitches]
+    with proj.slots(1) as (s,):
+        proj.upload(s, pano)
+        views = proj.project(s, shifts, consts, W, H)
+        proj.sync(s)
+        files = proj.project_jpeg(s, shifts, consts, W, H)
+    assert len(files) == len(yaws) * len(pitches)
+    for k in range(len(yaws)):
+        for j in range(len(pitches)):
+            path = tmp_path / f"v_{k}_{j}.jpg"
+            cv2.imwrite(str(path), views[k, j])          # what the reference does with the view (ref :277)
+            assert files[k * len(pitches) + j] == path.read_bytes()
