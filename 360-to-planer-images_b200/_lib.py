@@ -53,6 +53,7 @@ SIGNATURES = {
     "p2p_view_row_range": (_i, [_vp, _i, _pcp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "p2p_encode_jpeg": (_i, [_vp, _i, _u8p, _i, _i, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
     "p2p_project_views_jpeg": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
+    "p2p_process_image_jpeg": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
     "p2p_sync": (_i, [_vp, _i]),
     "p2p_set_stream": (_i, [_vp, _i, _vp]),
     "p2p_get_stream": (_i, [_vp, _i, C.POINTER(_vp)]),

@@ -988,16 +988,39 @@ int p2p_encode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, i
 int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                            const p2p_pitch_consts *pitch, int W, int H, int quality, uint8_t *out_host,
                            size_t out_stride, size_t *sizes) {
+    return p2p_process_image_jpeg(ctx, slot, nullptr, 0, 0, 0, n_yaw, yaw_shift, n_pitch, pitch, W, H, quality, out_host,
+                                  out_stride, sizes);
+}
+
+int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
+                           const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
+                           int quality, uint8_t *out_host, size_t out_stride, size_t *sizes) {
     if (!slot_ok(ctx, slot) || !out_host || !sizes) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    if (n_yaw <= 0 || n_pitch <= 0 || !pitch || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
     p2pjpeg::Geometry G;
     Slot &s = ctx->slots[slot];
     const int n = n_yaw * n_pitch;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
-        int rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, s.Wp);
-        if (rc) return rc;
         CK(cudaSetDevice(ctx->device));
+        int rc = P2P_OK;
+        if (bgr) {  // upload first: only the rows these views can touch (see p2p_process_image)
+            rc = check_dims(ctx, Wp, Hp);
+            if (rc) return rc;
+            int y0 = 0, y1 = Hp;
+            if (ctx->opt_partial && ctx->opt_interp == 0) {
+                int lo = 0, hi = 0;
+                rc = view_row_range(ctx, s.stream, n_pitch, pitch, W, H, Wp, Hp, &lo, &hi);
+                if (rc) return rc;
+                y0 = lo;
+                y1 = hi + 1;
+            }
+            rc = upload_rows(ctx, slot, bgr, Wp, Hp, row_stride, y0, y1);
+            if (rc) return rc;
+        }
+        if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+        rc = check_project_args(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out_host, s.Wp);
+        if (rc) return rc;
         rc = ensure(ctx, &s.d_out, &s.out_cap, (size_t)n * W * H * 3);
         if (rc) return rc;
         Slot *sl[1] = {&s};

@@ -111,6 +111,8 @@ class Projector:
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):
+        for pb in self.__dict__.pop("_jpeg_bufs", {}).values():
+            pb.free()
         if getattr(self, "ctx", None):
             self.lib.p2p_destroy(self.ctx)
             self.ctx = None
@@ -223,6 +225,17 @@ class Projector:
         return out
 
     # -- JPEG files (the encode side of cv2.imwrite, ref :277) ---------------------------------
+    def _jpeg_buffer(self, slot: int, n: int, W: int, H: int) -> np.ndarray:
+        """page-locked [n, W * H * 3 + 4096] file buffer of a slot (a slot is driven by one thread at a time)"""
+        cache = self.__dict__.setdefault("_jpeg_bufs", {})
+        shape = (n, W * H * 3 + 4096)
+        pb = cache.get(slot)
+        if pb is None or pb.shape != shape:
+            if pb is not None:
+                pb.free()
+            pb = cache[slot] = PinnedBuffer(shape)
+        return pb.array
+
     def encode_jpeg(self, images: np.ndarray, quality: int = 95, slot: int | None = None) -> list:
         """JPEG files (bytes) of ``images`` u8 [n, H, W, 3] (BGR), encoded on the GPU; byte-identical to
         ``cv2.imencode('.jpg', image)`` at OpenCV's defaults."""
@@ -232,19 +245,18 @@ class Projector:
         n, H, W, ch = images.shape
         if ch != 3:
             raise ValueError("images must be [n, H, W, 3]")
-        buf = np.empty((n, W * H * 3 + 4096), np.uint8)
         sizes = (C.c_size_t * n)()
 
         def run(s):
+            buf = self._jpeg_buffer(s, n, W, H)
             self._ck(self.lib.p2p_encode_jpeg(self.ctx, s, images.ctypes.data, 0, n, W, H, int(quality),
                                               buf.ctypes.data, buf.strides[0], sizes))
+            return [buf[i, :sizes[i]].tobytes() for i in range(n)]
 
         if slot is None:
             with self.slots(1) as (s,):
-                run(s)
-        else:
-            run(slot)
-        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+                return run(s)
+        return run(slot)
 
     def project_jpeg(self, slot: int, shifts, consts, W: int, H: int, quality: int = 95) -> list:
         """The n_yaw x n_pitch views of the panorama in ``slot`` as JPEG files (bytes, yaw-major): projection and
@@ -253,11 +265,49 @@ class Projector:
         n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
         n = n_yaw * n_pitch
         pc = self._consts_array(consts)
-        buf = np.empty((n, W * H * 3 + 4096), np.uint8)
+        buf = self._jpeg_buffer(slot, n, W, H)
         sizes = (C.c_size_t * n)()
         self._ck(self.lib.p2p_project_views_jpeg(self.ctx, slot, n_yaw, shifts.ctypes.data_as(C.POINTER(C.c_int32)),
                                                  n_pitch, pc, W, H, int(quality), buf.ctypes.data, buf.strides[0], sizes))
         return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+
+    def process_image_jpeg(self, slot: int, pano: np.ndarray, shifts, consts, W: int, H: int, quality: int = 95) -> list:
+        """upload (the rows the views touch) + project + JPEG-encode in one ABI call: the files (bytes, yaw-major)
+        of all n_yaw x n_pitch views.  Blocks this thread only; other slots keep running."""
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
+        n = n_yaw * n_pitch
+        pc = self._consts_array(consts)
+        buf = self._jpeg_buffer(slot, n, W, H)
+        sizes = (C.c_size_t * n)()
+        self._ck(self.lib.p2p_process_image_jpeg(self.ctx, slot, pano.ctypes.data, Wp, Hp, pano.strides[0], n_yaw,
+                                                 shifts.ctypes.data_as(C.POINTER(C.c_int32)), n_pitch, pc, W, H,
+                                                 int(quality), buf.ctypes.data, buf.strides[0], sizes))
+        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+
+    def project_image_jpeg(self, pano: np.ndarray, yaw_angles, pitch_angles, W: int, H: int, fov_deg=90,
+                           consts=None, tables=None, quality: int = 95) -> list:
+        """JPEG files [n_yaw][n_pitch] (bytes) of all views of one panorama; byte-identical to ``cv2.imwrite`` of
+        the views ``project_image`` returns.  Fractional yaws render through ``project_image`` first."""
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        yaw_angles, pitch_angles = list(yaw_angles), list(pitch_angles)
+        if consts is None:
+            consts = [pitch_constants(W, fov_deg, p) for p in pitch_angles]
+        if tables is None:
+            tables = [yaw_table(Wp, y) for y in yaw_angles]
+        if not yaw_angles or not pitch_angles:
+            return [[] for _ in yaw_angles]
+        if all(t[2] is not None for t in tables):
+            with self.slots(1) as (s,):
+                flat = self.process_image_jpeg(s, pano, [t[2] for t in tables], consts, W, H, quality)
+        else:
+            views = self.project_image(pano, yaw_angles, pitch_angles, W, H, fov_deg, consts=consts, tables=tables)
+            flat = self.encode_jpeg(views.reshape(-1, H, W, 3), quality)
+        n_p = len(pitch_angles)
+        return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
 
     def view_row_range(self, consts, W: int, H: int, Wp: int, Hp: int) -> tuple:
         """(first, last) panorama row (inclusive) the sampler reads for these pitch constants: what

@@ -16,7 +16,9 @@ the GPU path needs: the quantised yaw *column table* instead of a full-size (U, 
 three f32 *pitch constants* instead of a full-size map (the map itself is evaluated per pixel
 inside the kernel and never stored).
 
-cv2 is used for file decode / encode only (``imread`` :244, ``imwrite`` :277), as in the reference.
+cv2 is used for file decode (``imread`` :244) and for PNG encode (``imwrite`` :277), as in the reference.
+With ``--output_format jpg|jpeg`` the files are encoded on the GPU (``csrc/p2p_jpeg.cuh``): byte-identical to what
+``cv2.imwrite`` writes at OpenCV's defaults, without the pixels ever crossing PCIe.
 """
 from __future__ import annotations
 
@@ -87,6 +89,34 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
                               consts=consts, tables=tables)
 
 
+def _is_jpeg(output_format) -> bool:
+    return str(output_format).lower() in ("jpg", "jpeg")
+
+
+def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
+    """[n_yaw][n_pitch] JPEG files (bytes) through the device projection + encoder, using the module caches."""
+    pano = _engine._as_u8_image(pano_image, "pano_image")
+    Hp, Wp, _ = pano.shape
+    consts = [get_pitch_mapping(output_width, output_height, p, Wp, Hp, fov_deg) for p in pitch_angles]
+    tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
+    return proj.project_image_jpeg(pano, yaw_angles, pitch_angles, output_width, output_height, fov_deg,
+                                   consts=consts, tables=tables)
+
+
+def _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height, output_format,
+                executor):
+    """Write already-encoded views (one task per yaw, reference file names, ref :275); returns the futures."""
+
+    def save_yaw(k):
+        for i in range(len(pitch_angles)):
+            out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angles[k]}"
+                            f"_pitch_{pitch_angles[i]}.{output_format}")
+            (output_dir / out_filename).write_bytes(files[k][i])
+            logging.debug(f"Saved {output_dir / out_filename}")
+
+    return [executor.submit(save_yaw, k) for k in range(len(yaw_angles))]
+
+
 def process_yaw_and_pitchs(pano_image, yaw_angle, pitch_angles, output_width, output_height, fov_deg=90):
     """Process a single yaw angle and multiple pitch angles, returning all slices (ref :181-221)."""
     logging.debug(f"[Yaw/Pitch] Starting processing for yaw_angle={yaw_angle}")
@@ -134,16 +164,26 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
     base_name = input_image_path.stem
     yaw_angles = list(yaw_angles)
     pitch_angles = list(pitch_angles)
+    jpeg = _is_jpeg(output_format)
     try:
-        views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+        if jpeg:  # projected and encoded on the device: only the files come back
+            files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
+                                  fov_deg)
+        else:
+            views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
+                             fov_deg)
     except Exception as e:
         for yaw_angle in yaw_angles:
             logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
         return
 
     with ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
-        tasks = _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width,
-                            output_height, output_format, executor)
+        if jpeg:
+            tasks = _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
+                                output_format, executor)
+        else:
+            tasks = _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width,
+                                output_height, output_format, executor)
         for future, yaw_angle in zip(tasks, yaw_angles):
             try:
                 future.result()
@@ -184,9 +224,61 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
     num_workers = max(1, int(num_workers))
     W, H = int(output_width), int(output_height)
 
+    def run_device_jpeg(dev, files):
+        """JPEG output: every image is one synchronous device call (upload rows -> project -> encode -> files) on
+        its own slot; ``inflight`` host threads keep that many slots busy, decoders read ahead, writers only write."""
+        proj = get_projector(dev)
+        n_in = max(1, min(int(inflight), proj.n_slots - 1))
+
+        def one(f, pano):
+            try:
+                files_ = _project_jpeg(proj, pano, yaw_angles, pitch_angles, W, H, fov_deg)
+            except Exception as e:
+                for yaw in yaw_angles:
+                    logging.error(f"Error processing yaw_angle {yaw}: {e}")
+                return
+            for fut, yaw in zip(_save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
+                                            writers), yaw_angles):
+                try:
+                    fut.result()
+                except Exception as e:
+                    logging.error(f"Error processing yaw_angle {yaw}: {e}")
+
+        with ThreadPoolExecutor(max_workers=num_workers) as readers, \
+                ThreadPoolExecutor(max_workers=num_workers) as writers, \
+                ThreadPoolExecutor(max_workers=n_in) as gpu:
+            from collections import deque
+
+            ahead, running = deque(), deque()
+            it = iter(files)
+
+            def refill():
+                while len(ahead) < n_in + 1:
+                    f = next(it, None)
+                    if f is None:
+                        return
+                    logging.info(f"Loading image: {f}")
+                    ahead.append((f, readers.submit(cv2.imread, str(f))))
+
+            refill()
+            while ahead:
+                f, fut = ahead.popleft()
+                refill()
+                pano = fut.result()
+                if pano is None:
+                    logging.error(f"Failed to read image: {f}")
+                    continue
+                while len(running) >= n_in:
+                    running.popleft().result()
+                running.append(gpu.submit(one, f, pano))
+            while running:
+                running.popleft().result()
+
     def run_device(dev, files):
         from collections import deque
 
+        if _is_jpeg(output_format):
+            return run_device_jpeg(dev, files)
         proj = get_projector(dev)
         n_in = max(1, min(int(inflight), proj.n_slots - 1))
         out_bufs = [_engine.PinnedBuffer((len(yaw_angles), len(pitch_angles), H, W, 3)) for _ in range(n_in)]

@@ -160,6 +160,13 @@ int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw
                            const p2p_pitch_consts *pitch, int W, int H, int quality, uint8_t *out_host,
                            size_t out_stride, size_t *sizes);
 
+/* upload (only the rows the views can touch, like p2p_process_image) + project + encode in one call: what the
+ * reference does per image with --output_format jpg between cv2.imread (ref :244) and its cv2.imwrite calls (:277).
+ * Synchronous for this slot; other slots / threads keep running (the context lock is not held while waiting). */
+int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
+                           const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
+                           int quality, uint8_t *out_host, size_t out_stride, size_t *sizes);
+
 /* wait for everything enqueued on `slot` (slot < 0: all slots) */
 int p2p_sync(p2p_ctx *ctx, int slot);
 /* run the slot's work on a caller supplied cudaStream_t (e.g. torch's current stream) */

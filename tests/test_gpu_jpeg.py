@@ -70,3 +70,34 @@ def test_project_views_jpeg_equals_imwrite_of_the_views(pkg, proj, tmp_path):
             path = tmp_path / f"v_{k}_{j}.jpg"
             cv2.imwrite(str(path), views[k, j])          # what the reference does with the view (ref :277)
             assert files[k * len(pitches) + j] == path.read_bytes()
+
+
+def test_front_end_jpg_files_equal_imwrite_of_the_views(pkg, tmp_path):
+    """``--output_format jpg``: single-image path, directory pipeline and CLI write the bytes ``cv2.imwrite`` would write
+    for the very views the png path produces (integer-roll and fractional yaws)."""
+    src = tmp_path / "in"
+    src.mkdir()
+    sizes = [(1024, 512), (1000, 500), (1024, 512)]
+    panos = {}
+    for i, (Wp, Hp) in enumerate(sizes):
+        panos[f"p{i}"] = synth.smooth(Wp, Hp, 10 + i)
+        assert cv2.imwrite(str(src / f"p{i}.png"), panos[f"p{i}"])
+    W, H, fov, yaws, pitches = 200, 120, 100, [0, 90, 30], [60, 120]    # yaw 30 is fractional on Wp = 1000 / 1024
+    out_dir, out_single = tmp_path / "dir", tmp_path / "single"
+    pkg.main(str(src), str(out_dir), yaws, pitches, W, H, num_workers=3, output_format="jpg", fov_deg=fov)
+    out_single.mkdir()
+    pkg.process_single_image(src / "p1.png", out_single, yaws, pitches, W, H, num_workers=2, output_format="jpeg", fov_deg=fov)
+    names = sorted(p.name for p in out_dir.iterdir())
+    assert len(names) == len(sizes) * len(yaws) * len(pitches)
+    for base, pano in panos.items():
+        for y in yaws:
+            views = pkg.process_yaw_and_pitchs(pano, y, pitches, W, H, fov)
+            for p, view in zip(pitches, views):
+                want = cv2.imencode(".jpg", view)[1].tobytes()
+                assert (out_dir / f"{base}_{W}x{H}_yaw_{y}_pitch_{p}.jpg").read_bytes() == want, (base, y, p)
+                if base == "p1":
+                    assert (out_single / f"{base}_{W}x{H}_yaw_{y}_pitch_{p}.jpeg").read_bytes() == want
+    out_cli = tmp_path / "cli"
+    pkg.cli(["--input_path", str(src / "p0.png"), "--output_path", str(out_cli), "--output_format", "jpg", "--FOV", str(fov),
+             "--output_width", str(W), "--output_height", str(H), "--yaw_angles", "90", "--pitch_angles", "60"])
+    assert (out_cli / f"p0_{W}x{H}_yaw_90_pitch_60.jpg").read_bytes() == (out_dir / f"p0_{W}x{H}_yaw_90_pitch_60.jpg").read_bytes()
