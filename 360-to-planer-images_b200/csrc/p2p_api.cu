@@ -497,8 +497,8 @@ int enqueue_jpeg(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int 
         CK(cudaMemcpy(ctx->d_jtab, &T, sizeof(T), cudaMemcpyHostToDevice));
         ctx->jW = W; ctx->jH = H; ctx->jQ = quality;
     }
-    const size_t nb = (size_t)n * G.n_blocks, chunks = G.cap_bits_words / 4;
-    int rc = ensure(ctx, &s.j_coef, &s.j_coef_cap, nb * 64 * sizeof(int16_t));
+    const size_t nb = (size_t)n * G.blk_stride, chunks = G.cap_bits_words / 4;
+    int rc = ensure(ctx, &s.j_coef, &s.j_coef_cap, (size_t)n * G.n_blocks * 64 * sizeof(int16_t));
     if (!rc) rc = ensure(ctx, &s.j_bits, &s.j_bits_cap, 2 * nb * sizeof(uint32_t));
     if (!rc) rc = ensure(ctx, &s.j_stream, &s.j_stream_cap, (size_t)n * G.cap_bits_words * sizeof(uint32_t));
     if (!rc) rc = ensure(ctx, &s.j_cnt, &s.j_cnt_cap, 2 * (size_t)n * chunks * sizeof(uint32_t));
@@ -519,9 +519,9 @@ int enqueue_jpeg(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int 
     uint32_t *n_chunks = reinterpret_cast<uint32_t *>(s.j_tot + 2 * (size_t)n);
     cudaStream_t st = s.stream;
     CK(cudaMemsetAsync(s.j_stream, 0, (size_t)n * G.cap_bits_words * sizeof(uint32_t), st));
-    jpeg_dct_kernel<<<dim3((G.n_mcu + kMcuPerCta - 1) / kMcuPerCta, n), 64 * kMcuPerCta, 0, st>>>(d_bgr, s.j_coef, ctx->d_jtab, G);
+    jpeg_dct_kernel<<<dim3((G.mcux + kMcuPerCta - 1) / kMcuPerCta, G.mcuy, n), 64 * kMcuPerCta, 0, st>>>(d_bgr, s.j_coef, ctx->d_jtab, G);
     jpeg_size_kernel<<<dim3((G.n_blocks + 255) / 256, n), 256, 0, st>>>(s.j_coef, bits, ctx->d_jtab, G);
-    jpeg_scan_kernel<<<n, 1024, 0, st>>>(bits, offs, nullptr, (uint32_t)G.n_blocks, (size_t)G.n_blocks, tot_bits);
+    jpeg_scan_kernel<<<n, 1024, 0, st>>>(bits, offs, nullptr, (uint32_t)G.n_blocks, (size_t)G.blk_stride, tot_bits);
     jpeg_emit_kernel<<<dim3((G.n_blocks + 255) / 256, n), 256, 0, st>>>(s.j_coef, offs, s.j_stream, ctx->d_jtab, G, tot_bits,
                                                                         ctx->j_err_d);
     const unsigned cgrid = (unsigned)((chunks + 255) / 256);

@@ -10,7 +10,7 @@
 //   jccoefct.c dummy edge blocks (zero AC, previous DC)   jchuff.c    Huffman coding, 0xFF stuffing, 1-bit padding
 //
 // Pipeline (all images of a call in one grid each, blockIdx.y / z = image):
-//   jpeg_dct_kernel    BGR -> Y / Cb / Cr MCU (16 x 16 px) in shared memory -> FDCT -> quantised coefficients in
+//   jpeg_dct_kernel    BGR tile staged in shared memory -> Y / Cb / Cr MCUs (16 x 16 px) -> FDCT -> quantised coefficients in
 //                      zigzag order, stored in scan order (6 blocks per MCU: Y00 Y01 Y10 Y11 Cb Cr)
 //   jpeg_size_kernel   bits of every block's Huffman code (DC difference against the previous block of its component)
 //   jpeg_scan_kernel   exclusive prefix sum per image -> bit offset of every block
@@ -28,7 +28,8 @@ constexpr int kMcuPerCta = 4;        // jpeg_dct_kernel: 64 threads per MCU
 constexpr int kHeaderMax = 640;      // SOI + APP0 + 2 DQT + SOF0 + 4 DHT + SOS = 623 bytes
 
 struct Tables {
-    uint16_t div_y[64], div_c[64];   // 8 * q, natural order (jcdctmgr.c: the islow FDCT output is scaled by 8)
+    uint16_t div_y[64], div_c[64];   // d = 8 * q, natural order (jcdctmgr.c: the islow FDCT output is scaled by 8)
+    uint32_t rcp_y[64], rcp_c[64];   // floor(2^32 / d) + 1: umulhi(n, rcp) == n / d exactly for n < 2^32 / d (n < 2^18 here)
     uint32_t dc[2][16];              // (code << 8) | length, by category
     uint32_t ac[2][256];             // (code << 8) | length, by (run << 4) | size
     uint8_t header[kHeaderMax];
@@ -38,6 +39,7 @@ struct Tables {
 struct Geometry {
     int W, H;
     int mcux, mcuy, n_mcu, n_blocks; // per image
+    int blk_stride;                  // n_blocks rounded up to 4: per-image stride of the bits / offsets arrays
     int ybw, ybh;                    // real luma blocks (ceil(W / 8), ceil(H / 8)); chroma blocks are always real
     int cw, ch;                      // chroma plane size (ceil(W / 2), ceil(H / 2))
     size_t img_stride;               // bytes between input images (W * H * 3)
@@ -84,44 +86,73 @@ __device__ __forceinline__ void fdct_pass(int *d) {
 }
 
 // ---- colour conversion + downsample + FDCT + quantisation ----------------------------------------------------
-// grid: x = ceil(n_mcu / kMcuPerCta), y = image; block: 64 threads per MCU.
+// grid: x = ceil(mcux / kMcuPerCta), y = MCU row, z = image; block: 64 threads per MCU, kMcuPerCta MCUs side by side.
+// The CTA first stages its 16 rows x (kMcuPerCta * 16) pixels in shared memory with coalesced word loads (edge
+// replication = clamped coordinates on the slow byte path), converts from there, and writes its coefficients -
+// contiguous in scan order - with 16-byte stores.
+constexpr int kTileBytes = kMcuPerCta * 16 * 3;   // bytes per staged pixel row
+
 __global__ void __launch_bounds__(64 * kMcuPerCta)
 jpeg_dct_kernel(const uint8_t *__restrict__ bgr, int16_t *__restrict__ coef, const Tables *__restrict__ T, const Geometry G) {
-    __shared__ int s_blk[kMcuPerCta][6][64];  // level-shifted samples, then row-pass results
-    __shared__ int s_dc[kMcuPerCta][6];
+    __shared__ __align__(16) uint8_t s_px[16][kTileBytes];
+    __shared__ int s_blk[kMcuPerCta][6][64];            // level-shifted samples, then row-pass results
+    __shared__ __align__(16) int16_t s_out[kMcuPerCta][6][64];
     const int lm = threadIdx.x >> 6, tid = threadIdx.x & 63;
-    const int mcu = blockIdx.x * kMcuPerCta + lm;
-    const int img = blockIdx.y;
-    const bool live = mcu < G.n_mcu;
-    const int my = live ? mcu / G.mcux : 0, mx = live ? mcu - my * G.mcux : 0;
+    const int my = blockIdx.y, img = blockIdx.z;
+    const int mx = blockIdx.x * kMcuPerCta + lm;
+    const bool live = mx < G.mcux;
+    const int mcu = my * G.mcux + mx;
     const uint8_t *src = bgr + (size_t)img * G.img_stride;
+
+    // stage: tile row r = image row min(my * 16 + r, H - 1), tile byte c = pixel x0 + c / 3 (clamped), channel c % 3
+    {
+        const int x0 = blockIdx.x * kMcuPerCta * 16;
+        const bool fast = (x0 + kMcuPerCta * 16 <= G.W) && (((size_t)G.W * 3) % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+        constexpr int kWords = kTileBytes / 4;
+        for (int i = threadIdx.x; i < 16 * kWords; i += blockDim.x) {
+            const int r = i / kWords, w = i - r * kWords;
+            int y = my * 16 + r;
+            y = (y < G.H) ? y : G.H - 1;
+            const uint8_t *rowp = src + (size_t)y * G.W * 3;
+            uint32_t v;
+            if (fast) {
+                v = __ldg(reinterpret_cast<const uint32_t *>(rowp + (size_t)x0 * 3) + w);
+            } else {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = w * 4 + k;
+                    int x = x0 + c / 3;
+                    x = (x < G.W) ? x : G.W - 1;
+                    v |= (uint32_t)rowp[(size_t)x * 3 + (c % 3)] << (8 * k);
+                }
+            }
+            *reinterpret_cast<uint32_t *>(&s_px[r][w * 4]) = v;
+        }
+    }
+    __syncthreads();
 
     if (live) {
         // thread = one chroma sample = one 2 x 2 luma quad
         const int qx = tid & 7, qy = tid >> 3;
-        const int cx = mx * 8 + qx;                       // chroma column (input columns clamp: expand_right_edge)
+        const int cx = mx * 8 + qx;
         int cy = my * 8 + qy;                             // chroma row: the DOWNSAMPLED plane is replicated downwards
         cy = (cy < G.ch) ? cy : G.ch - 1;
+        const int rc = 2 * cy - my * 16;                  // its two input rows inside the tile (always 0 .. 14)
         int sb = 0, sr = 0;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                int x = 2 * cx + dx;
-                x = (x < G.W) ? x : G.W - 1;
-                // chroma rows: 2 cy + dy of the row-group padded input (odd H: the last row is duplicated)
-                int yc = 2 * cy + dy;
-                yc = (yc < G.H) ? yc : G.H - 1;
-                const uint8_t *pc = src + ((size_t)yc * G.W + x) * 3;
+                const int lx = 2 * qx + dx;
+                const uint8_t *pc = &s_px[rc + dy][(lm * 16 + lx) * 3];
                 const int b = pc[0], g = pc[1], r = pc[2];
                 sb += (-11059 * r - 21709 * g + 32768 * b + (128 << 16) + 32767) >> 16;
                 sr += (32768 * r - 27439 * g - 5329 * b + (128 << 16) + 32767) >> 16;
-                // luma rows clamp at the input level
-                int yl = my * 16 + 2 * qy + dy;
-                yl = (yl < G.H) ? yl : G.H - 1;
-                const uint8_t *pl = src + ((size_t)yl * G.W + x) * 3;
+                const int ly = 2 * qy + dy;
+                const uint8_t *pl = &s_px[ly][(lm * 16 + lx) * 3];
                 const int yv = (19595 * (int)pl[2] + 38470 * (int)pl[1] + 7471 * (int)pl[0] + 32768) >> 16;
-                const int ly = 2 * qy + dy, lx = 2 * qx + dx;                 // position in the 16 x 16 luma MCU
                 s_blk[lm][(ly >> 3) * 2 + (lx >> 3)][(ly & 7) * 8 + (lx & 7)] = yv - 128;
             }
         }
@@ -151,28 +182,35 @@ jpeg_dct_kernel(const uint8_t *__restrict__ bgr, int16_t *__restrict__ coef, con
         bool real = true;
         if (blk < 4) real = (mx * 2 + (blk & 1) < G.ybw) && (my * 2 + (blk >> 1) < G.ybh);
         const uint16_t *div = (blk < 4) ? T->div_y : T->div_c;
-        int16_t *out = coef + ((size_t)img * G.n_blocks + (size_t)mcu * 6 + blk) * 64;
+        const uint32_t *rcp = (blk < 4) ? T->rcp_y : T->rcp_c;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int nat = i * 8 + lane8;
             const int dv = div[nat];
-            const int a = (abs(d[i]) + (dv >> 1)) / dv;
-            const int q = real ? ((d[i] < 0) ? -a : a) : 0;
-            out[kZigzagPos[nat]] = (int16_t)q;
-            if (nat == 0) s_dc[lm][blk] = q;
+            const int a = (int)__umulhi((uint32_t)(abs(d[i]) + (dv >> 1)), rcp[nat]);   // (|x| + d / 2) / d
+            s_out[lm][blk][kZigzagPos[nat]] = (int16_t)(real ? ((d[i] < 0) ? -a : a) : 0);
         }
     }
     __syncthreads();
     if (live && tid == 0) {
         // dummy luma blocks carry the DC of the previous block of the MCU buffer
-        int16_t *out = coef + ((size_t)img * G.n_blocks + (size_t)mcu * 6) * 64;
-        int prev = s_dc[lm][0];
+        int prev = s_out[lm][0][0];
         for (int b = 1; b < 4; ++b) {
             const bool real = (mx * 2 + (b & 1) < G.ybw) && (my * 2 + (b >> 1) < G.ybh);
-            if (!real) out[b * 64] = (int16_t)prev;
-            else prev = s_dc[lm][b];
+            if (!real) s_out[lm][b][0] = (int16_t)prev;
+            else prev = s_out[lm][b][0];
         }
     }
+    __syncthreads();
+    // the CTA's MCUs are consecutive in scan order: one contiguous run of 768 bytes per MCU
+    {
+        const int n_live = (G.mcux - blockIdx.x * kMcuPerCta < kMcuPerCta) ? G.mcux - blockIdx.x * kMcuPerCta : kMcuPerCta;
+        const int n16 = n_live * 6 * 64 * 2 / 16;
+        uint4 *dst = reinterpret_cast<uint4 *>(coef + ((size_t)img * G.n_blocks + (size_t)(my * G.mcux + blockIdx.x * kMcuPerCta) * 6) * 64);
+        const uint4 *so = reinterpret_cast<const uint4 *>(&s_out[0][0][0]);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = so[i];
+    }
+    (void)mcu;
 }
 
 // ---- entropy coding ---------------------------------------------------------------------------------------------
@@ -224,49 +262,68 @@ jpeg_size_kernel(const int16_t *__restrict__ coef, uint32_t *__restrict__ bits, 
         }
     }
     if (run) total += s_ac[t][0] & 0xFF;
-    bits[(size_t)img * G.n_blocks + g] = total;
+    bits[(size_t)img * G.blk_stride + g] = total;
 }
 
-// exclusive prefix sum of n items per image (one CTA per image); out[i] = sum of in[0 .. i), total[img] = sum
+// exclusive prefix sum of n items per image (one CTA per image); out[i] = sum of in[0 .. i), total[img] = sum.
+// Tiles of 4096 items: every thread takes 4 consecutive items (one 16-byte load; `stride` and the buffers are
+// 16-byte aligned), warp shuffles + one shared-memory hop scan the tile, a running carry links the tiles.
 __global__ void __launch_bounds__(1024)
 jpeg_scan_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, const uint32_t *__restrict__ n_per_image,
                  uint32_t n_fixed, size_t stride, unsigned long long *__restrict__ total) {
-    __shared__ unsigned long long s_warp[32];
+    __shared__ uint32_t s_warp[32];
+    __shared__ unsigned long long s_carry;
     const int img = blockIdx.x;
     const uint32_t n = n_per_image ? n_per_image[img] : n_fixed;
     const uint32_t *src = in + (size_t)img * stride;
     uint32_t *dst = out + (size_t)img * stride;
-    const uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t lo = threadIdx.x * ipt, hi = (lo + ipt < n) ? lo + ipt : n;
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += src[i];
-    // block-level exclusive scan of the per-thread sums
-    unsigned long long inc = sum;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_warp[warp] = inc;
+    if (threadIdx.x == 0) s_carry = 0ull;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = s_warp[lane];
+    for (uint32_t base = 0; base < n; base += 4096u) {
+        const uint32_t i0 = base + threadIdx.x * 4u;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + 3u < n) {
+            v = *reinterpret_cast<const uint4 *>(src + i0);
+        } else {
+            if (i0 < n) v.x = src[i0];
+            if (i0 + 1u < n) v.y = src[i0 + 1u];
+            if (i0 + 2u < n) v.z = src[i0 + 2u];
+        }
+        const uint32_t sum = v.x + v.y + v.z + v.w;     // a tile holds < 2^32 (4096 items of < 2^20 each)
+        uint32_t inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += v;
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
         }
-        s_warp[lane] = w;
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        const uint32_t excl = (uint32_t)carry + (inc - sum) + (warp ? s_warp[warp - 1] : 0u);
+        const uint4 o4 = make_uint4(excl, excl + v.x, excl + v.x + v.y, excl + v.x + v.y + v.z);
+        if (i0 + 3u < n) {
+            *reinterpret_cast<uint4 *>(dst + i0) = o4;
+        } else {
+            if (i0 < n) dst[i0] = o4.x;
+            if (i0 + 1u < n) dst[i0 + 1u] = o4.y;
+            if (i0 + 2u < n) dst[i0 + 2u] = o4.z;
+        }
+        __syncthreads();                                 // everyone has read s_carry and s_warp
+        if (threadIdx.x == 0) s_carry = carry + s_warp[31];
+        __syncthreads();
     }
-    __syncthreads();
-    unsigned long long base = inc - sum + (warp ? s_warp[warp - 1] : 0ull);
-    for (uint32_t i = lo; i < hi; ++i) {
-        const uint32_t v = src[i];
-        dst[i] = (uint32_t)base;
-        base += v;
-    }
-    if (threadIdx.x == blockDim.x - 1) total[img] = s_warp[31];
+    if (threadIdx.x == 0) total[img] = s_carry;
 }
 
 struct BitSink {
@@ -317,7 +374,7 @@ jpeg_emit_kernel(const int16_t *__restrict__ coef, const uint32_t *__restrict__ 
     const int16_t *c = coef + ((size_t)img * G.n_blocks + g) * 64;
     const int p = pred_block(mcu, k);
     const int pred = (p < 0) ? 0 : coef[((size_t)img * G.n_blocks + p) * 64];
-    const uint32_t off = offs[(size_t)img * G.n_blocks + g];
+    const uint32_t off = offs[(size_t)img * G.blk_stride + g];
     BitSink bs;
     bs.words = stream + (size_t)img * G.cap_bits_words;
     bs.acc = 0;

@@ -81,6 +81,8 @@ inline void build_tables(int W, int H, int quality, Tables &T) {
         qc[i] = (uint8_t)b;
         T.div_y[i] = (uint16_t)(a * 8);
         T.div_c[i] = (uint16_t)(b * 8);
+        T.rcp_y[i] = (uint32_t)((1ull << 32) / (unsigned long long)(a * 8)) + 1u;
+        T.rcp_c[i] = (uint32_t)((1ull << 32) / (unsigned long long)(b * 8)) + 1u;
     }
     derive(kDcLumaBits, kDcVals, T.dc[0]);
     derive(kDcChromaBits, kDcVals, T.dc[1]);
@@ -117,6 +119,7 @@ inline Geometry make_geometry(int W, int H) {
     G.mcuy = (H + 15) / 16;
     G.n_mcu = G.mcux * G.mcuy;
     G.n_blocks = G.n_mcu * 6;
+    G.blk_stride = (G.n_blocks + 3) & ~3;
     G.ybw = (W + 7) / 8;
     G.ybh = (H + 7) / 8;
     G.cw = (W + 1) / 2;
@@ -124,7 +127,7 @@ inline Geometry make_geometry(int W, int H) {
     G.img_stride = (size_t)W * H * 3;
     // capacity: the raw image size (a q95 file of white noise needs 1.2 bytes / pixel; the kernels report overflow)
     const size_t raw = (size_t)G.mcux * 16 * G.mcuy * 16 * 3 + 1024;
-    G.cap_bits_words = ((raw / 4) + 3) & ~(size_t)3;
+    G.cap_bits_words = ((raw / 4) + 15) & ~(size_t)15;   // 16-byte chunks; chunk arrays stay 16-byte aligned per image
     G.cap_out = (raw + kHeaderMax + 16 + 15) & ~(size_t)15;
     return G;
 }
