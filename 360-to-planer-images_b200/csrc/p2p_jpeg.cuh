@@ -47,10 +47,17 @@ struct Geometry {
     size_t cap_out;                  // bytes of the output file buffer per image
 };
 
-__constant__ uint8_t kZigzagPos[64] = {  // natural index -> zigzag position
-    0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53,
-    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58,
-    62, 63};
+// natural index -> zigzag position, by column: kZigzagCol[c][r] = position of natural index r * 8 + c (one 8-byte load
+// per thread of the column pass)
+__device__ const uint8_t kZigzagCol[8][8] = {
+    {0, 2, 3, 9, 10, 20, 21, 35},
+    {1, 4, 8, 11, 19, 22, 34, 36},
+    {5, 7, 12, 18, 23, 33, 37, 48},
+    {6, 13, 17, 24, 32, 38, 47, 49},
+    {14, 16, 25, 31, 39, 46, 50, 57},
+    {15, 26, 30, 40, 45, 51, 56, 58},
+    {27, 29, 41, 44, 52, 55, 59, 62},
+    {28, 42, 43, 53, 54, 60, 61, 63}};
 
 // ---- jfdctint.c: one 8-point pass (exact integers) ---------------------------------------------------------
 template <bool FIRST>
@@ -95,7 +102,8 @@ constexpr int kTileBytes = kMcuPerCta * 16 * 3;   // bytes per staged pixel row
 __global__ void __launch_bounds__(64 * kMcuPerCta)
 jpeg_dct_kernel(const uint8_t *__restrict__ bgr, int16_t *__restrict__ coef, const Tables *__restrict__ T, const Geometry G) {
     __shared__ __align__(16) uint8_t s_px[16][kTileBytes];
-    __shared__ int s_blk[kMcuPerCta][6][64];            // level-shifted samples, then row-pass results
+    __shared__ int s_blk[kMcuPerCta][6][8 * 9];         // level-shifted samples, then row-pass results; rows padded to 9
+                                                        // words: the row / column passes hit 32 different banks
     __shared__ __align__(16) int16_t s_out[kMcuPerCta][6][64];
     const int lm = threadIdx.x >> 6, tid = threadIdx.x & 63;
     const int my = blockIdx.y, img = blockIdx.z;
@@ -153,42 +161,44 @@ jpeg_dct_kernel(const uint8_t *__restrict__ bgr, int16_t *__restrict__ coef, con
                 const int ly = 2 * qy + dy;
                 const uint8_t *pl = &s_px[ly][(lm * 16 + lx) * 3];
                 const int yv = (19595 * (int)pl[2] + 38470 * (int)pl[1] + 7471 * (int)pl[0] + 32768) >> 16;
-                s_blk[lm][(ly >> 3) * 2 + (lx >> 3)][(ly & 7) * 8 + (lx & 7)] = yv - 128;
+                s_blk[lm][(ly >> 3) * 2 + (lx >> 3)][(ly & 7) * 9 + (lx & 7)] = yv - 128;
             }
         }
         const int bias = (cx & 1) ? 2 : 1;
-        s_blk[lm][4][qy * 8 + qx] = ((sb + bias) >> 2) - 128;
-        s_blk[lm][5][qy * 8 + qx] = ((sr + bias) >> 2) - 128;
+        s_blk[lm][4][qy * 9 + qx] = ((sb + bias) >> 2) - 128;
+        s_blk[lm][5][qy * 9 + qx] = ((sr + bias) >> 2) - 128;
     }
     __syncthreads();
     const int blk = tid >> 3, lane8 = tid & 7;            // 48 threads: block 0..5, row / column 0..7
     int d[8];
     if (live && blk < 6) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = s_blk[lm][blk][lane8 * 8 + i];
+        for (int i = 0; i < 8; ++i) d[i] = s_blk[lm][blk][lane8 * 9 + i];
         fdct_pass<true>(d);
     }
     __syncthreads();
     if (live && blk < 6) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s_blk[lm][blk][lane8 * 8 + i] = d[i];
+        for (int i = 0; i < 8; ++i) s_blk[lm][blk][lane8 * 9 + i] = d[i];
     }
     __syncthreads();
     if (live && blk < 6) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = s_blk[lm][blk][i * 8 + lane8];
+        for (int i = 0; i < 8; ++i) d[i] = s_blk[lm][blk][i * 9 + lane8];
         fdct_pass<false>(d);
         // real block?  (jccoefct.c: blocks past the real block grid of the component are dummies)
         bool real = true;
         if (blk < 4) real = (mx * 2 + (blk & 1) < G.ybw) && (my * 2 + (blk >> 1) < G.ybh);
         const uint16_t *div = (blk < 4) ? T->div_y : T->div_c;
         const uint32_t *rcp = (blk < 4) ? T->rcp_y : T->rcp_c;
+        const uint2 zz2 = __ldg(reinterpret_cast<const uint2 *>(&kZigzagCol[lane8][0]));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int nat = i * 8 + lane8;
+            const int zpos = (int)(((i < 4) ? (zz2.x >> (8 * i)) : (zz2.y >> (8 * (i - 4)))) & 0xFFu);
             const int dv = div[nat];
             const int a = (int)__umulhi((uint32_t)(abs(d[i]) + (dv >> 1)), rcp[nat]);   // (|x| + d / 2) / d
-            s_out[lm][blk][kZigzagPos[nat]] = (int16_t)(real ? ((d[i] < 0) ? -a : a) : 0);
+            s_out[lm][blk][zpos] = (int16_t)(real ? ((d[i] < 0) ? -a : a) : 0);
         }
     }
     __syncthreads();
