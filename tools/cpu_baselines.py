@@ -1,0 +1,102 @@
+"""CPU baselines beside the GPU numbers (SURVEY 8d "CPU baseline beside it"), run on the GPU box's host cores.
+
+ (i)  compute only: the oracle port of the reference (NumPy maps + cv2.remap, one thread-pool task per yaw,
+      ref :252-265) on C1, C2 and C4, cold (map precompute included) and warm map caches;
+ (ii) files to files for C2: one 8192x4096 PNG in tmpfs -> 12 views written as png / jpg, the reference's
+      flow (imread :244 -> views -> imwrite :277, saved in submit order) against this framework's front end.
+
+    python tools/cpu_baselines.py > gpurun_out/cpu_baselines.jsonl
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as g  # noqa: E402
+from oracle import ref_port, synth  # noqa: E402
+
+CONFIGS = {
+    "C1": dict(Wp=2048, Hp=1024, W=640, H=480, fov=90, yaws=[0], pitches=[90], warm_reps=20),
+    "C2": dict(Wp=8192, Hp=4096, W=1920, H=1080, fov=120, yaws=[0, 90, 180, 270], pitches=[30, 60, 90], warm_reps=8),
+    "C4": dict(Wp=16384, Hp=8192, W=3840, H=2160, fov=100, yaws=[0, 90, 180, 270], pitches=[30, 60, 90], warm_reps=2),
+}
+
+
+def main():
+    import cv2
+
+    info = {"cores": os.cpu_count(), "cv2_threads": cv2.getNumThreads(), "numpy": np.__version__, "cv2": cv2.__version__,
+            "workers": ref_port.default_workers()}
+    print(json.dumps({"host": info}), flush=True)
+    for name, c in CONFIGS.items():
+        pano = synth.noise(c["Wp"], c["Hp"], 0)
+        px = len(c["yaws"]) * len(c["pitches"]) * c["W"] * c["H"]
+        ref_port.clear_caches()
+        t0 = time.perf_counter()
+        ref_port.process_image_views(pano, c["yaws"], c["pitches"], c["W"], c["H"], c["fov"])
+        cold = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(c["warm_reps"]):
+            ref_port.process_image_views(pano, c["yaws"], c["pitches"], c["W"], c["H"], c["fov"])
+        warm = (time.perf_counter() - t0) / c["warm_reps"]
+        print(json.dumps({"config": name, "kind": "compute only, oracle port of the reference", "views": px // (c["W"] * c["H"]),
+                          "cold_s": cold, "cold_mpix_s": px / cold / 1e6, "warm_s": warm, "warm_mpix_s": px / warm / 1e6}),
+              flush=True)
+        ref_port.clear_caches()
+
+    # ---- files to files, C2 ----
+    c = CONFIGS["C2"]
+    g.build()
+    pkg = g.load_package()
+    base = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path(tempfile.gettempdir())
+    with tempfile.TemporaryDirectory(dir=base) as td:
+        td = Path(td)
+        pano = synth.smooth(c["Wp"], c["Hp"], 0)
+        src = td / "pano.png"
+        cv2.imwrite(str(src), pano)
+        for fmt in ("png", "jpg"):
+            # the reference's flow with the oracle port
+            out = td / f"cpu_{fmt}"
+            out.mkdir()
+            ref_port.clear_caches()
+            times = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                img = cv2.imread(str(src))
+                t_read = time.perf_counter() - t0
+                views = ref_port.process_image_views(img, c["yaws"], c["pitches"], c["W"], c["H"], c["fov"])
+                t_proj = time.perf_counter() - t0 - t_read
+                for k, yaw in enumerate(c["yaws"]):
+                    for j, p in enumerate(c["pitches"]):
+                        cv2.imwrite(str(out / f"pano_{c['W']}x{c['H']}_yaw_{yaw}_pitch_{p}.{fmt}"), views[k][j])
+                total = time.perf_counter() - t0
+                times.append((total, t_read, t_proj, total - t_read - t_proj))
+            best = min(times[1:])  # warm map caches
+            print(json.dumps({"files": f"C2 png -> 12 x {fmt}", "impl": "reference flow (oracle port), warm maps",
+                              "total_s": best[0], "imread_s": best[1], "project_s": best[2], "imwrite_s": best[3],
+                              "cold_total_s": times[0][0]}), flush=True)
+            # this framework's front end
+            out2 = td / f"gpu_{fmt}"
+            times = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                pkg.process_single_image(src, out2 if out2.exists() else (out2.mkdir() or out2), c["yaws"], c["pitches"], c["W"],
+                                         c["H"], num_workers=info["workers"], output_format=fmt, fov_deg=c["fov"])
+                times.append(time.perf_counter() - t0)
+            same = all((out / f.name).read_bytes() == f.read_bytes() for f in out2.iterdir()) if fmt == "jpg" else \
+                all(np.array_equal(cv2.imread(str(out / f.name)), cv2.imread(str(f))) for f in out2.iterdir())
+            print(json.dumps({"files": f"C2 png -> 12 x {fmt}", "impl": "this framework (process_single_image)",
+                              "total_s": min(times[1:]), "first_s": times[0],
+                              "same_as_reference_flow": bool(same),
+                              "note": "imread of the 8K PNG dominates; jpg: files byte-identical, png: pixels identical"}),
+                  flush=True)
+
+
+if __name__ == "__main__":
+    main()
