@@ -104,8 +104,8 @@ class Projector:
             raise P2PError(rc, f"p2p_create(device={device}) failed: "
                                f"{self.lib.p2p_status_string(rc).decode()} (no CUDA device? there is no CPU fallback)")
         self.ctx = ctx
-        self._pool: queue.Queue = queue.Queue()
-        for i in range(self.n_slots):
+        self._pool: queue.LifoQueue = queue.LifoQueue()  # LIFO: reuse the slot whose device buffers are already allocated
+        for i in reversed(range(self.n_slots)):
             self._pool.put(i)
         self._lock = threading.Lock()
 

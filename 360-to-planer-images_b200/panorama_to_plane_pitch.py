@@ -191,18 +191,35 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
                 logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
 
 
+class _YawGroup:
+    """The save tasks of one yaw: ``result()`` waits for all of them and re-raises the first failure, so callers keep
+    the reference's per-yaw error reporting (ref :279-280) while every view is encoded by its own worker."""
+
+    def __init__(self, futures):
+        self.futures = futures
+
+    def result(self):
+        err = None
+        for f in self.futures:
+            try:
+                f.result()
+            except Exception as e:  # noqa: BLE001 - reported per yaw by the caller
+                err = err or e
+        if err is not None:
+            raise err
+
+
 def _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
                 output_format, executor):
-    """Submit one encode task per yaw (reference file names, ref :275); returns the futures."""
+    """Submit one encode task per view (reference file names, ref :275); returns one waitable per yaw."""
 
-    def save_yaw(k):
-        for i in range(len(pitch_angles)):
-            out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angles[k]}"
-                            f"_pitch_{pitch_angles[i]}.{output_format}")
-            cv2.imwrite(str(output_dir / out_filename), views[k, i])
-            logging.debug(f"Saved {output_dir / out_filename}")
+    def save(k, i):
+        out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angles[k]}"
+                        f"_pitch_{pitch_angles[i]}.{output_format}")
+        cv2.imwrite(str(output_dir / out_filename), views[k, i])
+        logging.debug(f"Saved {output_dir / out_filename}")
 
-    return [executor.submit(save_yaw, k) for k in range(len(yaw_angles))]
+    return [_YawGroup([executor.submit(save, k, i) for i in range(len(pitch_angles))]) for k in range(len(yaw_angles))]
 
 
 def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, output_width, output_height,
