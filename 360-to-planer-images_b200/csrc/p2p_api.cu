@@ -3,6 +3,7 @@
 #include "p2p.h"
 #include "p2p_kernels.cuh"
 #include "p2p_jpeg_host.cuh"
+#include "p2p_jpegdec.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -50,6 +51,13 @@ struct Slot {
     size_t j_out_cap = 0;
     unsigned long long *j_tot = nullptr;  // [3][n]: total bits, total 0xFF, n_chunks (as u32 pairs)
     size_t j_tot_cap = 0;
+    // JPEG decoder (p2p_upload_pano_jpeg): pinned coefficient staging, device coefficients and component planes
+    int16_t *jd_coef_h = nullptr;
+    size_t jd_coef_h_cap = 0;
+    int16_t *jd_coef_d = nullptr;
+    size_t jd_coef_d_cap = 0;
+    uint8_t *jd_planes = nullptr;
+    size_t jd_planes_cap = 0;
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
     unsigned long long *j_sizes_d = nullptr;
     int j_sizes_n = 0;
@@ -557,6 +565,68 @@ int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8
     return rc;
 }
 
+// ---- JPEG decoder (p2p_jpegdec.cuh) ------------------------------------------------------------
+// Decode `file` into the slot's BGR staging image (s.d_bgr, row stride = Wp * 3 rounded to 4).  The Huffman stage
+// runs on the calling thread WITHOUT the context lock; the lock is only taken to size buffers and to enqueue.
+int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pjdec::Parsed &P, size_t *dstride) {
+    using namespace p2pjdec;
+    if (parse_headers(file, len, P)) return P2P_ERR_UNSUPPORTED;
+    const Info &I = P.info;
+    Slot &s = ctx->slots[slot];
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        int rc = check_dims(ctx, I.W, I.H);
+        if (rc) return rc;
+        CK(cudaSetDevice(ctx->device));
+        const size_t bytes = I.n_coef * sizeof(int16_t);
+        if (s.jd_coef_h_cap < bytes) {
+            CK(cudaStreamSynchronize(s.stream));  // an earlier upload may still read the old staging buffer
+            if (s.jd_coef_h) CK(cudaFreeHost(s.jd_coef_h));
+            s.jd_coef_h = nullptr;
+            s.jd_coef_h_cap = 0;
+            CK(cudaHostAlloc(reinterpret_cast<void **>(&s.jd_coef_h), bytes, cudaHostAllocPortable));
+            s.jd_coef_h_cap = bytes;
+        } else {
+            CK(cudaStreamSynchronize(s.stream));
+        }
+    }
+    if (decode_scan(file, len, P, s.jd_coef_h)) return P2P_ERR_UNSUPPORTED;  // damaged data: let libjpeg deal with it
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    size_t plane_off[3], plane_bytes = 0;
+    for (int k = 0; k < 3; ++k) {
+        plane_off[k] = plane_bytes;
+        plane_bytes += (size_t)I.bw[k] * I.bh[k] * 64;
+    }
+    *dstride = ((size_t)I.W * 3 + 3) & ~(size_t)3;
+    int rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
+    if (!rc) rc = ensure(ctx, &s.jd_planes, &s.jd_planes_cap, plane_bytes);
+    if (!rc) rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, *dstride * I.H);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s.jd_coef_d, s.jd_coef_h, I.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
+    for (int k = 0; k < 3; ++k) {
+        Quant Q;
+        memcpy(Q.q, I.quant[k], sizeof(Q.q));
+        const int nb = I.bw[k] * I.bh[k];
+        jpegdec_idct_kernel<<<(nb + 31) / 32, 256, 0, s.stream>>>(s.jd_coef_d + I.coef_off[k], s.jd_planes + plane_off[k], Q, nb,
+                                                                  I.bw[k], I.bw[k] * 8);
+    }
+    ColorParams C;
+    C.y = s.jd_planes + plane_off[0];
+    C.cb = s.jd_planes + plane_off[1];
+    C.cr = s.jd_planes + plane_off[2];
+    C.pitch_y = I.bw[0] * 8;
+    C.pitch_c = I.bw[1] * 8;
+    C.W = I.W; C.H = I.H; C.hmax = I.hmax; C.vmax = I.vmax; C.cw = I.cw; C.ch = I.ch;
+    C.bgr = s.d_bgr;
+    C.stride = *dstride;
+    if (I.H > 65535) return fail(ctx, P2P_ERR_LIMIT, "image too tall for one grid");
+    jpegdec_color_kernel<<<dim3(((I.W + 3) / 4 + 255) / 256, I.H), 256, 0, s.stream>>>(C);
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    return P2P_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -581,6 +651,7 @@ const char *p2p_status_string(int status) {
         case P2P_ERR_NOMEM: return "out of memory";
         case P2P_ERR_STATE: return "bad slot state";
         case P2P_ERR_LIMIT: return "size limit exceeded";
+        case P2P_ERR_UNSUPPORTED: return "file outside the supported subset (use cv2.imread)";
         default: return "unknown status";
     }
 }
@@ -639,6 +710,9 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.j_out);
         cudaFree(s.j_tot);
         if (s.j_sizes_h) cudaFreeHost(s.j_sizes_h);
+        if (s.jd_coef_h) cudaFreeHost(s.jd_coef_h);
+        cudaFree(s.jd_coef_d);
+        cudaFree(s.jd_planes);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);
     }
@@ -1034,6 +1108,71 @@ int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, i
     int rc = collect_jpeg(ctx, s, n, G, out_host, out_stride, sizes);
     if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a JPEG file does not fit its output buffer (out_stride) or the encoder's capacity");
     if (rc) return fail(ctx, rc, "JPEG encoder: CUDA error");
+    return P2P_OK;
+}
+
+// ---- JPEG panoramas decoded on the device (the decode side of cv2.imread, ref :244) -----------------------
+int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H) {
+    if (!file || !W || !H) return P2P_ERR_INVALID;
+    p2pjdec::Parsed P;
+    if (p2pjdec::parse_headers(file, len, P)) return P2P_ERR_UNSUPPORTED;
+    *W = P.info.W;
+    *H = P.info.H;
+    return P2P_OK;
+}
+
+int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t capacity, int32_t *layout) {
+    if (!file || !layout) return P2P_ERR_INVALID;
+    p2pjdec::Parsed P;
+    if (p2pjdec::parse_headers(file, len, P)) return P2P_ERR_UNSUPPORTED;
+    const p2pjdec::Info &I = P.info;
+    layout[0] = I.W; layout[1] = I.H; layout[2] = I.hmax; layout[3] = I.vmax;
+    for (int k = 0; k < 3; ++k) {
+        layout[4 + 2 * k] = I.bw[k];
+        layout[5 + 2 * k] = I.bh[k];
+    }
+    if (!coef) return P2P_OK;
+    if (capacity < I.n_coef) return P2P_ERR_INVALID;
+    return p2pjdec::decode_scan(file, len, P, coef) ? P2P_ERR_UNSUPPORTED : P2P_OK;
+}
+
+int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp) {
+    if (!slot_ok(ctx, slot) || !file || !Wp || !Hp) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    p2pjdec::Parsed P;
+    size_t dstride = 0;
+    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride);
+    if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[slot];
+    rc = prepare_slot(ctx, s, P.info.W, P.info.H);
+    if (rc) return rc;
+    *Wp = P.info.W;
+    *Hp = P.info.H;
+    return launch_pack(ctx, s, s.d_bgr, dstride, 0, P.info.H);
+}
+
+int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
+                    size_t capacity_rows) {
+    if (!slot_ok(ctx, slot) || !file || !bgr_host) return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    p2pjdec::Parsed P;
+    size_t dstride = 0;
+    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride);
+    if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
+    if (rc) return rc;
+    if (row_stride < (size_t)P.info.W * 3 || capacity_rows < (size_t)P.info.H)
+        return fail(ctx, P2P_ERR_INVALID, "output buffer smaller than the image (see p2p_jpeg_probe)");
+    Slot &s = ctx->slots[slot];
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        s.valid = false;  // the staging image changed under whatever panorama the slot held
+        CK(cudaMemcpy2DAsync(bgr_host, row_stride, s.d_bgr, dstride, (size_t)P.info.W * 3, P.info.H, cudaMemcpyDeviceToHost,
+                             s.stream));
+    }
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "JPEG decoder: CUDA error");
     return P2P_OK;
 }
 

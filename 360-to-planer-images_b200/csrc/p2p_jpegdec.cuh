@@ -1,0 +1,488 @@
+// p2p_jpegdec.cuh - baseline JPEG decoder for the input panoramas (the decode side of the path).
+//
+// The reference loads every panorama with cv2.imread (ref app/panorama_to_plane-pitch.py:244); for a JPEG file that
+// is libjpeg-turbo at its decoder defaults (dct_method = JDCT_ISLOW, do_fancy_upsampling = TRUE).  Everything after
+// the entropy decoder is integer arithmetic on independent blocks / pixels, restated here operation by operation
+// (oracle/jpeg_decode_model.py is the NumPy restatement, pinned against cv2.imdecode), so the decoded panorama is
+// bit-identical to cv2.imread's:
+//   host   jdhuff.c   Huffman decoding of the single interleaved scan (serial by nature: stays on a CPU thread, outside
+//                     the context lock; quantised coefficients go to the device as int16, natural order)
+//   device jidctint.c jpeg_idct_islow on dequantised coefficients, + 128, clamp            (jpegdec_idct_kernel)
+//          jdsample.c h2v2 / h2v1 fancy upsampling (triangle filters, alternating rounding; replication when the
+//                     chroma plane is at most 2 samples wide), jdcolor.c ycc_rgb_convert   (jpegdec_color_kernel)
+// Supported: 8-bit, 3 components (YCbCr), 4:4:4 / 4:2:2 / 4:2:0, SOF0 / SOF1, one interleaved scan, restart markers.
+// Anything else (progressive, CMYK / grayscale, Adobe marker, EXIF orientation != 1, damaged data) is reported as
+// unsupported and the caller falls back to cv2.imread, as the reference does for every file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+namespace p2pjdec {
+
+struct Info {
+    int W = 0, H = 0;
+    int hmax = 1, vmax = 1;          // luma sampling factors (chroma is 1 x 1)
+    int mcux = 0, mcuy = 0;
+    int bw[3] = {0, 0, 0}, bh[3] = {0, 0, 0};   // blocks per row / column of each component plane (MCU padded)
+    int cw = 0, ch = 0;              // downsampled_width / height of the chroma components
+    uint16_t quant[3][64];           // natural order, per component
+    size_t coef_off[3] = {0, 0, 0};  // element offset of each component in the coefficient buffer
+    size_t n_coef = 0;
+};
+
+// ---- host: markers + Huffman decoding ---------------------------------------------------------------------------
+static const uint8_t kNat[64 + 16] = {  // zigzag position -> natural index (+ 16 safety entries like jpeg_natural_order)
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
+    62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+struct HuffTable {
+    bool present = false;
+    uint16_t look[512];     // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
+    int32_t maxcode[18];    // largest code of each length (-1 if none); [17] = sentinel
+    int32_t valoff[18];     // vals index = code + valoff[length]
+    uint8_t vals[256];
+};
+
+inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, HuffTable &t) {
+    memset(&t, 0, sizeof(t));
+    memcpy(t.vals, vals, (size_t)nvals);
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; ++l) {
+        if (bits[l - 1]) {
+            t.valoff[l] = k - code;
+            for (int i = 0; i < bits[l - 1]; ++i, ++k, ++code) {
+                if (l <= 9) {
+                    const int first = code << (9 - l);
+                    for (int f = 0; f < (1 << (9 - l)); ++f) t.look[first + f] = (uint16_t)((l << 8) | vals[k]);
+                }
+            }
+            t.maxcode[l] = code - 1;
+        } else {
+            t.maxcode[l] = -1;
+        }
+        if (code > (1 << l)) return false;
+        code <<= 1;
+    }
+    t.maxcode[17] = 0x7fffffff;
+    t.present = (k == nvals);
+    return t.present;
+}
+
+struct BitReader {
+    const uint8_t *p, *end;
+    uint64_t acc = 0;
+    int n = 0;            // valid bits in acc (top-aligned at bit n - 1 .. 0)
+    bool marker = false;  // the byte stream hit a marker: zeros are fed from here on
+    inline void fill() {
+        // bulk path: 4 bytes at once when none of them is 0xFF (no stuffing, no marker)
+        while (n <= 32 && !marker && p + 4 <= end) {
+            const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+            const uint32_t v = ~w;
+            if ((v - 0x01010101u) & ~v & 0x80808080u) break;   // some byte is 0xFF
+            acc = (acc << 32) | w;
+            n += 32;
+            p += 4;
+        }
+        while (n <= 56) {
+            uint32_t b = 0;
+            if (!marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0) {
+                        p += 2;
+                    } else {
+                        marker = true;
+                        b = 0;
+                    }
+                } else {
+                    ++p;
+                }
+            } else {
+                marker = true;
+            }
+            acc = (acc << 8) | b;
+            n += 8;
+        }
+    }
+    inline uint32_t peek(int k) { return (uint32_t)(acc >> (n - k)) & ((1u << k) - 1u); }
+    inline void skip(int k) { n -= k; }
+};
+
+// the caller guarantees at least 32 valid bits (one check per coefficient: code <= 16 bits + value <= 15 bits)
+inline int decode_sym(BitReader &br, const HuffTable &t) {
+    const uint16_t e = t.look[br.peek(9)];
+    if (e) {
+        br.skip(e >> 8);
+        return e & 0xFF;
+    }
+    const uint32_t w = br.peek(16);
+    for (int l = 10; l <= 16; ++l) {
+        const int32_t code = (int32_t)(w >> (16 - l));
+        if (code <= t.maxcode[l]) {
+            br.skip(l);
+            return t.vals[(code + t.valoff[l]) & 0xFF];
+        }
+    }
+    return -1;
+}
+
+inline int receive_extend(BitReader &br, int s) {
+    const int v = (int)br.peek(s);
+    br.skip(s);
+    return (v < (1 << (s - 1))) ? v - (1 << s) + 1 : v;
+}
+
+// EXIF orientation of an APP1 segment (0 = none found)
+inline int exif_orientation(const uint8_t *seg, size_t len) {
+    if (len < 14 || memcmp(seg, "Exif\0\0", 6) != 0) return 0;
+    const uint8_t *t = seg + 6;
+    const size_t n = len - 6;
+    const bool le = (t[0] == 'I' && t[1] == 'I'), be = (t[0] == 'M' && t[1] == 'M');
+    if (!le && !be) return 0;
+    auto r16 = [&](size_t o) -> uint32_t { return le ? (uint32_t)(t[o] | (t[o + 1] << 8)) : (uint32_t)((t[o] << 8) | t[o + 1]); };
+    auto r32 = [&](size_t o) -> uint32_t {
+        return le ? (uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24)
+                  : ((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | (uint32_t)t[o + 3];
+    };
+    const size_t ifd = r32(4);
+    if (ifd + 2 > n) return 0;
+    const uint32_t cnt = r16(ifd);
+    for (uint32_t i = 0; i < cnt; ++i) {
+        const size_t e = ifd + 2 + 12 * (size_t)i;
+        if (e + 12 > n) return 0;
+        if (r16(e) == 0x0112) return (int)r16(e + 8);
+    }
+    return 0;
+}
+
+// Parse the headers of a JPEG file.  Returns 0 and fills `info`, the Huffman tables and the scan position if the
+// file is in the supported subset, 1 if not.
+struct Parsed {
+    Info info;
+    HuffTable dc[4], ac[4];
+    int td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    int dri = 0;
+    size_t ecs = 0;   // offset of the entropy-coded data
+};
+
+inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
+    if (len < 4 || d[0] != 0xFF || d[1] != 0xD8) return 1;
+    size_t i = 2;
+    uint16_t qt[4][64];
+    bool have_qt[4] = {false, false, false, false};
+    bool jfif = false, have_frame = false;
+    int cid[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, hs[3] = {1, 1, 1}, vs[3] = {1, 1, 1};
+    Info &I = P.info;
+    while (i + 4 <= len) {
+        if (d[i] != 0xFF) return 1;
+        while (i + 1 < len && d[i + 1] == 0xFF) ++i;
+        if (i + 4 > len) return 1;
+        const int m = d[i + 1];
+        i += 2;
+        if (m == 0xD9) return 1;
+        if ((m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        const size_t L = ((size_t)d[i] << 8) | d[i + 1];
+        if (L < 2 || i + L > len) return 1;
+        const uint8_t *seg = d + i + 2;
+        const size_t sl = L - 2;
+        i += L;
+        if (m == 0xDB) {
+            size_t j = 0;
+            while (j < sl) {
+                const int pq = seg[j] >> 4, t = seg[j] & 15;
+                ++j;
+                if (t > 3 || pq > 1 || j + (pq ? 128 : 64) > sl) return 1;
+                for (int k = 0; k < 64; ++k) {
+                    const uint32_t v = pq ? (uint32_t)((seg[j + 2 * k] << 8) | seg[j + 2 * k + 1]) : seg[j + k];
+                    qt[t][kNat[k]] = (uint16_t)v;
+                }
+                j += pq ? 128 : 64;
+                have_qt[t] = true;
+            }
+        } else if (m == 0xC4) {
+            size_t j = 0;
+            while (j < sl) {
+                if (j + 17 > sl) return 1;
+                const int tc = seg[j] >> 4, th = seg[j] & 15;
+                int nv = 0;
+                for (int k = 0; k < 16; ++k) nv += seg[j + 1 + k];
+                if (tc > 1 || th > 3 || nv > 256 || j + 17 + nv > sl) return 1;
+                if (!build_huff(seg + j + 1, seg + j + 17, nv, tc ? P.ac[th] : P.dc[th])) return 1;
+                j += 17 + (size_t)nv;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {
+            if (have_frame || sl < 6 || seg[0] != 8 || seg[5] != 3 || sl < 6 + 9) return 1;
+            I.H = (seg[1] << 8) | seg[2];
+            I.W = (seg[3] << 8) | seg[4];
+            if (I.W <= 0 || I.H <= 0) return 1;
+            for (int k = 0; k < 3; ++k) {
+                cid[k] = seg[6 + 3 * k];
+                hs[k] = seg[7 + 3 * k] >> 4;
+                vs[k] = seg[7 + 3 * k] & 15;
+                tq[k] = seg[8 + 3 * k];
+                if (tq[k] > 3) return 1;
+            }
+            have_frame = true;
+        } else if (m >= 0xC2 && m <= 0xCF) {
+            return 1;  // progressive, lossless, arithmetic, hierarchical
+        } else if (m == 0xDD) {
+            if (sl < 2) return 1;
+            P.dri = (seg[0] << 8) | seg[1];
+        } else if (m == 0xE0) {
+            if (sl >= 5 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
+        } else if (m == 0xE1) {
+            const int o = exif_orientation(seg, sl);
+            if (o > 1) return 1;  // cv2.imread rotates / flips such files
+        } else if (m == 0xEE) {
+            if (sl >= 5 && memcmp(seg, "Adobe", 5) == 0) return 1;
+        } else if (m == 0xDA) {
+            if (!have_frame || sl < 1 + 6 + 3 || seg[0] != 3) return 1;
+            for (int k = 0; k < 3; ++k) {
+                if (seg[1 + 2 * k] != cid[k]) return 1;
+                P.td[k] = seg[2 + 2 * k] >> 4;
+                P.ta[k] = seg[2 + 2 * k] & 15;
+                if (P.td[k] > 3 || P.ta[k] > 3 || !P.dc[P.td[k]].present || !P.ac[P.ta[k]].present) return 1;
+            }
+            if (seg[7] != 0 || seg[8] != 63 || seg[9] != 0) return 1;
+            // colour space as libjpeg guesses it (jdapimin.c): JFIF -> YCbCr; else by component ids
+            if (!jfif && cid[0] == 'R' && cid[1] == 'G' && cid[2] == 'B') return 1;
+            if (hs[1] != 1 || vs[1] != 1 || hs[2] != 1 || vs[2] != 1) return 1;
+            if (!((hs[0] == 1 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 2))) return 1;
+            I.hmax = hs[0];
+            I.vmax = vs[0];
+            I.mcux = (I.W + 8 * I.hmax - 1) / (8 * I.hmax);
+            I.mcuy = (I.H + 8 * I.vmax - 1) / (8 * I.vmax);
+            size_t off = 0;
+            for (int k = 0; k < 3; ++k) {
+                if (!have_qt[tq[k]]) return 1;
+                memcpy(I.quant[k], qt[tq[k]], sizeof(I.quant[k]));
+                I.bw[k] = I.mcux * (k ? 1 : I.hmax);
+                I.bh[k] = I.mcuy * (k ? 1 : I.vmax);
+                I.coef_off[k] = off;
+                off += (size_t)I.bw[k] * I.bh[k] * 64;
+            }
+            I.n_coef = off;
+            I.cw = (I.W + I.hmax - 1) / I.hmax;
+            I.ch = (I.H + I.vmax - 1) / I.vmax;
+            P.ecs = i;
+            return 0;
+        }
+    }
+    return 1;
+}
+
+// Huffman-decode the scan into `coef` (int16, natural order, component planes [by][bx][64]).  0 = ok, 1 = damaged.
+inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef) {
+    const Info &I = P.info;
+    BitReader br;
+    br.p = d + P.ecs;
+    br.end = d + len;
+    int pred[3] = {0, 0, 0};
+    const int nblk[3] = {I.hmax * I.vmax, 1, 1};
+    int togo = P.dri;
+    for (int my = 0; my < I.mcuy; ++my) {
+        for (int mx = 0; mx < I.mcux; ++mx) {
+            if (P.dri) {
+                if (togo == 0) {
+                    // byte-align, expect RSTn
+                    br.acc = 0;
+                    br.n = 0;
+                    br.marker = false;
+                    if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] < 0xD0 || br.p[1] > 0xD7) return 1;
+                    br.p += 2;
+                    pred[0] = pred[1] = pred[2] = 0;
+                    togo = P.dri;
+                }
+                --togo;
+            }
+            for (int c = 0; c < 3; ++c) {
+                const HuffTable &dct = P.dc[P.td[c]], &act = P.ac[P.ta[c]];
+                for (int b = 0; b < nblk[c]; ++b) {
+                    const int by = c ? my : my * I.vmax + b / I.hmax;
+                    const int bx = c ? mx : mx * I.hmax + b % I.hmax;
+                    int16_t *blk = coef + I.coef_off[c] + ((size_t)by * I.bw[c] + bx) * 64;
+                    memset(blk, 0, 128);
+                    if (br.n < 32) br.fill();
+                    int s = decode_sym(br, dct);
+                    if (s < 0 || s > 11) return 1;
+                    if (s) pred[c] += receive_extend(br, s);
+                    blk[0] = (int16_t)pred[c];
+                    for (int k = 1; k < 64;) {
+                        if (br.n < 32) br.fill();
+                        const int rs = decode_sym(br, act);
+                        if (rs < 0) return 1;
+                        const int r = rs >> 4;
+                        s = rs & 15;
+                        if (s == 0) {
+                            if (r != 15) break;
+                            k += 16;
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) return 1;
+                        blk[kNat[k]] = (int16_t)receive_extend(br, s);
+                        ++k;
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ---- device: IDCT ---------------------------------------------------------------------------------------------------
+// jidctint.c: one 8-point pass; `in` are the 8 inputs, outputs descaled by N bits
+template <int N>
+__device__ __forceinline__ void idct_pass(const int *in, int *out) {
+    int z2 = in[2], z3 = in[6];
+    int z1 = (z2 + z3) * 4433;
+    int tmp2 = z1 + z3 * -15137;
+    int tmp3 = z1 + z2 * 6270;
+    z2 = in[0];
+    z3 = in[4];
+    int tmp0 = (z2 + z3) << 13, tmp1 = (z2 - z3) << 13;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7];
+    tmp1 = in[5];
+    tmp2 = in[3];
+    tmp3 = in[1];
+    z1 = tmp0 + tmp3;
+    z2 = tmp1 + tmp2;
+    z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446;
+    tmp1 *= 16819;
+    tmp2 *= 25172;
+    tmp3 *= 12299;
+    z1 *= -7373;
+    z2 *= -20995;
+    z3 = z3 * -16069 + z5;
+    z4 = z4 * -3196 + z5;
+    tmp0 += z1 + z3;
+    tmp1 += z2 + z4;
+    tmp2 += z2 + z3;
+    tmp3 += z1 + z4;
+    constexpr int R = 1 << (N - 1);
+    out[0] = (tmp10 + tmp3 + R) >> N;
+    out[7] = (tmp10 - tmp3 + R) >> N;
+    out[1] = (tmp11 + tmp2 + R) >> N;
+    out[6] = (tmp11 - tmp2 + R) >> N;
+    out[2] = (tmp12 + tmp1 + R) >> N;
+    out[5] = (tmp12 - tmp1 + R) >> N;
+    out[3] = (tmp13 + tmp0 + R) >> N;
+    out[4] = (tmp13 - tmp0 + R) >> N;
+}
+
+struct Quant {
+    uint16_t q[64];
+};
+
+// 8 threads per block, 32 blocks per CTA; plane[(by * 8 + r) * pitch + bx * 8 + c]
+__global__ void __launch_bounds__(256)
+jpegdec_idct_kernel(const int16_t *__restrict__ coef, uint8_t *__restrict__ plane, const __grid_constant__ Quant Q,
+                    int n_blocks, int bw, int pitch) {
+    __shared__ int ws[32][8][9];
+    const int lb = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+    const int blk = blockIdx.x * 32 + lb;
+    const bool live = blk < n_blocks;
+    int in[8], out[8];
+    if (live) {
+        const int16_t *c = coef + (size_t)blk * 64;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) in[k] = (int)c[k * 8 + l8] * (int)Q.q[k * 8 + l8];   // column l8
+        idct_pass<13 - 2>(in, out);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ws[lb][k][l8] = out[k];
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) in[k] = ws[lb][l8][k];                                 // row l8
+        idct_pass<13 + 2 + 3>(in, out);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lo |= (uint32_t)min(max(out[k] + 128, 0), 255) << (8 * k);
+            hi |= (uint32_t)min(max(out[k + 4] + 128, 0), 255) << (8 * k);
+        }
+        const int by = blk / bw, bx = blk - by * bw;
+        *reinterpret_cast<uint2 *>(plane + (size_t)(by * 8 + l8) * pitch + bx * 8) = make_uint2(lo, hi);
+    }
+}
+
+// ---- device: upsampling + colour conversion -------------------------------------------------------------------------
+struct ColorParams {
+    const uint8_t *y, *cb, *cr;   // component planes (pitch = blocks per row * 8)
+    int pitch_y, pitch_c;
+    int W, H, hmax, vmax, cw, ch;
+    uint8_t *bgr;                 // output rows
+    size_t stride;
+};
+
+// chroma sample of output pixel (x, y): jdsample.c fancy upsampling (or replication for planes <= 2 samples wide)
+__device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ c, int pitch, int x, int y, const ColorParams &P) {
+    if (P.hmax == 1) return c[(size_t)y * pitch + x];
+    const int cx = x >> 1;
+    if (P.cw <= 2) {  // h2v1_upsample / h2v2_upsample: plain replication
+        const int cy = (P.vmax == 2) ? (y >> 1) : y;
+        return c[(size_t)cy * pitch + cx];
+    }
+    if (P.vmax == 1) {  // h2v1_fancy_upsample
+        const uint8_t *r = c + (size_t)y * pitch;
+        const int v = r[cx];
+        if (x & 1) return (cx == P.cw - 1) ? v : (3 * v + r[cx + 1] + 2) >> 2;
+        return (cx == 0) ? v : (3 * v + r[cx - 1] + 1) >> 2;
+    }
+    // h2v2_fancy_upsample: nearer row weighs 3, the other 1; context rows replicate at the image edges
+    const int cy = y >> 1;
+    int fy = (y & 1) ? cy + 1 : cy - 1;
+    fy = min(max(fy, 0), P.ch - 1);
+    const uint8_t *r0 = c + (size_t)cy * pitch, *r1 = c + (size_t)fy * pitch;
+    const int cs = 3 * r0[cx] + r1[cx];
+    if (x & 1) {
+        if (cx == P.cw - 1) return (cs * 4 + 7) >> 4;
+        return (cs * 3 + (3 * r0[cx + 1] + r1[cx + 1]) + 7) >> 4;
+    }
+    if (cx == 0) return (cs * 4 + 8) >> 4;
+    return (cs * 3 + (3 * r0[cx - 1] + r1[cx - 1]) + 8) >> 4;
+}
+
+// thread per 4 output pixels of a row: 12 bytes = 3 words when the row can take word stores
+__global__ void __launch_bounds__(256)
+jpegdec_color_kernel(const __grid_constant__ ColorParams P) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= P.W) return;
+    uint32_t px[4];
+    const int n = (P.W - x0 < 4) ? P.W - x0 : 4;
+    for (int i = 0; i < n; ++i) {
+        const int x = x0 + i;
+        const int yy = P.y[(size_t)y * P.pitch_y + x];
+        const int cb = chroma_at(P.cb, P.pitch_c, x, y, P) - 128, cr = chroma_at(P.cr, P.pitch_c, x, y, P) - 128;
+        // jdcolor.c build_ycc_rgb_table / ycc_rgb_convert
+        const int r = yy + ((91881 * cr + 32768) >> 16);
+        const int b = yy + ((116130 * cb + 32768) >> 16);
+        const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+        px[i] = (uint32_t)min(max(b, 0), 255) | ((uint32_t)min(max(g, 0), 255) << 8) | ((uint32_t)min(max(r, 0), 255) << 16);
+    }
+    uint8_t *o = P.bgr + (size_t)y * P.stride + (size_t)x0 * 3;
+    if (n == 4 && (P.stride & 3) == 0) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(o);
+        w[0] = px[0] | (px[1] << 24);
+        w[1] = (px[1] >> 8) | (px[2] << 16);
+        w[2] = (px[2] >> 16) | (px[3] << 8);
+    } else {
+        for (int i = 0; i < n; ++i) {
+            o[3 * i] = (uint8_t)px[i];
+            o[3 * i + 1] = (uint8_t)(px[i] >> 8);
+            o[3 * i + 2] = (uint8_t)(px[i] >> 16);
+        }
+    }
+}
+
+}  // namespace p2pjdec

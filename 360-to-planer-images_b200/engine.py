@@ -309,6 +309,38 @@ class Projector:
         n_p = len(pitch_angles)
         return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
 
+    # -- JPEG panoramas decoded on the device (the decode side of cv2.imread, ref :244) ----------
+    def jpeg_probe(self, data: bytes):
+        """(W, H) if the device decoder handles this file, else None (read it with cv2.imread)."""
+        w, h = C.c_int(), C.c_int()
+        rc = self.lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h))
+        return (w.value, h.value) if rc == 0 else None
+
+    def upload_jpeg(self, slot: int, data: bytes) -> tuple:
+        """Decode a JPEG file into ``slot`` as its panorama; returns (Wp, Hp).  Raises ``P2PError`` with code -6 for
+        files outside the supported subset."""
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.p2p_upload_pano_jpeg(self.ctx, slot, data, len(data), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def decode_jpeg(self, data: bytes, slot: int | None = None) -> np.ndarray:
+        """The array ``cv2.imdecode(data, cv2.IMREAD_COLOR)`` returns (u8 [H, W, 3], BGR), decoded on the device."""
+        dims = self.jpeg_probe(data)
+        if dims is None:
+            raise P2PError(-6, "JPEG file outside the supported subset (fall back to cv2.imread)")
+        W, H = dims
+        out = np.empty((H, W, 3), np.uint8)
+
+        def run(s):
+            self._ck(self.lib.p2p_decode_jpeg(self.ctx, s, data, len(data), out.ctypes.data, out.strides[0], H))
+
+        if slot is None:
+            with self.slots(1) as (s,):
+                run(s)
+        else:
+            run(slot)
+        return out
+
     def view_row_range(self, consts, W: int, H: int, Wp: int, Hp: int) -> tuple:
         """(first, last) panorama row (inclusive) the sampler reads for these pitch constants: what
         ``process_image`` transfers over PCIe (any yaw, any image; memoised per geometry)."""

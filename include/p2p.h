@@ -38,7 +38,8 @@ typedef enum p2p_status {
     P2P_ERR_CUDA = -2,    /* a CUDA runtime call failed; see p2p_last_error */
     P2P_ERR_NOMEM = -3,   /* device or pinned-host allocation failed */
     P2P_ERR_STATE = -4,   /* slot holds no panorama / size mismatch */
-    P2P_ERR_LIMIT = -5    /* size beyond the limits inherited from cv2.remap (< 32767) */
+    P2P_ERR_LIMIT = -5,   /* size beyond the limits inherited from cv2.remap (< 32767) */
+    P2P_ERR_UNSUPPORTED = -6 /* input file outside the subset the device decoder handles: use cv2.imread */
 } p2p_status;
 
 /* Per-pitch constants of the pitch map, formed on the host exactly as the reference does
@@ -166,6 +167,24 @@ int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw
 int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
                            const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
                            int quality, uint8_t *out_host, size_t out_stride, size_t *sizes);
+
+/* ---- JPEG panoramas decoded on the device (replaces cv2.imread(path) of a .jpg / .jpeg input, ref :244) ---- */
+/* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr, 4:4:4 / 4:2:2 / 4:2:0,
+ * baseline or extended sequential Huffman, one interleaved scan, restart markers allowed, no Adobe marker, EXIF
+ * orientation 1 or absent), else P2P_ERR_UNSUPPORTED - the caller then reads the file with cv2.imread as before. */
+int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
+/* Host stage only (no GPU, debug / tests): layout[10] = {W, H, hmax, vmax, blocks per row and column of Y, Cb, Cr};
+ * if coef != NULL the quantised coefficients (int16, natural order, component planes [by][bx][64], Y then Cb then Cr;
+ * capacity in elements) exactly as jdhuff.c decodes them. */
+int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t capacity, int32_t *layout);
+/* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, bit-identical pixels): the Huffman
+ * stage runs on the calling CPU thread (outside the context lock), inverse DCT, chroma upsampling and colour
+ * conversion on the device; the pixels never exist in host memory. */
+int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp);
+/* Same decoder, pixels returned to the host (BGR, row_stride bytes per row, at least capacity_rows rows): the array
+ * cv2.imread / cv2.imdecode would return.  Synchronous; the slot's panorama is invalidated. */
+int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
+                    size_t capacity_rows);
 
 /* wait for everything enqueued on `slot` (slot < 0: all slots) */
 int p2p_sync(p2p_ctx *ctx, int slot);

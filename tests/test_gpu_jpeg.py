@@ -101,3 +101,49 @@ def test_front_end_jpg_files_equal_imwrite_of_the_views(pkg, tmp_path):
     pkg.cli(["--input_path", str(src / "p0.png"), "--output_path", str(out_cli), "--output_format", "jpg", "--FOV", str(fov),
              "--output_width", str(W), "--output_height", str(H), "--yaw_angles", "90", "--pitch_angles", "60"])
     assert (out_cli / f"p0_{W}x{H}_yaw_90_pitch_60.jpg").read_bytes() == (out_dir / f"p0_{W}x{H}_yaw_90_pitch_60.jpg").read_bytes()
+
+
+# ---- decode side ----------------------------------------------------------------------------------------------------
+SAMPLING = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+            "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444}
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (3, 4), (17, 33), (53, 37), (240, 136), (1000, 333), (1024, 512)])
+@pytest.mark.parametrize("sname", ["420", "422", "444"])
+def test_decode_equals_cv2_imdecode(proj, w, h, sname):
+    rng = np.random.default_rng(w * 7 + h)
+    for q, rst, kind in ((95, 0, "noise"), (100, 0, "smooth"), (60, 5, "noise"), (20, 1, "sat")):
+        if kind == "noise":
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == "sat":
+            img = (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+        else:
+            img = synth.smooth(w, h, 3) if w >= 8 and h >= 8 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        data = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,
+                                          cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING[sname]])[1].tobytes()
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(proj.decode_jpeg(data), ref), (q, rst, kind)
+
+
+def test_upload_jpeg_equals_imread_path(pkg, proj, tmp_path):
+    """A JPEG panorama decoded on the device gives the views of the cv2.imread path, bit for bit."""
+    Wp, Hp, W, H, fov = 2048, 1024, 240, 136, 120
+    pano = synth.smooth(Wp, Hp, 7)
+    path = tmp_path / "pano.jpg"
+    cv2.imwrite(str(path), pano)
+    data = path.read_bytes()
+    assert proj.jpeg_probe(data) == (Wp, Hp)
+    shifts = [pkg.yaw_table(Wp, y)[2] for y in (0, 90, 180, 270)]
+    consts = [pkg.pitch_constants(W, fov, p) for p in (30, 60, 90)]
+    with proj.slots(1) as (s,):
+        assert proj.upload_jpeg(s, data) == (Wp, Hp)
+        got = proj.project(s, shifts, consts, W, H)
+        proj.sync(s)
+        assert np.array_equal(proj.download_pano(s, Wp, Hp), cv2.imread(str(path)))
+        proj.upload(s, cv2.imread(str(path)))
+        want = proj.project(s, shifts, consts, W, H)
+        proj.sync(s)
+    assert np.array_equal(got, want)
+    with pytest.raises(pkg.P2PError) as ei:
+        proj.decode_jpeg(cv2.imencode(".jpg", pano[:64, :64], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes())
+    assert ei.value.code == -6

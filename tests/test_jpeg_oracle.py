@@ -38,3 +38,66 @@ def test_oracle_file_equals_imwrite(tmp_path):
     path = tmp_path / "x.jpg"
     cv2.imwrite(str(path), img)   # the call at ref :277
     assert path.read_bytes() == jm.encode(img)
+
+
+# ---- the decode side: oracle/jpeg_decode_model.py against cv2.imdecode (what cv2.imread does at ref :244) ----------
+SAMPLING = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+            "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444}
+
+
+def jpeg_files():
+    rng = np.random.default_rng(11)
+    for (h, w) in [(1, 1), (2, 3), (3, 4), (17, 33), (40, 56), (47, 95)]:
+        for sname, sv in SAMPLING.items():
+            for q, rst in ((100, 0), (95, 0), (75, 3), (20, 1)):
+                img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if q != 20 else \
+                    (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+                data = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,
+                                                  cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sv])[1].tobytes()
+                yield f"{w}x{h}_{sname}_q{q}_rst{rst}", data
+
+
+@pytest.mark.parametrize("name,data", list(jpeg_files()), ids=[n for n, _ in jpeg_files()])
+def test_decoder_oracle_equals_cv2_imdecode(name, data):
+    from oracle import jpeg_decode_model as jd
+
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    assert np.array_equal(jd.decode(data), ref)
+
+
+def test_host_huffman_stage_equals_oracle(pkg):
+    """The C++ entropy decoder inside the library (no GPU needed) against the oracle's coefficient planes."""
+    import ctypes as C
+
+    from oracle import jpeg_decode_model as jd
+
+    lib = pkg._lib.load()
+    for name, data in jpeg_files():
+        lay = (C.c_int32 * 10)()
+        assert lib.p2p_jpeg_coefficients(data, len(data), None, 0, lay) == 0, name
+        n = sum(lay[4 + 2 * k] * lay[5 + 2 * k] * 64 for k in range(3))
+        coef = np.zeros(n, np.int16)
+        assert lib.p2p_jpeg_coefficients(data, len(data), coef.ctypes.data, n, lay) == 0, name
+        planes, _ = jd.entropy_decode(jd.parse(data))
+        assert np.array_equal(coef, np.concatenate([p.reshape(-1) for p in planes]).astype(np.int16)), name
+
+
+def test_unsupported_files_are_reported(pkg):
+    import ctypes as C
+
+    lib = pkg._lib.load()
+    w, h = C.c_int(), C.c_int()
+    img = synth.smooth(64, 48, 1)
+    prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()
+    gray = cv2.imencode(".jpg", img[..., 0])[1].tobytes()
+    png = cv2.imencode(".png", img)[1].tobytes()
+    ok = cv2.imencode(".jpg", img)[1].tobytes()
+    for data in (prog, gray, png, ok[:300], b""):
+        assert lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h)) == -6
+    assert lib.p2p_jpeg_probe(ok, len(ok), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
+    # EXIF orientation 6 (rotated): cv2.imread would rotate the image, so the device decoder declines
+    exif = (b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01\x00\x06\x00\x00"
+            b"\x00\x00\x00\x00")
+    seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
+    rotated = ok[:2] + seg + ok[2:]
+    assert lib.p2p_jpeg_probe(rotated, len(rotated), C.byref(w), C.byref(h)) == -6
