@@ -1178,14 +1178,22 @@ int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uin
 
 int p2p_sync(p2p_ctx *ctx, int slot) {
     if (!ctx) return P2P_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
-    if (slot < 0) {
-        for (int i = 0; i < ctx->n_slots; ++i) CK(cudaStreamSynchronize(ctx->slots[i].stream));
-        return P2P_OK;
+    // the streams are read under the lock, the wait itself happens outside it: a thread waiting for its slot must
+    // not keep the other threads (other slots) from enqueueing
+    std::vector<cudaStream_t> streams;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (slot >= 0 && !slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+        for (int i = 0; i < ctx->n_slots; ++i)
+            if (slot < 0 || i == slot) streams.push_back(ctx->slots[i].stream);
     }
-    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
-    CK(cudaStreamSynchronize(ctx->slots[slot].stream));
+    cudaError_t e = cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < streams.size() && e == cudaSuccess; ++i) e = cudaStreamSynchronize(streams[i]);
+    if (e != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        cudaGetLastError();
+        return fail(ctx, P2P_ERR_CUDA, "cudaStreamSynchronize", e);
+    }
     return P2P_OK;
 }
 

@@ -39,8 +39,12 @@ static const uint8_t kNat[64 + 16] = {  // zigzag position -> natural index (+ 1
     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
     62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
+constexpr int kFastBits = 10;
 struct HuffTable {
     bool present = false;
+    // AC tables: 10-bit lookahead that resolves code AND value bits at once when both fit:
+    // (value << 8) | (run << 4) | total bits, 0 = take the general path
+    int32_t fast_ac[1 << kFastBits];
     uint16_t look[512];     // 9-bit lookahead: (length << 8) | symbol, 0 = longer code
     int32_t maxcode[18];    // largest code of each length (-1 if none); [17] = sentinel
     int32_t valoff[18];     // vals index = code + valoff[length]
@@ -69,6 +73,17 @@ inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, Huff
     }
     t.maxcode[17] = 0x7fffffff;
     t.present = (k == nvals);
+    // combined code + value lookup (used for AC tables only)
+    for (int i = 0; i < (1 << kFastBits); ++i) {
+        t.fast_ac[i] = 0;
+        const uint16_t e = t.look[i >> (kFastBits - 9)];
+        if (!e) continue;
+        const int len = e >> 8, rs = e & 0xFF, run = rs >> 4, sz = rs & 15;
+        if (sz == 0 || len + sz > kFastBits) continue;
+        int v = (i >> (kFastBits - len - sz)) & ((1 << sz) - 1);
+        if (v < (1 << (sz - 1))) v += 1 - (1 << sz);
+        t.fast_ac[i] = (int32_t)(((uint32_t)v << 8) | (uint32_t)(run << 4) | (uint32_t)(len + sz));
+    }
     return t.present;
 }
 
@@ -313,6 +328,15 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                     blk[0] = (int16_t)pred[c];
                     for (int k = 1; k < 64;) {
                         if (br.n < 32) br.fill();
+                        const int32_t fa = act.fast_ac[br.peek(kFastBits)];
+                        if (fa) {  // short code + small value: one lookup
+                            k += (fa >> 4) & 15;
+                            if (k > 63) return 1;
+                            br.skip(fa & 15);
+                            blk[kNat[k]] = (int16_t)(fa >> 8);
+                            ++k;
+                            continue;
+                        }
                         const int rs = decode_sym(br, act);
                         if (rs < 0) return 1;
                         const int r = rs >> 4;

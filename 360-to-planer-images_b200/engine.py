@@ -53,6 +53,13 @@ def yaw_table(pano_width: int, yaw_deg):
     return np.ascontiguousarray(ix, np.int32), np.ascontiguousarray(fx, np.int32), shift
 
 
+def jpeg_probe(data: bytes):
+    """(W, H) if the device JPEG decoder handles this file, else None (read it with cv2.imread).  Headers only, no GPU."""
+    w, h = C.c_int(), C.c_int()
+    rc = _lib.load().p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h))
+    return (w.value, h.value) if rc == 0 else None
+
+
 def _as_u8_image(a, what="panorama") -> np.ndarray:
     a = np.asarray(a)
     if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
@@ -312,9 +319,7 @@ class Projector:
     # -- JPEG panoramas decoded on the device (the decode side of cv2.imread, ref :244) ----------
     def jpeg_probe(self, data: bytes):
         """(W, H) if the device decoder handles this file, else None (read it with cv2.imread)."""
-        w, h = C.c_int(), C.c_int()
-        rc = self.lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h))
-        return (w.value, h.value) if rc == 0 else None
+        return jpeg_probe(data)
 
     def upload_jpeg(self, slot: int, data: bytes) -> tuple:
         """Decode a JPEG file into ``slot`` as its panorama; returns (Wp, Hp).  Raises ``P2PError`` with code -6 for

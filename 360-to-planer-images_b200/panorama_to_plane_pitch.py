@@ -58,7 +58,7 @@ def get_projector(device: int | None = None) -> _engine.Projector:
     d = _default_device if device is None else int(device)
     with _projectors_lock:
         if d not in _projectors:
-            _projectors[d] = _engine.Projector(d, n_slots=6)
+            _projectors[d] = _engine.Projector(d, n_slots=8)
         return _projectors[d]
 
 
@@ -79,13 +79,75 @@ def get_pitch_mapping(output_width, output_height, pitch_angle, pano_width, pano
     return pitch_mapping_cache[key]
 
 
-def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
-    """[n_yaw][n_pitch] views through the batched device path, using the module caches."""
-    pano = _engine._as_u8_image(pano_image, "pano_image")
-    Hp, Wp, _ = pano.shape
+class _JpegSource:
+    """A JPEG panorama the device decoder handles, still as file bytes (the pixels will only exist on the GPU)."""
+
+    __slots__ = ("data", "Wp", "Hp")
+
+    def __init__(self, data, dims):
+        self.data, (self.Wp, self.Hp) = data, dims
+
+
+def _open_image(path):
+    """``cv2.imread(path)`` of the reference (ref :244): a BGR array, or None if unreadable - except that a JPEG file
+    inside the device decoder's subset (baseline YCbCr, no EXIF rotation ...) stays as bytes and is decoded on the GPU
+    (bit-identical pixels, ``csrc/p2p_jpegdec.cuh``)."""
+    import cv2
+
+    path = Path(path)
+    if path.suffix.lower() in (".jpg", ".jpeg"):
+        try:
+            data = path.read_bytes()
+        except OSError:
+            data = b""
+        dims = _engine.jpeg_probe(data) if data else None
+        if dims is not None:
+            return _JpegSource(data, dims)
+    return cv2.imread(str(path))
+
+
+def _decode_source(proj, src):
+    """Host pixels of a source (fractional-yaw path, or a damaged file the device decoder gave up on)."""
+    import cv2
+
+    if not isinstance(src, _JpegSource):
+        return src
+    try:
+        return proj.decode_jpeg(src.data)
+    except _engine.P2PError as e:
+        if e.code != -6:
+            raise
+    img = cv2.imdecode(np.frombuffer(src.data, np.uint8), cv2.IMREAD_COLOR)
+    if img is None:
+        raise ValueError("Failed to decode image")
+    return img
+
+
+def _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
+    if isinstance(src, _JpegSource):
+        Wp, Hp = src.Wp, src.Hp
+    else:
+        Hp, Wp, _ = src.shape
     consts = [get_pitch_mapping(output_width, output_height, p, Wp, Hp, fov_deg) for p in pitch_angles]
     tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
-    return proj.project_image(pano, yaw_angles, pitch_angles, output_width, output_height, fov_deg,
+    return consts, tables
+
+
+def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
+    """[n_yaw][n_pitch] views through the batched device path, using the module caches."""
+    src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
+    consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
+        try:  # decode on the device straight into a slot, project from there
+            with proj.slots(1) as (s,):
+                proj.upload_jpeg(s, src.data)
+                out = proj.project(s, [t[2] for t in tables], consts, output_width, output_height)
+                proj.sync(s)
+            return out
+        except _engine.P2PError as e:
+            if e.code != -6:
+                raise
+    return proj.project_image(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height, fov_deg,
                               consts=consts, tables=tables)
 
 
@@ -95,12 +157,20 @@ def _is_jpeg(output_format) -> bool:
 
 def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
     """[n_yaw][n_pitch] JPEG files (bytes) through the device projection + encoder, using the module caches."""
-    pano = _engine._as_u8_image(pano_image, "pano_image")
-    Hp, Wp, _ = pano.shape
-    consts = [get_pitch_mapping(output_width, output_height, p, Wp, Hp, fov_deg) for p in pitch_angles]
-    tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
-    return proj.project_image_jpeg(pano, yaw_angles, pitch_angles, output_width, output_height, fov_deg,
-                                   consts=consts, tables=tables)
+    src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
+    consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
+        try:  # JPEG in, JPEG out: no pixel ever crosses PCIe
+            with proj.slots(1) as (s,):
+                proj.upload_jpeg(s, src.data)
+                flat = proj.project_jpeg(s, [t[2] for t in tables], consts, output_width, output_height)
+            n_p = len(pitch_angles)
+            return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
+        except _engine.P2PError as e:
+            if e.code != -6:
+                raise
+    return proj.project_image_jpeg(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height,
+                                   fov_deg, consts=consts, tables=tables)
 
 
 def _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height, output_format,
@@ -134,13 +204,11 @@ def panorama_to_plane(path, FOV, output_size, yaw, pitch):
 
     ``output_size`` is (width, height).  Raises ``FileNotFoundError`` if the image can not be read.
     """
-    import cv2
-
-    pano = cv2.imread(str(path))
+    pano = _open_image(path)
     if pano is None:
         raise FileNotFoundError(f"Failed to read image: {path}")
     W, H = int(output_size[0]), int(output_size[1])
-    return process_yaw_and_pitchs(pano, yaw, [pitch], W, H, FOV)[0]
+    return _project(get_projector(), pano, [yaw], [pitch], W, H, FOV)[0, 0]
 
 
 def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles, output_width,
@@ -157,7 +225,7 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
     input_image_path = Path(input_image_path)
     output_dir = Path(output_dir)
     logging.info(f"Loading image: {input_image_path}")
-    input_image = cv2.imread(str(input_image_path))
+    input_image = _open_image(input_image_path)
     if input_image is None:
         logging.error(f"Failed to read image: {input_image_path}")
         return
@@ -223,14 +291,12 @@ def _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, out
 
 
 def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, output_width, output_height,
-                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=3):
+                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=4):
     """Directory front end (ref ``main`` :320-341 processes the files one after the other).
 
-    Same files and names out as calling ``process_single_image`` per file, but pipelined: decoder
-    threads read ahead, every image is uploaded / projected / read back asynchronously on its own
-    slot (stream), and encoder threads write the previous images while the next ones are in flight.
-    ``devices`` shards the files round-robin over several GPUs (one pipeline per device, no data
-    exchange).  Images that need a fractional yaw take the synchronous path.
+    Same files and names out as calling ``process_single_image`` per file, but ``inflight`` images are in flight at
+    once, each on its own slot (stream) driven by its own host thread, while the writer pool saves earlier results.
+    ``devices`` shards the files round-robin over several GPUs (one pipeline per device, no data exchange).
     """
     import cv2
 
@@ -241,134 +307,42 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
     num_workers = max(1, int(num_workers))
     W, H = int(output_width), int(output_height)
 
-    def run_device_jpeg(dev, files):
-        """JPEG output: every image is one synchronous device call (upload rows -> project -> encode -> files) on
-        its own slot; ``inflight`` host threads keep that many slots busy, decoders read ahead, writers only write."""
+    def run_device(dev, files):
+        """Every image is handled start to finish by one of ``inflight`` host threads on its own slot (stream): read
+        (a JPEG the device decoder handles is Huffman-decoded on this thread, everything else by ``cv2.imread``),
+        upload / decode, project, read back or encode, hand the files to the writer pool.  The library calls only
+        hold the context lock while they enqueue, so the threads overlap on the GPU and on the host."""
         proj = get_projector(dev)
-        n_in = max(1, min(int(inflight), proj.n_slots - 1))
+        n_in = max(1, min(int(inflight), proj.n_slots - 1, num_workers))
+        jpeg_out = _is_jpeg(output_format)
 
-        def one(f, pano):
+        def one(f, writers):
+            logging.info(f"Loading image: {f}")
+            src = _open_image(f)
+            if src is None:
+                logging.error(f"Failed to read image: {f}")
+                return
             try:
-                files_ = _project_jpeg(proj, pano, yaw_angles, pitch_angles, W, H, fov_deg)
+                if jpeg_out:
+                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
+                else:
+                    views = _project(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    futs = _save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
+                                       writers)
             except Exception as e:
                 for yaw in yaw_angles:
                     logging.error(f"Error processing yaw_angle {yaw}: {e}")
                 return
-            for fut, yaw in zip(_save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
-                                            writers), yaw_angles):
+            for fut, yaw in zip(futs, yaw_angles):
                 try:
                     fut.result()
                 except Exception as e:
                     logging.error(f"Error processing yaw_angle {yaw}: {e}")
 
-        with ThreadPoolExecutor(max_workers=num_workers) as readers, \
-                ThreadPoolExecutor(max_workers=num_workers) as writers, \
-                ThreadPoolExecutor(max_workers=n_in) as gpu:
-            from collections import deque
-
-            ahead, running = deque(), deque()
-            it = iter(files)
-
-            def refill():
-                while len(ahead) < n_in + 1:
-                    f = next(it, None)
-                    if f is None:
-                        return
-                    logging.info(f"Loading image: {f}")
-                    ahead.append((f, readers.submit(cv2.imread, str(f))))
-
-            refill()
-            while ahead:
-                f, fut = ahead.popleft()
-                refill()
-                pano = fut.result()
-                if pano is None:
-                    logging.error(f"Failed to read image: {f}")
-                    continue
-                while len(running) >= n_in:
-                    running.popleft().result()
-                running.append(gpu.submit(one, f, pano))
-            while running:
-                running.popleft().result()
-
-    def run_device(dev, files):
-        from collections import deque
-
-        if _is_jpeg(output_format):
-            return run_device_jpeg(dev, files)
-        proj = get_projector(dev)
-        n_in = max(1, min(int(inflight), proj.n_slots - 1))
-        out_bufs = [_engine.PinnedBuffer((len(yaw_angles), len(pitch_angles), H, W, 3)) for _ in range(n_in)]
-        free_bufs = deque(range(n_in))
-        pending = deque()  # (slot_ctx, slot, buf_index, pano, base_name)
-        with ThreadPoolExecutor(max_workers=num_workers) as readers, \
-                ThreadPoolExecutor(max_workers=num_workers) as writers:
-            ahead = deque()
-            it = iter(files)
-
-            def refill():
-                while len(ahead) < n_in + 1:
-                    f = next(it, None)
-                    if f is None:
-                        return
-                    logging.info(f"Loading image: {f}")
-                    ahead.append((f, readers.submit(cv2.imread, str(f))))
-
-            def retire():
-                cm, slot, bi, _pano, base, futs_in = pending.popleft()
-                try:
-                    proj.sync(slot)
-                    futs = _save_views(cv2, out_bufs[bi].array, base, output_dir, yaw_angles, pitch_angles, W, H,
-                                       output_format, writers)
-                    for fut, yaw in zip(futs, yaw_angles):
-                        try:
-                            fut.result()  # the pinned buffer is reused afterwards
-                        except Exception as e:
-                            logging.error(f"Error processing yaw_angle {yaw}: {e}")
-                except Exception as e:
-                    for yaw in yaw_angles:
-                        logging.error(f"Error processing yaw_angle {yaw}: {e}")
-                finally:
-                    cm.__exit__(None, None, None)
-                    free_bufs.append(bi)
-
-            refill()
-            while ahead:
-                f, fut = ahead.popleft()
-                refill()
-                pano = fut.result()
-                if pano is None:
-                    logging.error(f"Failed to read image: {f}")
-                    continue
-                try:
-                    pano = _engine._as_u8_image(pano, "input image")
-                    Hp, Wp, _ = pano.shape
-                    consts = [get_pitch_mapping(W, H, p, Wp, Hp, fov_deg) for p in pitch_angles]
-                    tables = [get_yaw_mapping(Wp, Hp, y) for y in yaw_angles]
-                    if any(t[2] is None for t in tables):  # fractional yaw: synchronous two-stage path
-                        views = proj.project_image(pano, yaw_angles, pitch_angles, W, H, fov_deg,
-                                                   consts=consts, tables=tables)
-                        for fut2, yaw in zip(_save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles,
-                                                         W, H, output_format, writers), yaw_angles):
-                            try:
-                                fut2.result()
-                            except Exception as e:
-                                logging.error(f"Error processing yaw_angle {yaw}: {e}")
-                        continue
-                    while not free_bufs:
-                        retire()
-                    bi = free_bufs.popleft()
-                    cm = proj.slots(1)
-                    (slot,) = cm.__enter__()
-                    proj.process_image(slot, pano, [t[2] for t in tables], consts, W, H, out_bufs[bi].array)
-                    pending.append((cm, slot, bi, pano, f.stem, None))
-                except Exception as e:
-                    for yaw in yaw_angles:
-                        logging.error(f"Error processing yaw_angle {yaw}: {e}")
-            while pending:
-                retire()
-        for b in out_bufs:
-            b.free()
+        with ThreadPoolExecutor(max_workers=num_workers) as writers, ThreadPoolExecutor(max_workers=n_in) as workers:
+            for fut in [workers.submit(one, f, writers) for f in files]:
+                fut.result()
 
     if not yaw_angles or not pitch_angles:
         return

@@ -147,3 +147,30 @@ def test_upload_jpeg_equals_imread_path(pkg, proj, tmp_path):
     with pytest.raises(pkg.P2PError) as ei:
         proj.decode_jpeg(cv2.imencode(".jpg", pano[:64, :64], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes())
     assert ei.value.code == -6
+
+
+def test_front_end_jpeg_input_equals_imread_path(pkg, tmp_path):
+    """A .jpg panorama goes through the device decoder in every front door (single image, directory pipeline,
+    ``panorama_to_plane``); the results equal what the cv2.imread pixels give.  Files outside the decoder's subset
+    (progressive) and fractional yaws take the fallbacks."""
+    src = tmp_path / "in"
+    src.mkdir()
+    pano = synth.smooth(1024, 512, 21)
+    cv2.imwrite(str(src / "a.jpg"), pano)
+    cv2.imwrite(str(src / "b.jpeg"), pano[::-1].copy(), [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    cv2.imwrite(str(src / "c.jpg"), pano[:, ::-1].copy(), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    W, H, fov, yaws, pitches = 200, 120, 100, [0, 90, 30], [60, 120]    # yaw 30 is fractional on Wp = 1024
+    out_png, out_jpg = tmp_path / "png", tmp_path / "jpg"
+    pkg.main(str(src), str(out_png), yaws, pitches, W, H, num_workers=3, output_format="png", fov_deg=fov)
+    pkg.main(str(src), str(out_jpg), yaws, pitches, W, H, num_workers=3, output_format="jpg", fov_deg=fov)
+    for name in ("a.jpg", "b.jpeg", "c.jpg"):
+        img = cv2.imread(str(src / name))
+        stem = name.split(".")[0]
+        for y in yaws:
+            views = pkg.process_yaw_and_pitchs(img, y, pitches, W, H, fov)
+            for p, view in zip(pitches, views):
+                assert np.array_equal(cv2.imread(str(out_png / f"{stem}_{W}x{H}_yaw_{y}_pitch_{p}.png")), view), (name, y, p)
+                assert (out_jpg / f"{stem}_{W}x{H}_yaw_{y}_pitch_{p}.jpg").read_bytes() == \
+                    cv2.imencode(".jpg", view)[1].tobytes(), (name, y, p)
+    one = pkg.panorama_to_plane(src / "a.jpg", fov, (W, H), 90, 60)
+    assert np.array_equal(one, pkg.process_yaw_and_pitchs(cv2.imread(str(src / "a.jpg")), 90, [60], W, H, fov)[0])
