@@ -92,6 +92,7 @@ struct BitReader {
     uint64_t acc = 0;
     int n = 0;            // valid bits in acc (top-aligned at bit n - 1 .. 0)
     bool marker = false;  // the byte stream hit a marker: zeros are fed from here on
+    int zero_bits = 0;    // how many of the bits fed so far were such zeros (consuming one = damaged / truncated data)
     inline void fill() {
         // bulk path: 4 bytes at once when none of them is 0xFF (no stuffing, no marker)
         while (n <= 32 && !marker && p + 4 <= end) {
@@ -112,17 +113,21 @@ struct BitReader {
                     } else {
                         marker = true;
                         b = 0;
+                        zero_bits += 8;
                     }
                 } else {
                     ++p;
                 }
             } else {
                 marker = true;
+                zero_bits += 8;
             }
             acc = (acc << 8) | b;
             n += 8;
         }
     }
+    // true if the decoder has consumed bits that were never in the file
+    inline bool overran() const { return zero_bits > n; }
     inline uint32_t peek(int k) { return (uint32_t)(acc >> (n - k)) & ((1u << k) - 1u); }
     inline void skip(int k) { n -= k; }
 };
@@ -304,9 +309,11 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
             if (P.dri) {
                 if (togo == 0) {
                     // byte-align, expect RSTn
+                    if (br.overran()) return 1;
                     br.acc = 0;
                     br.n = 0;
                     br.marker = false;
+                    br.zero_bits = 0;
                     if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] < 0xD0 || br.p[1] > 0xD7) return 1;
                     br.p += 2;
                     pred[0] = pred[1] = pred[2] = 0;
@@ -355,6 +362,7 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
             }
         }
     }
+    if (br.overran()) return 1;   // truncated or damaged scan: libjpeg has its own recovery, leave the file to it
     return 0;
 }
 

@@ -95,6 +95,16 @@ def test_unsupported_files_are_reported(pkg):
     for data in (prog, gray, png, ok[:300], b""):
         assert lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h)) == -6
     assert lib.p2p_jpeg_probe(ok, len(ok), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
+    # a truncated scan must not be decoded with made-up bits: libjpeg has its own recovery, the file is left to it
+    lay = (C.c_int32 * 10)()
+    big = cv2.imencode(".jpg", synth.noise(64, 48, 2))[1].tobytes()
+    assert lib.p2p_jpeg_coefficients(big, len(big), None, 0, lay) == 0
+    coef = np.zeros(sum(lay[4 + 2 * k] * lay[5 + 2 * k] * 64 for k in range(3)), np.int16)
+    assert lib.p2p_jpeg_coefficients(big, len(big), coef.ctypes.data, coef.size, lay) == 0
+    cut = big[:len(big) // 2]
+    assert lib.p2p_jpeg_coefficients(cut, len(cut), coef.ctypes.data, coef.size, lay) == -6
+    cut_eoi = cut + b"\xff\xd9"
+    assert lib.p2p_jpeg_coefficients(cut_eoi, len(cut_eoi), coef.ctypes.data, coef.size, lay) == -6
     # EXIF orientation 6 (rotated): cv2.imread would rotate the image, so the device decoder declines
     exif = (b"Exif\x00\x00MM\x00\x2a\x00\x00\x00\x08\x00\x01\x01\x12\x00\x03\x00\x00\x00\x01\x00\x06\x00\x00"
             b"\x00\x00\x00\x00")
