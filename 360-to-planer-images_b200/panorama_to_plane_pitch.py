@@ -58,7 +58,7 @@ def get_projector(device: int | None = None) -> _engine.Projector:
     d = _default_device if device is None else int(device)
     with _projectors_lock:
         if d not in _projectors:
-            _projectors[d] = _engine.Projector(d, n_slots=8)
+            _projectors[d] = _engine.Projector(d, n_slots=16)  # device buffers are allocated per slot on first use
         return _projectors[d]
 
 
@@ -291,11 +291,11 @@ def _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, out
 
 
 def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, output_width, output_height,
-                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=4):
+                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=None):
     """Directory front end (ref ``main`` :320-341 processes the files one after the other).
 
-    Same files and names out as calling ``process_single_image`` per file, but ``inflight`` images are in flight at
-    once, each on its own slot (stream) driven by its own host thread, while the writer pool saves earlier results.
+    Same files and names out as calling ``process_single_image`` per file, but ``inflight`` images (default: one per
+    worker, at most 15) are in flight at once, each on its own slot (stream) driven by its own host thread, while the writer pool saves earlier results.
     ``devices`` shards the files round-robin over several GPUs (one pipeline per device, no data exchange).
     """
     import cv2
@@ -313,7 +313,8 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
         upload / decode, project, read back or encode, hand the files to the writer pool.  The library calls only
         hold the context lock while they enqueue, so the threads overlap on the GPU and on the host."""
         proj = get_projector(dev)
-        n_in = max(1, min(int(inflight), proj.n_slots - 1, num_workers))
+        # the host Huffman stage of a JPEG input runs on the worker thread: as many images in flight as there are workers
+        n_in = max(1, min(int(inflight) if inflight else num_workers, proj.n_slots - 1))
         jpeg_out = _is_jpeg(output_format)
 
         def one(f, writers):
