@@ -163,7 +163,8 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float | None = None):
     same-sized images, ref :42-73).  Returns (Mpix/s, ms_per_step, steps_done, info)."""
     import cv2
 
-    from oracle import ref_port, synth
+    from oracle import ref_port
+    from tools import synth_inputs as synth
 
     pano = synth.noise(WP, HP, 0)
     ref_port.clear_caches()
@@ -217,7 +218,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     import torch
 
     import __graft_entry__ as g
-    from oracle import synth  # synthetic input generator only
+    from tools import synth_inputs as synth  # synthetic input generator (no oracle code)
 
     g.build()
     pkg = g.load_package()

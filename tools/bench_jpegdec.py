@@ -15,7 +15,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import __graft_entry__ as g  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth_inputs as synth  # noqa: E402
 
 
 def main():

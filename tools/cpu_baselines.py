@@ -19,7 +19,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import __graft_entry__ as g  # noqa: E402
-from oracle import ref_port, synth  # noqa: E402
+from oracle import ref_port  # noqa: E402  (the CPU baseline being timed, like bench.py's cpu_baseline leg)
+from tools import synth_inputs as synth  # noqa: E402
 
 CONFIGS = {
     "C1": dict(Wp=2048, Hp=1024, W=640, H=480, fov=90, yaws=[0], pitches=[90], warm_reps=20),

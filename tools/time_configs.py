@@ -8,7 +8,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import __graft_entry__ as g  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth_inputs as synth  # noqa: E402
 
 CONFIGS = {
     "C1": dict(Wp=2048, Hp=1024, W=640, H=480, fov=90, views=[([0], [90])]),
