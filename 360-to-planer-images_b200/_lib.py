@@ -74,6 +74,7 @@ SIGNATURES = {
 
 OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH, OPT_MIRROR, OPT_INTERP, OPT_TRIG = 0, 1, 2, 3, 4, 5, 6, 7
 OPT_PARTIAL_UPLOAD = 8
+OPT_GPU_HUFFMAN, OPT_GPU_HUFFMAN_COUNT = 9, 10
 
 _lib = None
 

@@ -58,6 +58,18 @@ struct Slot {
     size_t jd_coef_d_cap = 0;
     uint8_t *jd_planes = nullptr;
     size_t jd_planes_cap = 0;
+    // device Huffman stage: destuffed scan, subsequence states / block counts, tables, DC differences
+    uint32_t *jd_stream = nullptr;
+    size_t jd_stream_cap = 0;
+    unsigned long long *jd_states = nullptr;  // [2][n_sub]: start, end
+    size_t jd_states_cap = 0;
+    uint32_t *jd_nblk = nullptr;              // [2][n_sub rounded]: blocks per subsequence, exclusive offsets
+    size_t jd_nblk_cap = 0;
+    p2pjdec::DevHuff *jd_tables = nullptr;    // [3]
+    int32_t *jd_dc = nullptr;                 // [2][3][dc_stride]: DC differences, exclusive sums
+    size_t jd_dc_cap = 0;
+    unsigned long long *jd_tot_d = nullptr;   // scan totals (device) [4]
+    struct JdFlags { int changed; int pad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
     unsigned long long *j_sizes_d = nullptr;
     int j_sizes_n = 0;
@@ -87,6 +99,8 @@ struct p2p_ctx {
     int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
     int opt_partial = 1;       // p2p_process_image transfers only the panorama rows its views can touch
+    int opt_gpu_huffman = 1;   // JPEG inputs without restart markers: Huffman decoding on the device
+    long long gpu_huffman_used = 0, gpu_huffman_fallback = 0;
     p2pjpeg::Tables *d_jtab = nullptr;  // JPEG tables + header of (jW, jH, jQ)
     int jW = 0, jH = 0, jQ = 0;
     int *j_err_h = nullptr, *j_err_d = nullptr;  // mapped: set by the encoder kernels when a file does not fit
@@ -566,18 +580,156 @@ int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8
 }
 
 // ---- JPEG decoder (p2p_jpegdec.cuh) ------------------------------------------------------------
+// Huffman stage on the device (p2pjdec::huff_*): fills s.jd_coef_d.  Returns P2P_OK, an error, or 1 = "not handled"
+// (restart markers, no convergence, inconsistent block count): the caller then runs the host decoder.
+// The destuffing pass runs on the calling thread; the lock is held only while enqueueing.
+int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p2pjdec::Parsed &P) {
+    using namespace p2pjdec;
+    const Info &I = P.info;
+    if (P.dri != 0) return 1;
+    // destuff into the pinned staging buffer (FF 00 -> FF; any other marker ends the scan), then store the words
+    // MSB-first so a 32-bit window is one funnel shift
+    uint8_t *dst = reinterpret_cast<uint8_t *>(s.jd_coef_h);
+    const size_t cap = s.jd_coef_h_cap;
+    size_t n = 0;
+    {
+        const uint8_t *p = file + P.ecs, *end = file + len;
+        while (p < end) {
+            const uint8_t *ff = static_cast<const uint8_t *>(memchr(p, 0xFF, (size_t)(end - p)));
+            const size_t run = ff ? (size_t)(ff - p) : (size_t)(end - p);
+            if (n + run + 16 > cap) return 1;
+            memcpy(dst + n, p, run);
+            n += run;
+            if (!ff) return 1;                       // no EOI: truncated file
+            if (ff + 1 < end && ff[1] == 0) {
+                dst[n++] = 0xFF;
+                p = ff + 2;
+            } else {
+                break;                               // a marker (EOI for a complete file)
+            }
+        }
+    }
+    if (n == 0 || n * 8 >= (1ull << 32)) return 1;
+    const size_t n_words = (n + 3) / 4 + 3;
+    memset(dst + n, 0, n_words * 4 - n);
+    uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+    for (size_t i = 0; i < n_words; ++i) w[i] = __builtin_bswap32(w[i]);
+
+    HuffGeom G;
+    memset(&G, 0, sizeof(G));
+    G.n_bits = (uint32_t)(n * 8);
+    G.n_sub = (G.n_bits + kSubBits - 1) / kSubBits;
+    G.nb = I.hmax * I.vmax + 2;
+    G.hmax = I.hmax; G.vmax = I.vmax; G.mcux = I.mcux;
+    G.total_blocks = (uint32_t)I.mcux * I.mcuy * G.nb;
+    uint32_t max_dc = 0;
+    for (int c = 0; c < 3; ++c) {
+        G.bw[c] = I.bw[c];
+        G.coef_off[c] = I.coef_off[c];
+        G.dc_count[c] = (uint32_t)I.mcux * I.mcuy * (c ? 1 : I.hmax * I.vmax);
+        max_dc = G.dc_count[c] > max_dc ? G.dc_count[c] : max_dc;
+    }
+    G.dc_stride = (max_dc + 3) & ~3u;
+    const size_t nsub4 = ((size_t)G.n_sub + 3) & ~(size_t)3;
+    DevHuff T[3];
+    for (int c = 0; c < 3; ++c) {
+        const HuffTable &d = P.dc[P.td[c]], &a = P.ac[P.ta[c]];
+        memcpy(T[c].dc_look, d.look, sizeof(d.look));
+        memcpy(T[c].dc_maxcode, d.maxcode, sizeof(d.maxcode));
+        memcpy(T[c].dc_valoff, d.valoff, sizeof(d.valoff));
+        memcpy(T[c].dc_vals, d.vals, sizeof(T[c].dc_vals));
+        memcpy(T[c].ac_fast, a.fast_ac, sizeof(a.fast_ac));
+        memcpy(T[c].ac_look, a.look, sizeof(a.look));
+        memcpy(T[c].ac_maxcode, a.maxcode, sizeof(a.maxcode));
+        memcpy(T[c].ac_valoff, a.valoff, sizeof(a.valoff));
+        memcpy(T[c].ac_vals, a.vals, sizeof(a.vals));
+    }
+    cudaStream_t st = s.stream;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        int rc = ensure(ctx, &s.jd_stream, &s.jd_stream_cap, n_words * 4);
+        if (!rc) rc = ensure(ctx, &s.jd_states, &s.jd_states_cap, 2 * (size_t)G.n_sub * sizeof(unsigned long long));
+        if (!rc) rc = ensure(ctx, &s.jd_nblk, &s.jd_nblk_cap, 2 * nsub4 * sizeof(uint32_t));
+        if (!rc) rc = ensure(ctx, &s.jd_dc, &s.jd_dc_cap, 2 * 3 * (size_t)G.dc_stride * sizeof(int32_t));
+        if (!rc) rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
+        if (rc) return rc;
+        if (!s.jd_tables) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tables), 3 * sizeof(DevHuff)));
+        if (!s.jd_tot_d) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tot_d), 4 * sizeof(unsigned long long)));
+        if (!s.jd_flags_h) {
+            CK(cudaHostAlloc(reinterpret_cast<void **>(&s.jd_flags_h), sizeof(*s.jd_flags_h), cudaHostAllocMapped | cudaHostAllocPortable));
+            CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.jd_flags_d), s.jd_flags_h, 0));
+        }
+        CK(cudaMemcpyAsync(s.jd_stream, w, n_words * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.jd_tables, T, sizeof(T), cudaMemcpyHostToDevice, st));   // T is pageable: staged before return
+        CK(cudaMemsetAsync(s.jd_coef_d, 0, I.n_coef * sizeof(int16_t), st));
+        huff_sync_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states, s.jd_states + G.n_sub,
+                                                              s.jd_nblk, 1, &s.jd_flags_d->changed);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // synchronisation rounds: each needs the "anything changed" flag back on the host
+    bool converged = false;
+    for (int round = 0; round < kMaxSyncRounds; ++round) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            CK(cudaSetDevice(ctx->device));
+            s.jd_flags_h->changed = 0;
+            huff_sync_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states,
+                                                                  s.jd_states + G.n_sub, s.jd_nblk, 0, &s.jd_flags_d->changed);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) return P2P_ERR_CUDA;
+        if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->changed) == 0) {
+            converged = true;
+            break;
+        }
+    }
+    if (!converged) return 1;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        p2pjpeg::jpeg_scan_kernel<<<1, 1024, 0, st>>>(s.jd_nblk, s.jd_nblk + nsub4, nullptr, G.n_sub, nsub4, &s.jd_flags_d->total);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return P2P_ERR_CUDA;
+    const unsigned long long total = *reinterpret_cast<volatile unsigned long long *>(&s.jd_flags_h->total);
+    // the padding bits after the last block may decode as a few more "blocks"; fewer than expected = damaged data
+    if (total < G.total_blocks || total > (unsigned long long)G.total_blocks + 8) return 1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    int32_t *dcdiff = s.jd_dc;
+    uint32_t *dcsum = reinterpret_cast<uint32_t *>(s.jd_dc + 3 * (size_t)G.dc_stride);
+    huff_write_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states, s.jd_nblk + nsub4,
+                                                           s.jd_coef_d, dcdiff);
+    // per component: exclusive sums of the DC differences in scan order (mod 2^32 arithmetic = two's complement sums)
+    CK(cudaMemcpyAsync(s.jd_nblk, G.dc_count, 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // reuse as n_per_image
+    p2pjpeg::jpeg_scan_kernel<<<3, 1024, 0, st>>>(reinterpret_cast<const uint32_t *>(dcdiff), dcsum, s.jd_nblk, 0u,
+                                                  (size_t)G.dc_stride, s.jd_tot_d);
+    huff_dc_kernel<<<dim3((G.dc_stride + 255) / 256, 3), 256, 0, st>>>(dcdiff, dcsum, G, s.jd_coef_d);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    ctx->gpu_huffman_used++;
+    return P2P_OK;
+}
+
 // Decode `file` into the slot's BGR staging image (s.d_bgr, row stride = Wp * 3 rounded to 4).  The Huffman stage
-// runs on the calling thread WITHOUT the context lock; the lock is only taken to size buffers and to enqueue.
+// runs on the device (files without restart markers) or on the calling thread WITHOUT the context lock; the lock is
+// only taken to size buffers and to enqueue.
 int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pjdec::Parsed &P, size_t *dstride) {
     using namespace p2pjdec;
     if (parse_headers(file, len, P)) return P2P_ERR_UNSUPPORTED;
     const Info &I = P.info;
     Slot &s = ctx->slots[slot];
+    int use_gpu = 0;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         int rc = check_dims(ctx, I.W, I.H);
         if (rc) return rc;
         CK(cudaSetDevice(ctx->device));
+        use_gpu = ctx->opt_gpu_huffman;
         const size_t bytes = I.n_coef * sizeof(int16_t);
         if (s.jd_coef_h_cap < bytes) {
             CK(cudaStreamSynchronize(s.stream));  // an earlier upload may still read the old staging buffer
@@ -590,7 +742,19 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
             CK(cudaStreamSynchronize(s.stream));
         }
     }
-    if (decode_scan(file, len, P, s.jd_coef_h)) return P2P_ERR_UNSUPPORTED;  // damaged data: let libjpeg deal with it
+    bool coef_on_device = false;
+    if (use_gpu) {
+        const int rc = device_huffman(ctx, s, file, len, P);
+        if (rc == P2P_OK) coef_on_device = true;
+        else if (rc != 1) return rc;
+        else {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->gpu_huffman_fallback++;
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(s.stream);   // the staging buffer was used for the stream upload
+        }
+    }
+    if (!coef_on_device && decode_scan(file, len, P, s.jd_coef_h)) return P2P_ERR_UNSUPPORTED;  // damaged: leave it to libjpeg
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     size_t plane_off[3], plane_bytes = 0;
@@ -603,7 +767,8 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
     if (!rc) rc = ensure(ctx, &s.jd_planes, &s.jd_planes_cap, plane_bytes);
     if (!rc) rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, *dstride * I.H);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(s.jd_coef_d, s.jd_coef_h, I.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
+    if (!coef_on_device)
+        CK(cudaMemcpyAsync(s.jd_coef_d, s.jd_coef_h, I.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
     for (int k = 0; k < 3; ++k) {
         Quant Q;
         memcpy(Q.q, I.quant[k], sizeof(Q.q));
@@ -713,6 +878,13 @@ void p2p_destroy(p2p_ctx *ctx) {
         if (s.jd_coef_h) cudaFreeHost(s.jd_coef_h);
         cudaFree(s.jd_coef_d);
         cudaFree(s.jd_planes);
+        cudaFree(s.jd_stream);
+        cudaFree(s.jd_states);
+        cudaFree(s.jd_nblk);
+        cudaFree(s.jd_tables);
+        cudaFree(s.jd_dc);
+        cudaFree(s.jd_tot_d);
+        if (s.jd_flags_h) cudaFreeHost(s.jd_flags_h);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);
     }
@@ -763,6 +935,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "partial_upload must be 0 or 1");
             ctx->opt_partial = value;
             return P2P_OK;
+        case P2P_OPT_GPU_HUFFMAN:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "gpu_huffman must be 0 or 1");
+            ctx->opt_gpu_huffman = value;
+            return P2P_OK;
 
         default:
             return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -782,6 +958,8 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
         case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
         case P2P_OPT_PARTIAL_UPLOAD: *value = ctx->opt_partial; return P2P_OK;
+        case P2P_OPT_GPU_HUFFMAN: *value = ctx->opt_gpu_huffman; return P2P_OK;
+        case P2P_OPT_GPU_HUFFMAN_COUNT: *value = (int)ctx->gpu_huffman_used; return P2P_OK;
 
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
     }

@@ -366,6 +366,229 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
     return 0;
 }
 
+// ---- device Huffman decoding (self-synchronising subsequences) ----------------------------------------------------
+// A Huffman stream has no random access, but a decoder started at a wrong bit / block position falls back into step
+// with the true decoder after a few code words.  So (Weissenberger & Schmidt, "Massively parallel Huffman decoding on
+// GPUs", ICPP 2018, adapted to the JPEG block structure): cut the destuffed scan into subsequences of kSubBits bits,
+// let one thread decode each from a guessed state (bit position = start of the subsequence, first block of an MCU,
+// DC coefficient), record the state it ends in (bit position, block-in-MCU, zigzag index), then repeat "start
+// subsequence i + 1 from the end state of subsequence i" until nothing changes - subsequence 0 starts from the true
+// state, so a fixed point is the sequential decoder's trajectory.  A prefix sum over the blocks completed per
+// subsequence gives every thread its first output block, the last pass writes the coefficients, a scan per component
+// turns the DC differences into DC values.  Typical photographs converge in < 10 rounds (white noise does not:
+// the host decoder takes over when kMaxSyncRounds is exceeded, as it does for files with restart markers).
+__device__ const uint8_t kNatDev[64 + 16] = {
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
+    62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+constexpr int kSubBits = 1024;
+constexpr int kMaxSyncRounds = 48;
+
+struct DevHuff {                 // one per component: its DC and AC table
+    uint16_t dc_look[512];
+    int32_t dc_maxcode[18], dc_valoff[18];
+    uint8_t dc_vals[16];
+    int32_t ac_fast[1 << kFastBits];
+    uint16_t ac_look[512];
+    int32_t ac_maxcode[18], ac_valoff[18];
+    uint8_t ac_vals[256];
+};
+
+struct HuffGeom {
+    uint32_t n_bits;             // bits of the destuffed scan
+    uint32_t n_sub;              // subsequences
+    int nb;                      // blocks per MCU (hmax * vmax + 2)
+    int hmax, vmax, mcux;
+    uint32_t total_blocks;
+    int bw[3];
+    size_t coef_off[3];
+    uint32_t dc_count[3];        // blocks per component
+    uint32_t dc_stride;          // per-component stride of the DC difference arrays (multiple of 4)
+};
+
+// 32 bits of the stream starting at bit `pos` (words are stored big-endian-swapped: MSB = first bit); two zero
+// words follow the data
+__device__ __forceinline__ uint32_t window32(const uint32_t *__restrict__ w, uint32_t pos) {
+    const uint32_t j = pos >> 5, sh = pos & 31;
+    return __funnelshift_l(__ldg(w + j + 1), __ldg(w + j), sh);
+}
+
+__device__ __forceinline__ int extend_bits(uint32_t v, int s) {   // jdhuff.c HUFF_EXTEND
+    return ((int)v < (1 << (s - 1))) ? (int)v - (1 << s) + 1 : (int)v;
+}
+
+// symbol and code length for the code at the top of `win`; an invalid code (garbage decoding) consumes 16 bits
+__device__ __forceinline__ int slow_symbol(uint32_t win, const int32_t *maxcode, const int32_t *valoff,
+                                           const uint8_t *vals, int nvals_mask, int &len) {
+    const uint32_t w16 = win >> 16;
+    for (int l = 10; l <= 16; ++l) {
+        const int32_t code = (int32_t)(w16 >> (16 - l));
+        if (code <= maxcode[l]) {
+            len = l;
+            return vals[(code + valoff[l]) & nvals_mask];
+        }
+    }
+    len = 16;
+    return 0;
+}
+
+struct HState {
+    uint32_t pos;
+    int b, z;
+};
+__device__ __forceinline__ unsigned long long pack_state(HState s) {
+    return ((unsigned long long)s.pos << 16) | ((unsigned long long)(s.b & 0xFF) << 8) | (unsigned long long)(s.z & 0xFF);
+}
+__device__ __forceinline__ HState unpack_state(unsigned long long v) {
+    HState s;
+    s.pos = (uint32_t)(v >> 16);
+    s.b = (int)((v >> 8) & 0xFF);
+    s.z = (int)(v & 0xFF);
+    return s;
+}
+
+// Decode from state `st` until the bit position reaches `end`.  WRITE: coefficients (natural order, DC = difference)
+// go to their block, starting with scan-order block `blk`; returns the number of blocks completed.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T,
+                                                      const HuffGeom &G, HState &st, uint32_t end, uint32_t blk,
+                                                      int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff) {
+    uint32_t done = 0;
+    int16_t *cur = nullptr;
+    int comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
+    auto locate = [&]() {   // address of the block being written
+        const uint32_t mcu = blk / (uint32_t)G.nb;
+        const int k = (int)(blk - mcu * (uint32_t)G.nb);
+        const uint32_t my = mcu / (uint32_t)G.mcux, mx = mcu - my * (uint32_t)G.mcux;
+        const int c = (k < G.nb - 2) ? 0 : k - (G.nb - 2) + 1;
+        const uint32_t by = c ? my : my * G.vmax + k / G.hmax, bx = c ? mx : mx * G.hmax + k % G.hmax;
+        cur = coef + G.coef_off[c] + ((size_t)by * G.bw[c] + bx) * 64;
+    };
+    if (WRITE && blk < G.total_blocks) locate();
+    while (st.pos < end) {
+        if (WRITE && blk >= G.total_blocks) break;
+        const DevHuff &H = T[comp];
+        const uint32_t win = window32(w, st.pos);
+        if (st.z == 0) {
+            int len, s;
+            const uint16_t e = H.dc_look[win >> 23];
+            if (e) {
+                len = e >> 8;
+                s = e & 0xFF;
+            } else {
+                s = slow_symbol(win, H.dc_maxcode, H.dc_valoff, H.dc_vals, 15, len);
+            }
+            s = (s > 15) ? 15 : s;
+            if (WRITE) {
+                const int diff = s ? extend_bits((win << len) >> (32 - s), s) : 0;
+                const uint32_t mcu = blk / (uint32_t)G.nb;
+                const int k = (int)(blk - mcu * (uint32_t)G.nb);
+                const uint32_t idx = comp ? mcu : mcu * (uint32_t)(G.nb - 2) + (uint32_t)k;
+                dcdiff[(size_t)comp * G.dc_stride + idx] = diff;
+            }
+            st.pos += (uint32_t)(len + s);
+            st.z = 1;
+            continue;
+        }
+        const int32_t fa = H.ac_fast[win >> (32 - kFastBits)];
+        if (fa) {
+            st.z += (fa >> 4) & 15;
+            if (WRITE && st.z < 64) cur[kNatDev[st.z]] = (int16_t)(fa >> 8);
+            st.z += 1;
+            st.pos += (uint32_t)(fa & 15);
+        } else {
+            int len, rs;
+            const uint16_t e = H.ac_look[win >> 23];
+            if (e) {
+                len = e >> 8;
+                rs = e & 0xFF;
+            } else {
+                rs = slow_symbol(win, H.ac_maxcode, H.ac_valoff, H.ac_vals, 255, len);
+            }
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+                st.z = (r == 15) ? st.z + 16 : 64;
+                st.pos += (uint32_t)len;
+            } else {
+                st.z += r;
+                if (WRITE && st.z < 64) cur[kNatDev[st.z]] = (int16_t)extend_bits((win << len) >> (32 - s), s);
+                st.z += 1;
+                st.pos += (uint32_t)(len + s);
+            }
+        }
+        if (st.z >= 64) {   // block complete
+            st.z = 0;
+            st.b = (st.b + 1 == G.nb) ? 0 : st.b + 1;
+            comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
+            ++done;
+            if (WRITE) {
+                ++blk;
+                if (blk < G.total_blocks) locate();
+            }
+        }
+    }
+    return done;
+}
+
+// round 0: every subsequence from its guessed state; later rounds: only where the predecessor's end state moved
+__global__ void __launch_bounds__(128)
+huff_sync_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
+                 unsigned long long *__restrict__ start, unsigned long long *__restrict__ endst,
+                 uint32_t *__restrict__ nblk, int first_round, int *__restrict__ changed) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n_sub) return;
+    HState st;
+    if (first_round) {
+        st.pos = i * (uint32_t)kSubBits;
+        st.b = 0;
+        st.z = 0;
+        start[i] = pack_state(st);
+    } else {
+        if (i == 0) return;
+        const unsigned long long prev = endst[i - 1];
+        if (prev == start[i]) return;
+        start[i] = prev;
+        st = unpack_state(prev);
+        *changed = 1;
+    }
+    const uint32_t end = (i + 1 == G.n_sub) ? G.n_bits : (i + 1) * (uint32_t)kSubBits;
+    nblk[i] = huff_decode_range<false>(w, T, G, st, end, 0u, nullptr, nullptr);
+    endst[i] = pack_state(st);
+}
+
+__global__ void __launch_bounds__(128)
+huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
+                  const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
+                  int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n_sub) return;
+    HState st = unpack_state(start[i]);
+    const uint32_t end = (i + 1 == G.n_sub) ? G.n_bits : (i + 1) * (uint32_t)kSubBits;
+    huff_decode_range<true>(w, T, G, st, end, blkoff[i], coef, dcdiff);
+}
+
+// DC value of block idx of component c = inclusive prefix sum of the differences (dcsum holds the exclusive sums)
+__global__ void __launch_bounds__(256)
+huff_dc_kernel(const int32_t *__restrict__ dcdiff, const uint32_t *__restrict__ dcsum, const HuffGeom G,
+               int16_t *__restrict__ coef) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (idx >= G.dc_count[c]) return;
+    const int dc = (int)dcsum[(size_t)c * G.dc_stride + idx] + dcdiff[(size_t)c * G.dc_stride + idx];
+    uint32_t by, bx;
+    if (c) {
+        by = idx / (uint32_t)G.mcux;
+        bx = idx - by * (uint32_t)G.mcux;
+    } else {
+        const uint32_t per = (uint32_t)(G.nb - 2), mcu = idx / per, k = idx - mcu * per;
+        const uint32_t my = mcu / (uint32_t)G.mcux, mx = mcu - my * (uint32_t)G.mcux;
+        by = my * G.vmax + k / G.hmax;
+        bx = mx * G.hmax + k % G.hmax;
+    }
+    coef[G.coef_off[c] + ((size_t)by * G.bw[c] + bx) * 64] = (int16_t)dc;
+}
+
 // ---- device: IDCT ---------------------------------------------------------------------------------------------------
 // jidctint.c: one 8-point pass; `in` are the 8 inputs, outputs descaled by N bits
 template <int N>

@@ -174,3 +174,33 @@ def test_front_end_jpeg_input_equals_imread_path(pkg, tmp_path):
                     cv2.imencode(".jpg", view)[1].tobytes(), (name, y, p)
     one = pkg.panorama_to_plane(src / "a.jpg", fov, (W, H), 90, 60)
     assert np.array_equal(one, pkg.process_yaw_and_pitchs(cv2.imread(str(src / "a.jpg")), 90, [60], W, H, fov)[0])
+
+
+def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
+    """Files without restart markers are Huffman-decoded on the device (self-synchronising subsequences); the pixels
+    must equal the host decoder's (= cv2's), the fallback must work, and the option must switch the stage off."""
+    L = pkg._lib
+    rng = np.random.default_rng(99)
+    smooth = synth.smooth(2048, 1024, 9)
+    textured = np.clip(smooth.astype(np.int16) + rng.integers(-12, 13, smooth.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+    for img, q, samp in ((smooth, 95, "420"), (textured, 90, "420"), (textured, 85, "444"), (smooth[:333, :1000], 75, "422")):
+        data = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING[samp]])[1].tobytes()
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
+        got = proj.decode_jpeg(data)
+        assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1, "the device Huffman stage did not run"
+        assert np.array_equal(got, ref), (q, samp)
+        proj.set_option(L.OPT_GPU_HUFFMAN, 0)
+        try:
+            host = proj.decode_jpeg(data)
+        finally:
+            proj.set_option(L.OPT_GPU_HUFFMAN, 1)
+        assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1
+        assert np.array_equal(host, ref)
+    # white noise does not synchronise within the round limit, restart markers are not handled on the device:
+    # both take the host stage and still give cv2's pixels
+    noise = synth.noise(1024, 512, 1)
+    for params in ([cv2.IMWRITE_JPEG_QUALITY, 95], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
+        img = noise if len(params) == 2 else smooth
+        data = cv2.imencode(".jpg", img, params)[1].tobytes()
+        assert np.array_equal(proj.decode_jpeg(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
