@@ -375,15 +375,15 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
 // subsequence i + 1 from the end state of subsequence i" until nothing changes - subsequence 0 starts from the true
 // state, so a fixed point is the sequential decoder's trajectory.  A prefix sum over the blocks completed per
 // subsequence gives every thread its first output block, the last pass writes the coefficients, a scan per component
-// turns the DC differences into DC values.  Typical photographs converge in < 10 rounds (white noise does not:
-// the host decoder takes over when kMaxSyncRounds is exceeded, as it does for files with restart markers).
+// turns the DC differences into DC values.  Typical photographs converge in < 10 rounds, white noise at quality 95
+// in about 80; past kMaxSyncRounds, and for files with restart markers, the host decoder takes over.
 __device__ const uint8_t kNatDev[64 + 16] = {
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
     62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
 constexpr int kSubBits = 1024;
-constexpr int kMaxSyncRounds = 48;
+constexpr int kMaxSyncRounds = 192;
 
 struct DevHuff {                 // one per component: its DC and AC table
     uint16_t dc_look[512];
