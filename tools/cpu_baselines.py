@@ -98,6 +98,26 @@ def main():
                               "note": "imread of the 8K PNG dominates; jpg: files byte-identical, png: pixels identical"}),
                   flush=True)
 
+        # ---- the front door BASELINE.json names: panorama_to_plane(path, FOV, output_size, yaw, pitch) on a .jpg file ----
+        jp = td / "pano_front.jpg"
+        cv2.imwrite(str(jp), pano)
+        ref_port.clear_caches()
+        t_ref = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            img = cv2.imread(str(jp))
+            want = ref_port.process_yaw_and_pitchs(img, 90, [60], c["W"], c["H"], c["fov"])[0]
+            t_ref.append(time.perf_counter() - t0)
+        t_gpu = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            got = pkg.panorama_to_plane(jp, c["fov"], (c["W"], c["H"]), 90, 60)
+            t_gpu.append(time.perf_counter() - t0)
+        print(json.dumps({"front_door": "panorama_to_plane(8192x4096 .jpg, FOV 120, (1920, 1080), yaw 90, pitch 60)",
+                          "reference_flow_cold_s": t_ref[0], "reference_flow_warm_s": min(t_ref[1:]),
+                          "this_framework_first_s": t_gpu[0], "this_framework_s": min(t_gpu[1:]),
+                          "same_pixels": bool(np.array_equal(got, want))}), flush=True)
+
         # ---- a folder of JPEG panoramas -> jpg views (the codec rows either side of the path on the GPU) ----
         n_files = 8
         folder = td / "folder"
