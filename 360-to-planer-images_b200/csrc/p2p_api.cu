@@ -69,7 +69,9 @@ struct Slot {
     int32_t *jd_dc = nullptr;                 // [2][3][dc_stride]: DC differences, exclusive sums
     size_t jd_dc_cap = 0;
     unsigned long long *jd_tot_d = nullptr;   // scan totals (device) [4]
-    struct JdFlags { int changed; int pad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
+    struct JdFlags { int changed; int bad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
+    uint8_t *jd_sub = nullptr;                // subsequence layout + first subsequence of every restart interval
+    size_t jd_sub_cap = 0;
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
     unsigned long long *j_sizes_d = nullptr;
     int j_sizes_n = 0;
@@ -581,17 +583,22 @@ int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8
 
 // ---- JPEG decoder (p2p_jpegdec.cuh) ------------------------------------------------------------
 // Huffman stage on the device (p2pjdec::huff_*): fills s.jd_coef_d.  Returns P2P_OK, an error, or 1 = "not handled"
-// (restart markers, no convergence, inconsistent block count): the caller then runs the host decoder.
+// (no convergence, inconsistent block counts, unexpected markers): the caller then runs the host decoder.
 // The destuffing pass runs on the calling thread; the lock is held only while enqueueing.
 int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p2pjdec::Parsed &P) {
     using namespace p2pjdec;
     const Info &I = P.info;
-    if (P.dri != 0) return 1;
-    // destuff into the pinned staging buffer (FF 00 -> FF; any other marker ends the scan), then store the words
-    // MSB-first so a 32-bit window is one funnel shift
+    const uint32_t nb = (uint32_t)(I.hmax * I.vmax + 2);
+    const uint32_t total_mcus = (uint32_t)I.mcux * I.mcuy;
+    const uint32_t total_blocks = total_mcus * nb;
+    const uint32_t ivl_mcus = P.dri ? (uint32_t)P.dri : total_mcus;
+    const uint32_t n_ivl = (total_mcus + ivl_mcus - 1) / ivl_mcus;
+    // destuff into the pinned staging buffer (FF 00 -> FF; RSTn starts the next interval, byte-aligned; any other
+    // marker ends the scan), then store the words MSB-first so a 32-bit window is one funnel shift
     uint8_t *dst = reinterpret_cast<uint8_t *>(s.jd_coef_h);
     const size_t cap = s.jd_coef_h_cap;
     size_t n = 0;
+    std::vector<uint32_t> ivl_byte(1, 0u);   // byte offset of every interval in the destuffed stream
     {
         const uint8_t *p = file + P.ecs, *end = file + len;
         while (p < end) {
@@ -600,33 +607,61 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
             if (n + run + 16 > cap) return 1;
             memcpy(dst + n, p, run);
             n += run;
-            if (!ff) return 1;                       // no EOI: truncated file
-            if (ff + 1 < end && ff[1] == 0) {
+            if (!ff || ff + 1 >= end) return 1;      // no EOI: truncated file
+            const uint8_t m = ff[1];
+            if (m == 0) {
                 dst[n++] = 0xFF;
                 p = ff + 2;
+            } else if (m >= 0xD0 && m <= 0xD7 && P.dri) {
+                if (n >= (1ull << 29)) return 1;
+                ivl_byte.push_back((uint32_t)n);
+                p = ff + 2;
+            } else if (m == 0xFF) {
+                p = ff + 1;                          // fill byte before a marker
             } else {
-                break;                               // a marker (EOI for a complete file)
+                break;                               // EOI for a complete file
             }
         }
     }
-    if (n == 0 || n * 8 >= (1ull << 32)) return 1;
+    if (n == 0 || n * 8 >= (1ull << 32) || ivl_byte.size() != n_ivl) return 1;
     const size_t n_words = (n + 3) / 4 + 3;
     memset(dst + n, 0, n_words * 4 - n);
     uint32_t *w = reinterpret_cast<uint32_t *>(dst);
     for (size_t i = 0; i < n_words; ++i) w[i] = __builtin_bswap32(w[i]);
+    // subsequences: a regular kSubBits grid inside every interval
+    ivl_byte.push_back((uint32_t)n);
+    std::vector<SubSeq> subs;
+    std::vector<uint32_t> ivl_first(n_ivl + 1);
+    subs.reserve(n * 8 / kSubBits + n_ivl + 1);
+    for (uint32_t k = 0; k < n_ivl; ++k) {
+        ivl_first[k] = (uint32_t)subs.size();
+        const uint32_t b0 = ivl_byte[k] * 8u, b1 = ivl_byte[k + 1] * 8u;
+        if (b1 <= b0) return 1;
+        for (uint32_t b = b0; b < b1; b += kSubBits) {
+            SubSeq q;
+            q.begin = b;
+            q.end = (b + kSubBits < b1) ? b + kSubBits : b1;
+            q.ivl = k;
+            q.first = (b == b0) ? 1u : 0u;
+            subs.push_back(q);
+        }
+    }
+    ivl_first[n_ivl] = (uint32_t)subs.size();
 
     HuffGeom G;
     memset(&G, 0, sizeof(G));
     G.n_bits = (uint32_t)(n * 8);
-    G.n_sub = (G.n_bits + kSubBits - 1) / kSubBits;
-    G.nb = I.hmax * I.vmax + 2;
+    G.n_sub = (uint32_t)subs.size();
+    G.nb = (int)nb;
     G.hmax = I.hmax; G.vmax = I.vmax; G.mcux = I.mcux;
-    G.total_blocks = (uint32_t)I.mcux * I.mcuy * G.nb;
+    G.total_blocks = total_blocks;
+    G.n_ivl = n_ivl;
+    G.ivl_blocks = ivl_mcus * nb;
     uint32_t max_dc = 0;
     for (int c = 0; c < 3; ++c) {
         G.bw[c] = I.bw[c];
         G.coef_off[c] = I.coef_off[c];
-        G.dc_count[c] = (uint32_t)I.mcux * I.mcuy * (c ? 1 : I.hmax * I.vmax);
+        G.dc_count[c] = total_mcus * (c ? 1u : (uint32_t)(I.hmax * I.vmax));
         max_dc = G.dc_count[c] > max_dc ? G.dc_count[c] : max_dc;
     }
     G.dc_stride = (max_dc + 3) & ~3u;
@@ -645,15 +680,22 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
         memcpy(T[c].ac_vals, a.vals, sizeof(a.vals));
     }
     cudaStream_t st = s.stream;
+    const unsigned sgrid = (G.n_sub + 127) / 128;
+    SubSeq *d_sub = nullptr;
+    uint32_t *d_ivl_first = nullptr;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         CK(cudaSetDevice(ctx->device));
+        const size_t sub_bytes = ((size_t)G.n_sub * sizeof(SubSeq) + 15) & ~(size_t)15;
         int rc = ensure(ctx, &s.jd_stream, &s.jd_stream_cap, n_words * 4);
         if (!rc) rc = ensure(ctx, &s.jd_states, &s.jd_states_cap, 2 * (size_t)G.n_sub * sizeof(unsigned long long));
         if (!rc) rc = ensure(ctx, &s.jd_nblk, &s.jd_nblk_cap, 2 * nsub4 * sizeof(uint32_t));
         if (!rc) rc = ensure(ctx, &s.jd_dc, &s.jd_dc_cap, 2 * 3 * (size_t)G.dc_stride * sizeof(int32_t));
         if (!rc) rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
+        if (!rc) rc = ensure(ctx, &s.jd_sub, &s.jd_sub_cap, sub_bytes + ((size_t)n_ivl + 1) * sizeof(uint32_t));
         if (rc) return rc;
+        d_sub = reinterpret_cast<SubSeq *>(s.jd_sub);
+        d_ivl_first = reinterpret_cast<uint32_t *>(s.jd_sub + sub_bytes);
         if (!s.jd_tables) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tables), 3 * sizeof(DevHuff)));
         if (!s.jd_tot_d) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tot_d), 4 * sizeof(unsigned long long)));
         if (!s.jd_flags_h) {
@@ -661,10 +703,14 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
             CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.jd_flags_d), s.jd_flags_h, 0));
         }
         CK(cudaMemcpyAsync(s.jd_stream, w, n_words * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.jd_tables, T, sizeof(T), cudaMemcpyHostToDevice, st));   // T is pageable: staged before return
+        // the tables below live in pageable memory: cudaMemcpyAsync stages them before it returns
+        CK(cudaMemcpyAsync(s.jd_tables, T, sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_sub, subs.data(), (size_t)G.n_sub * sizeof(SubSeq), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ivl_first, ivl_first.data(), ((size_t)n_ivl + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(s.jd_coef_d, 0, I.n_coef * sizeof(int16_t), st));
-        huff_sync_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states, s.jd_states + G.n_sub,
-                                                              s.jd_nblk, 1, &s.jd_flags_d->changed);
+        s.jd_flags_h->bad = 0;
+        huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
+                                              s.jd_nblk, 1, &s.jd_flags_d->changed);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -675,8 +721,8 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
             std::lock_guard<std::mutex> lk(ctx->mu);
             CK(cudaSetDevice(ctx->device));
             s.jd_flags_h->changed = 0;
-            huff_sync_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states,
-                                                                  s.jd_states + G.n_sub, s.jd_nblk, 0, &s.jd_flags_d->changed);
+            huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
+                                                  s.jd_nblk, 0, &s.jd_flags_d->changed);
             ctx->launches++;
             CK(cudaGetLastError());
         }
@@ -691,19 +737,19 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
         std::lock_guard<std::mutex> lk(ctx->mu);
         CK(cudaSetDevice(ctx->device));
         p2pjpeg::jpeg_scan_kernel<<<1, 1024, 0, st>>>(s.jd_nblk, s.jd_nblk + nsub4, nullptr, G.n_sub, nsub4, &s.jd_flags_d->total);
-        ctx->launches++;
+        huff_check_kernel<<<(n_ivl + 255) / 256, 256, 0, st>>>(s.jd_nblk + nsub4, s.jd_nblk, d_ivl_first, G, &s.jd_flags_d->bad);
+        ctx->launches += 2;
         CK(cudaGetLastError());
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return P2P_ERR_CUDA;
-    const unsigned long long total = *reinterpret_cast<volatile unsigned long long *>(&s.jd_flags_h->total);
-    // the padding bits after the last block may decode as a few more "blocks"; fewer than expected = damaged data
-    if (total < G.total_blocks || total > (unsigned long long)G.total_blocks + 8) return 1;
+    // every interval must hold its quota of blocks (its padding bits may decode as a few more): else damaged data
+    if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->bad) != 0) return 1;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     int32_t *dcdiff = s.jd_dc;
     uint32_t *dcsum = reinterpret_cast<uint32_t *>(s.jd_dc + 3 * (size_t)G.dc_stride);
-    huff_write_kernel<<<(G.n_sub + 127) / 128, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, s.jd_states, s.jd_nblk + nsub4,
-                                                           s.jd_coef_d, dcdiff);
+    huff_write_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, d_ivl_first, s.jd_states, s.jd_nblk + nsub4,
+                                           s.jd_coef_d, dcdiff);
     // per component: exclusive sums of the DC differences in scan order (mod 2^32 arithmetic = two's complement sums)
     CK(cudaMemcpyAsync(s.jd_nblk, G.dc_count, 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // reuse as n_per_image
     p2pjpeg::jpeg_scan_kernel<<<3, 1024, 0, st>>>(reinterpret_cast<const uint32_t *>(dcdiff), dcsum, s.jd_nblk, 0u,
@@ -884,6 +930,7 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.jd_tables);
         cudaFree(s.jd_dc);
         cudaFree(s.jd_tot_d);
+        cudaFree(s.jd_sub);
         if (s.jd_flags_h) cudaFreeHost(s.jd_flags_h);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);

@@ -5,8 +5,8 @@
 // the entropy decoder is integer arithmetic on independent blocks / pixels, restated here operation by operation
 // (oracle/jpeg_decode_model.py is the NumPy restatement, pinned against cv2.imdecode), so the decoded panorama is
 // bit-identical to cv2.imread's:
-//   host   jdhuff.c   Huffman decoding of the single interleaved scan (serial by nature: stays on a CPU thread, outside
-//                     the context lock; quantised coefficients go to the device as int16, natural order)
+//   device jdhuff.c   Huffman decoding of the single interleaved scan as self-synchronising subsequences (huff_*_kernel);
+//   host              the same decoder in C++ (decode_scan) as the fallback when the device stage does not converge
 //   device jidctint.c jpeg_idct_islow on dequantised coefficients, + 128, clamp            (jpegdec_idct_kernel)
 //          jdsample.c h2v2 / h2v1 fancy upsampling (triangle filters, alternating rounding; replication when the
 //                     chroma plane is at most 2 samples wide), jdcolor.c ycc_rgb_convert   (jpegdec_color_kernel)
@@ -376,7 +376,8 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
 // state, so a fixed point is the sequential decoder's trajectory.  A prefix sum over the blocks completed per
 // subsequence gives every thread its first output block, the last pass writes the coefficients, a scan per component
 // turns the DC differences into DC values.  Typical photographs converge in < 10 rounds, white noise at quality 95
-// in about 80; past kMaxSyncRounds, and for files with restart markers, the host decoder takes over.
+// in about 80; past kMaxSyncRounds the host decoder takes over.  Restart intervals are independent scans: every interval
+// starts in a known state, subsequences never span them, DC sums restart with them.
 __device__ const uint8_t kNatDev[64 + 16] = {
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55,
@@ -405,6 +406,17 @@ struct HuffGeom {
     size_t coef_off[3];
     uint32_t dc_count[3];        // blocks per component
     uint32_t dc_stride;          // per-component stride of the DC difference arrays (multiple of 4)
+    // restart intervals (one interval = the whole scan when the file has no restart markers): an interval starts
+    // byte-aligned in the true state (first block of an MCU, DC) with DC predictors 0 and holds ivl_blocks blocks
+    uint32_t n_ivl;
+    uint32_t ivl_blocks;         // blocks per interval (restart_interval * nb); the last interval may hold fewer
+};
+
+// per-subsequence layout built on the host: bit range and restart interval; subsequences never span intervals
+struct SubSeq {
+    uint32_t begin, end;         // bit positions in the destuffed scan
+    uint32_t ivl;                // restart interval
+    uint32_t first;              // 1 = first subsequence of its interval (its start state is known)
 };
 
 // 32 bits of the stream starting at bit `pos` (words are stored big-endian-swapped: MSB = first bit); two zero
@@ -449,11 +461,13 @@ __device__ __forceinline__ HState unpack_state(unsigned long long v) {
 }
 
 // Decode from state `st` until the bit position reaches `end`.  WRITE: coefficients (natural order, DC = difference)
-// go to their block, starting with scan-order block `blk`; returns the number of blocks completed.
+// go to their block, starting with scan-order block `blk` and stopping at block `blk_limit`; returns the number of blocks
+// completed.
 template <bool WRITE>
 __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T,
                                                       const HuffGeom &G, HState &st, uint32_t end, uint32_t blk,
-                                                      int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff) {
+                                                      uint32_t blk_limit, int16_t *__restrict__ coef,
+                                                      int32_t *__restrict__ dcdiff) {
     uint32_t done = 0;
     int16_t *cur = nullptr;
     int comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
@@ -465,9 +479,9 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
         const uint32_t by = c ? my : my * G.vmax + k / G.hmax, bx = c ? mx : mx * G.hmax + k % G.hmax;
         cur = coef + G.coef_off[c] + ((size_t)by * G.bw[c] + bx) * 64;
     };
-    if (WRITE && blk < G.total_blocks) locate();
+    if (WRITE && blk < blk_limit) locate();
     while (st.pos < end) {
-        if (WRITE && blk >= G.total_blocks) break;
+        if (WRITE && blk >= blk_limit) break;   // the interval's quota is done: the rest are padding bits
         const DevHuff &H = T[comp];
         const uint32_t win = window32(w, st.pos);
         if (st.z == 0) {
@@ -524,7 +538,7 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
             ++done;
             if (WRITE) {
                 ++blk;
-                if (blk < G.total_blocks) locate();
+                if (blk < blk_limit) locate();
             }
         }
     }
@@ -534,54 +548,80 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
 // round 0: every subsequence from its guessed state; later rounds: only where the predecessor's end state moved
 __global__ void __launch_bounds__(128)
 huff_sync_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
-                 unsigned long long *__restrict__ start, unsigned long long *__restrict__ endst,
-                 uint32_t *__restrict__ nblk, int first_round, int *__restrict__ changed) {
+                 const SubSeq *__restrict__ sub, unsigned long long *__restrict__ start,
+                 unsigned long long *__restrict__ endst, uint32_t *__restrict__ nblk, int first_round,
+                 int *__restrict__ changed) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.n_sub) return;
+    const SubSeq q = sub[i];
     HState st;
     if (first_round) {
-        st.pos = i * (uint32_t)kSubBits;
+        st.pos = q.begin;
         st.b = 0;
         st.z = 0;
         start[i] = pack_state(st);
     } else {
-        if (i == 0) return;
+        if (q.first) return;   // the true state: never moves
         const unsigned long long prev = endst[i - 1];
         if (prev == start[i]) return;
         start[i] = prev;
         st = unpack_state(prev);
         *changed = 1;
     }
-    const uint32_t end = (i + 1 == G.n_sub) ? G.n_bits : (i + 1) * (uint32_t)kSubBits;
-    nblk[i] = huff_decode_range<false>(w, T, G, st, end, 0u, nullptr, nullptr);
+    nblk[i] = huff_decode_range<false>(w, T, G, st, q.end, 0u, 0u, nullptr, nullptr);
     endst[i] = pack_state(st);
+}
+
+// blkoff = exclusive prefix sum of nblk over ALL subsequences; ivl_first[k] = first subsequence of interval k
+// (ivl_first[n_ivl] = n_sub).  An interval must hold at least its quota of blocks (the padding bits at its end may
+// decode as a few more).
+__global__ void __launch_bounds__(256)
+huff_check_kernel(const uint32_t *__restrict__ blkoff, const uint32_t *__restrict__ nblk,
+                  const uint32_t *__restrict__ ivl_first, const HuffGeom G, int *__restrict__ bad) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= G.n_ivl) return;
+    const uint32_t a = ivl_first[k], b = ivl_first[k + 1];
+    const uint32_t got = (b == G.n_sub ? blkoff[b - 1] + nblk[b - 1] : blkoff[b]) - blkoff[a];
+    const uint32_t first_blk = k * G.ivl_blocks;
+    const uint32_t quota = (first_blk + G.ivl_blocks <= G.total_blocks) ? G.ivl_blocks : G.total_blocks - first_blk;
+    if (got < quota || got > quota + 8u) *bad = 1;
 }
 
 __global__ void __launch_bounds__(128)
 huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
+                  const SubSeq *__restrict__ sub, const uint32_t *__restrict__ ivl_first,
                   const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
                   int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.n_sub) return;
+    const SubSeq q = sub[i];
     HState st = unpack_state(start[i]);
-    const uint32_t end = (i + 1 == G.n_sub) ? G.n_bits : (i + 1) * (uint32_t)kSubBits;
-    huff_decode_range<true>(w, T, G, st, end, blkoff[i], coef, dcdiff);
+    // scan-order index of the block in progress: interval base + blocks completed earlier in this interval
+    const uint32_t first_blk = q.ivl * G.ivl_blocks;
+    const uint32_t blk = first_blk + (blkoff[i] - blkoff[ivl_first[q.ivl]]);
+    const uint32_t limit = (first_blk + G.ivl_blocks <= G.total_blocks) ? first_blk + G.ivl_blocks : G.total_blocks;
+    huff_decode_range<true>(w, T, G, st, q.end, blk, limit, coef, dcdiff);
 }
 
-// DC value of block idx of component c = inclusive prefix sum of the differences (dcsum holds the exclusive sums)
+// DC value of block idx of component c = sum of the differences since the start of its restart interval
+// (dcsum holds the exclusive sums over the whole scan)
 __global__ void __launch_bounds__(256)
 huff_dc_kernel(const int32_t *__restrict__ dcdiff, const uint32_t *__restrict__ dcsum, const HuffGeom G,
                int16_t *__restrict__ coef) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (idx >= G.dc_count[c]) return;
-    const int dc = (int)dcsum[(size_t)c * G.dc_stride + idx] + dcdiff[(size_t)c * G.dc_stride + idx];
+    const uint32_t per = c ? 1u : (uint32_t)(G.nb - 2);              // blocks of this component per MCU
+    const uint32_t seg = (G.ivl_blocks / (uint32_t)G.nb) * per;      // ... and per restart interval
+    const uint32_t seg0 = (idx / seg) * seg;
+    const size_t base = (size_t)c * G.dc_stride;
+    const int dc = (int)(dcsum[base + idx] - dcsum[base + seg0]) + dcdiff[base + idx];
     uint32_t by, bx;
     if (c) {
         by = idx / (uint32_t)G.mcux;
         bx = idx - by * (uint32_t)G.mcux;
     } else {
-        const uint32_t per = (uint32_t)(G.nb - 2), mcu = idx / per, k = idx - mcu * per;
+        const uint32_t mcu = idx / per, k = idx - mcu * per;
         const uint32_t my = mcu / (uint32_t)G.mcux, mx = mcu - my * (uint32_t)G.mcux;
         by = my * G.vmax + k / G.hmax;
         bx = mx * G.hmax + k % G.hmax;

@@ -68,9 +68,9 @@ typedef enum p2p_option {
     ,P2P_OPT_TRIG = 7              /* 0 (default): f32 arccos / arctan2 exactly as NumPy evaluates them on AVX-512
                                      hosts (Intel SVML, ref :162-164) - coordinates and pixels then match the
                                      reference bit for bit there; 1: table-free minimax fits (<= 1.2 ulp) */
-    ,P2P_OPT_GPU_HUFFMAN = 9       /* 1 (default): JPEG inputs without restart markers are Huffman-decoded on the device
-                                     (self-synchronising subsequences); the host decoder takes over when that does not
-                                     converge, and for files with restart markers; 0: always the host decoder */
+    ,P2P_OPT_GPU_HUFFMAN = 9       /* 1 (default): JPEG inputs are Huffman-decoded on the device (self-synchronising
+                                     subsequences, restart intervals as independent scans); the library's host decoder
+                                     takes over when that does not converge; 0: always the host decoder */
     ,P2P_OPT_GPU_HUFFMAN_COUNT = 10 /* read-only: JPEG inputs whose Huffman stage ran on the device so far */
     ,P2P_OPT_PARTIAL_UPLOAD = 8    /* 1 (default): p2p_process_image copies only the panorama rows its views can
                                      touch (p2p_view_row_range) over PCIe; 0: always the whole panorama */

@@ -197,10 +197,14 @@ def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
             proj.set_option(L.OPT_GPU_HUFFMAN, 1)
         assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1
         assert np.array_equal(host, ref)
-    # white noise needs ~80 synchronisation rounds, restart markers are not handled on the device (host stage):
-    # both still give cv2's pixels
+    # white noise needs ~80 synchronisation rounds; restart intervals are independent scans with known start states
     noise = synth.noise(1024, 512, 1)
-    for params in ([cv2.IMWRITE_JPEG_QUALITY, 95], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
-        img = noise if len(params) == 2 else smooth
+    for params in ([cv2.IMWRITE_JPEG_QUALITY, 95], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 4],
+                   [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 1],
+                   [cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_RST_INTERVAL, 1000,
+                    cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING["444"]]):
+        img = noise if len(params) == 2 else textured
         data = cv2.imencode(".jpg", img, params)[1].tobytes()
-        assert np.array_equal(proj.decode_jpeg(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+        n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
+        assert np.array_equal(proj.decode_jpeg(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)), params
+        assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1, params
