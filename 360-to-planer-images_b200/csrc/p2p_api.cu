@@ -69,7 +69,7 @@ struct Slot {
     int32_t *jd_dc = nullptr;                 // [2][3][dc_stride]: DC differences, exclusive sums
     size_t jd_dc_cap = 0;
     unsigned long long *jd_tot_d = nullptr;   // scan totals (device) [4]
-    struct JdFlags { int changed; int bad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
+    struct JdFlags { int changed[8]; int bad; int pad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
     uint8_t *jd_sub = nullptr;                // subsequence layout + first subsequence of every restart interval
     size_t jd_sub_cap = 0;
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
@@ -710,24 +710,28 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
         CK(cudaMemsetAsync(s.jd_coef_d, 0, I.n_coef * sizeof(int16_t), st));
         s.jd_flags_h->bad = 0;
         huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
-                                              s.jd_nblk, 1, &s.jd_flags_d->changed);
+                                              s.jd_nblk, 1, &s.jd_flags_d->changed[0]);
         ctx->launches++;
         CK(cudaGetLastError());
     }
     // synchronisation rounds: each needs the "anything changed" flag back on the host
     bool converged = false;
-    for (int round = 0; round < kMaxSyncRounds; ++round) {
+    for (int round = 0; round < kMaxSyncRounds; round += kRoundsPerCheck) {
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
             CK(cudaSetDevice(ctx->device));
-            s.jd_flags_h->changed = 0;
-            huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
-                                                  s.jd_nblk, 0, &s.jd_flags_d->changed);
-            ctx->launches++;
+            // several rounds per host check (a round in which nothing moves costs one early-exit pass); the flag that
+            // decides convergence is the one of the LAST round of the batch
+            for (int r = 0; r < kRoundsPerCheck; ++r) {
+                s.jd_flags_h->changed[r] = 0;   // nothing of this slot is running: the stream was drained above
+                huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states,
+                                                      s.jd_states + G.n_sub, s.jd_nblk, 0, &s.jd_flags_d->changed[r]);
+            }
+            ctx->launches += kRoundsPerCheck;
             CK(cudaGetLastError());
         }
         if (cudaStreamSynchronize(st) != cudaSuccess) return P2P_ERR_CUDA;
-        if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->changed) == 0) {
+        if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->changed[kRoundsPerCheck - 1]) == 0) {
             converged = true;
             break;
         }

@@ -385,6 +385,7 @@ __device__ const uint8_t kNatDev[64 + 16] = {
 
 constexpr int kSubBits = 1024;
 constexpr int kMaxSyncRounds = 192;
+constexpr int kRoundsPerCheck = 4;   // synchronisation rounds enqueued per host-side convergence check
 
 struct DevHuff {                 // one per component: its DC and AC table
     uint16_t dc_look[512];
