@@ -54,6 +54,8 @@ SIGNATURES = {
     "p2p_encode_jpeg": (_i, [_vp, _i, _u8p, _i, _i, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
     "p2p_project_views_jpeg": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
     "p2p_process_image_jpeg": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
+    "p2p_encode_png": (_i, [_vp, _i, _u8p, _i, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
+    "p2p_process_image_png": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _u8p, _sz, C.POINTER(_sz), _u8p]),
     "p2p_jpeg_probe": (_i, [_u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "p2p_jpeg_coefficients": (_i, [_u8p, _sz, _vp, _sz, _i32p]),
     "p2p_upload_pano_jpeg": (_i, [_vp, _i, _u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),

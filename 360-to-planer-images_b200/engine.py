@@ -232,16 +232,18 @@ class Projector:
         return out
 
     # -- JPEG files (the encode side of cv2.imwrite, ref :277) ---------------------------------
-    def _jpeg_buffer(self, slot: int, n: int, W: int, H: int) -> np.ndarray:
-        """page-locked [n, W * H * 3 + 4096] file buffer of a slot (a slot is driven by one thread at a time)"""
+    def _file_buffer(self, slot: int, n: int, stride: int) -> np.ndarray:
+        """page-locked [n, stride] file buffer of a slot (a slot is driven by one thread at a time)"""
         cache = self.__dict__.setdefault("_jpeg_bufs", {})
-        shape = (n, W * H * 3 + 4096)
         pb = cache.get(slot)
-        if pb is None or pb.shape != shape:
+        if pb is None or pb.shape[0] < n or pb.shape[1] < stride:
             if pb is not None:
                 pb.free()
-            pb = cache[slot] = PinnedBuffer(shape)
-        return pb.array
+            pb = cache[slot] = PinnedBuffer((n, stride))
+        return pb.array[:n]
+
+    def _jpeg_buffer(self, slot: int, n: int, W: int, H: int) -> np.ndarray:
+        return self._file_buffer(slot, n, W * H * 3 + 4096)
 
     def encode_jpeg(self, images: np.ndarray, quality: int = 95, slot: int | None = None) -> list:
         """JPEG files (bytes) of ``images`` u8 [n, H, W, 3] (BGR), encoded on the GPU; byte-identical to
@@ -315,6 +317,53 @@ class Projector:
             flat = self.encode_jpeg(views.reshape(-1, H, W, 3), quality)
         n_p = len(pitch_angles)
         return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
+
+    # -- PNG files (cv2.imwrite(<name>.png), ref :277: the default output format) -------------------
+    def encode_png(self, images: np.ndarray, slot: int | None = None) -> list:
+        """PNG files (bytes) of ``images`` u8 [n, H, W, 3] (BGR), encoded on the GPU; byte-identical to
+        ``cv2.imencode('.png', image)``.  ``None`` for an image the device encoder does not handle (tiny images, blocks
+        zlib would store uncompressed): encode those with cv2."""
+        images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim == 3:
+            images = images[None]
+        n, H, W, ch = images.shape
+        if ch != 3:
+            raise ValueError("images must be [n, H, W, 3]")
+        sizes = (C.c_size_t * n)()
+
+        def run(s):
+            buf = self._file_buffer(s, n, W * H * 4 + 4096)
+            self._ck(self.lib.p2p_encode_png(self.ctx, s, images.ctypes.data, 0, n, W, H, buf.ctypes.data, buf.strides[0], sizes))
+            return [buf[i, :sizes[i]].tobytes() if sizes[i] else None for i in range(n)]
+
+        if slot is None:
+            with self.slots(1) as (s,):
+                return run(s)
+        return run(slot)
+
+    def process_image_png(self, slot: int, pano, shifts, consts, W: int, H: int, want_pixels: bool = True):
+        """upload (``pano`` = None: use the panorama resident in ``slot``) + project + PNG-encode in one ABI call.
+        Returns (files, pixels): files[i] is bytes or None (view not handled by the device encoder); pixels is the
+        [n_yaw, n_pitch, H, W, 3] array when ``want_pixels`` (so the caller can ``cv2.imwrite`` the None views)."""
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
+        n = n_yaw * n_pitch
+        pc = self._consts_array(consts)
+        buf = self._file_buffer(slot, n, W * H * 4 + 4096)
+        sizes = (C.c_size_t * n)()
+        pixels = np.empty((n_yaw, n_pitch, H, W, 3), np.uint8) if want_pixels else None
+        if pano is not None:
+            pano = _as_u8_image(pano)
+            Hp, Wp, _ = pano.shape
+            src, stride = pano.ctypes.data, pano.strides[0]
+        else:
+            Hp = Wp = 0
+            src, stride = None, 0
+        self._ck(self.lib.p2p_process_image_png(self.ctx, slot, src, Wp, Hp, stride, n_yaw,
+                                                shifts.ctypes.data_as(C.POINTER(C.c_int32)), n_pitch, pc, W, H,
+                                                buf.ctypes.data, buf.strides[0], sizes,
+                                                pixels.ctypes.data if want_pixels else None))
+        return [buf[i, :sizes[i]].tobytes() if sizes[i] else None for i in range(n)], pixels
 
     # -- JPEG panoramas decoded on the device (the decode side of cv2.imread, ref :244) ----------
     def jpeg_probe(self, data: bytes):

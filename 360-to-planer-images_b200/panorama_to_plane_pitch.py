@@ -16,9 +16,10 @@ the GPU path needs: the quantised yaw *column table* instead of a full-size (U, 
 three f32 *pitch constants* instead of a full-size map (the map itself is evaluated per pixel
 inside the kernel and never stored).
 
-cv2 is used for file decode (``imread`` :244) and for PNG encode (``imwrite`` :277), as in the reference.
-With ``--output_format jpg|jpeg`` the files are encoded on the GPU (``csrc/p2p_jpeg.cuh``): byte-identical to what
-``cv2.imwrite`` writes at OpenCV's defaults, without the pixels ever crossing PCIe.
+Views are encoded on the GPU - PNG (``csrc/p2p_png.cuh``) and JPEG (``csrc/p2p_jpeg.cuh``) - byte-identical to what
+``cv2.imwrite`` (ref :277) writes at OpenCV's defaults, so only the files cross PCIe; ``.jpg`` panoramas are decoded on the
+GPU too (``csrc/p2p_jpegdec.cuh``, bit-identical to ``cv2.imread``, ref :244).  cv2 remains for PNG input files and for the
+few files / views outside the device codecs' subsets.
 """
 from __future__ import annotations
 
@@ -173,6 +174,53 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
                                    fov_deg, consts=consts, tables=tables)
 
 
+def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
+    """([n_yaw][n_pitch] PNG files (bytes) or None, views or None): projection and PNG encoder on the device.  A None file
+    is a view the device encoder does not handle (tiny output, incompressible content): ``views`` then holds the pixels
+    of all views so that ``cv2.imwrite`` can write those, exactly as the reference would."""
+    src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
+    consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    n_p = len(pitch_angles)
+    if yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
+        shifts = [t[2] for t in tables]
+        with proj.slots(1) as (s,):
+            pano = src
+            if isinstance(src, _JpegSource):
+                try:
+                    proj.upload_jpeg(s, src.data)
+                    pano = None                      # the panorama is resident in the slot
+                except _engine.P2PError as e:
+                    if e.code != -6:
+                        raise
+                    pano = _decode_source(proj, src)
+            flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False)
+            views = None
+            if any(f is None for f in flat):         # read the pixels back only when cv2 has to write some views
+                views = proj.project(s, shifts, consts, output_width, output_height)
+                proj.sync(s)
+        return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))], views
+    views = proj.project_image(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height, fov_deg,
+                               consts=consts, tables=tables)
+    flat = proj.encode_png(views.reshape(-1, output_height, output_width, 3)) if views.size else []
+    return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))], views
+
+
+def _save_png(cv2, files, views, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
+              output_format, executor):
+    """Write device-encoded PNG files; views the device encoder declined are encoded by ``cv2.imwrite`` (ref :277)."""
+
+    def save(k, i):
+        out_filename = (f"{base_name}_{output_width}x{output_height}_yaw_{yaw_angles[k]}"
+                        f"_pitch_{pitch_angles[i]}.{output_format}")
+        if files[k][i] is not None:
+            (output_dir / out_filename).write_bytes(files[k][i])
+        else:
+            cv2.imwrite(str(output_dir / out_filename), views[k, i])
+        logging.debug(f"Saved {output_dir / out_filename}")
+
+    return [_YawGroup([executor.submit(save, k, i) for i in range(len(pitch_angles))]) for k in range(len(yaw_angles))]
+
+
 def _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height, output_format,
                 executor):
     """Write already-encoded views (one task per yaw, reference file names, ref :275); returns the futures."""
@@ -233,10 +281,14 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
     yaw_angles = list(yaw_angles)
     pitch_angles = list(pitch_angles)
     jpeg = _is_jpeg(output_format)
+    png = str(output_format).lower() == "png"
     try:
         if jpeg:  # projected and encoded on the device: only the files come back
             files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
                                   fov_deg)
+        elif png:
+            files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
+                                        output_height, fov_deg)
         else:
             views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
                              fov_deg)
@@ -249,6 +301,9 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
         if jpeg:
             tasks = _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
                                 output_format, executor)
+        elif png:
+            tasks = _save_png(cv2, files, views, base_name, output_dir, yaw_angles, pitch_angles, output_width,
+                              output_height, output_format, executor)
         else:
             tasks = _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, output_width,
                                 output_height, output_format, executor)
@@ -327,6 +382,10 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
                 if jpeg_out:
                     files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
                     futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
+                elif str(output_format).lower() == "png":
+                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    futs = _save_png(cv2, files_, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
+                                     writers)
                 else:
                     views = _project(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
                     futs = _save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,

@@ -172,6 +172,21 @@ int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, i
                            const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
                            int quality, uint8_t *out_host, size_t out_stride, size_t *sizes);
 
+/* ---- PNG files of the views (replaces cv2.imwrite(<name>.png, view), ref :277: the default --output_format) ---- */
+/* PNG files of n_images images (BGR u8, tightly packed, host or device memory), encoded on the GPU and byte-identical
+ * to cv2.imwrite / cv2.imencode('.png') at OpenCV's defaults (filter Sub, zlib level 1, strategy Z_RLE, 8192-byte IDAT
+ * chunks).  sizes[i] = 0 means "not handled on the device": images whose filtered data is <= 16384 bytes, images zlib
+ * would store uncompressed (white noise), a stream ending exactly on an IDAT boundary - use cv2.imwrite for those.
+ * Synchronous.  P2P_ERR_LIMIT if a file does not fit out_stride bytes (W * H * 4 + 4096 always suffices). */
+int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H,
+                   uint8_t *out_host, size_t out_stride, size_t *sizes);
+/* upload (rows the views touch; bgr = NULL: project from the panorama resident in the slot) + project + PNG-encode.
+ * pixels_host (optional, n_yaw * n_pitch * H * W * 3 bytes) also receives the pixels, so the caller can write the views
+ * the device encoder did not handle (sizes[i] = 0) with cv2.imwrite. */
+int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
+                          const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
+                          uint8_t *out_host, size_t out_stride, size_t *sizes, uint8_t *pixels_host);
+
 /* ---- JPEG panoramas decoded on the device (replaces cv2.imread(path) of a .jpg / .jpeg input, ref :244) ---- */
 /* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr, 4:4:4 / 4:2:2 / 4:2:0,
  * baseline or extended sequential Huffman, one interleaved scan, restart markers allowed, no Adobe marker, EXIF

@@ -1,0 +1,32 @@
+"""The PNG oracle (oracle/png_model.py: step-by-step restatement of zlib's deflate_rle + trees.c and libpng's framing at
+OpenCV's settings) pinned against zlib itself and byte for byte against ``cv2.imencode('.png')`` (ref :277)."""
+import zlib
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import png_model as pm
+from oracle import synth
+
+
+def images():
+    rng = np.random.default_rng(5)
+    yield "smooth", synth.smooth(300, 200, 1)
+    yield "flat", np.full((64, 100, 3), 9, np.uint8)
+    yield "textured", np.clip(synth.smooth(256, 128, 2).astype(int) + rng.integers(-5, 6, (128, 256, 3)), 0, 255).astype(np.uint8)
+    yield "stripes", np.repeat(rng.integers(0, 256, (90, 30, 3), dtype=np.uint8), 10, axis=1)
+    yield "noise", synth.noise(96, 64, 1)
+    yield "long_runs", np.concatenate([np.zeros((40, 500, 3), np.uint8), synth.smooth(500, 30, 3)], axis=0)
+
+
+@pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
+def test_deflate_model_equals_zlib(name, img):
+    raw = pm.sub_filter(img)
+    co = zlib.compressobj(1, zlib.DEFLATED, 15, 8, zlib.Z_RLE)
+    assert pm.deflate_rle(raw)[0] == co.compress(raw) + co.flush()
+
+
+@pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
+def test_png_oracle_equals_cv2_imencode(name, img):
+    assert pm.encode_png(img) == cv2.imencode(".png", img)[1].tobytes()
