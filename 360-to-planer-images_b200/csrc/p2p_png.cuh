@@ -84,23 +84,34 @@ png_filter_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ F, cons
     o[2] = (uint8_t)b;
 }
 
-// ---- tiled scans over the positions of an image (one CTA per image, 4096 items per tile) ----------------------------
+// ---- chunked scans over the positions of an image ------------------------------------------------------------------
+// A CTA owns one chunk of kScanChunk positions (tiles of 4096).  WRITE = false computes only the chunk aggregate
+// (chunk_agg), png_chunk_carry_kernel turns the aggregates into the carry every chunk starts from, WRITE = true
+// repeats the scan with that carry and writes the results.
 // MODE 0: s[i] = start of the maximal run of equal bytes containing i (inclusive max-scan of run-start indices)
 // MODE 1: token flags from (F, s) and their exclusive sum (the token index, not stored): writes tlen[i] (0 none,
 //         1 literal, 3..258 match), the position of every kSymPerBlock-th token (= deflate block starts), the token count
-template <int MODE>
+constexpr uint32_t kScanChunk = 65536;
+
+template <int MODE, bool WRITE>
 __global__ void __launch_bounds__(1024)
-png_scan_kernel(const uint8_t *__restrict__ F, uint32_t *__restrict__ S, uint16_t *__restrict__ tlen, uint32_t *__restrict__ blockpos, uint32_t *__restrict__ ntok, const Geom G) {
+png_scan_kernel(const uint8_t *__restrict__ F, uint32_t *__restrict__ S, uint16_t *__restrict__ tlen,
+                uint32_t *__restrict__ blockpos, uint32_t *__restrict__ chunk_agg, const uint32_t *__restrict__ chunk_carry,
+                const Geom G) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
-    const int img = blockIdx.x;
+    const int img = blockIdx.y;
+    const uint32_t n_chunks = (G.N + kScanChunk - 1) / kScanChunk;
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= n_chunks) return;
     const uint8_t *f = F + (size_t)img * G.Npad;
     uint32_t *s = S + (size_t)img * G.Npad;
     const uint32_t N = G.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0u;
+    if (threadIdx.x == 0) s_carry = WRITE ? chunk_carry[(size_t)img * n_chunks + chunk] : 0u;
     __syncthreads();
-    for (uint32_t base = 0; base < N; base += 4096u) {
+    const uint32_t c_end = ((chunk + 1) * kScanChunk < N) ? (chunk + 1) * kScanChunk : N;
+    for (uint32_t base = chunk * kScanChunk; base < c_end; base += 4096u) {
         const uint32_t i0 = base + threadIdx.x * 4u;
         uint32_t v[4];
         uint32_t tl[4];
@@ -167,7 +178,9 @@ png_scan_kernel(const uint8_t *__restrict__ F, uint32_t *__restrict__ S, uint16_
         }
         __syncthreads();
         const uint32_t carry = s_carry;
-        if (MODE == 0) {
+        if (!WRITE) {
+            // aggregate only
+        } else if (MODE == 0) {
             // exclusive prefix (max) of everything before this thread's 4 items
             uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
             ex = (lane == 0) ? 0u : ex;
@@ -196,7 +209,23 @@ png_scan_kernel(const uint8_t *__restrict__ F, uint32_t *__restrict__ S, uint16_
         if (threadIdx.x == 0) s_carry = (MODE == 0) ? max(carry, s_warp[31]) : carry + s_warp[31];
         __syncthreads();
     }
-    if (MODE == 1 && threadIdx.x == 0) ntok[img] = s_carry;
+    if (!WRITE && threadIdx.x == 0) chunk_agg[(size_t)img * n_chunks + chunk] = s_carry;
+}
+
+// carry of every chunk = aggregate of the chunks before it (max for MODE 0, sum for MODE 1); total[img] = whole image
+template <int MODE>
+__global__ void png_chunk_carry_kernel(const uint32_t *__restrict__ chunk_agg, uint32_t *__restrict__ chunk_carry,
+                                       uint32_t *__restrict__ total, const Geom G) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= G.n) return;
+    const uint32_t n_chunks = (G.N + kScanChunk - 1) / kScanChunk;
+    uint32_t acc = 0;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        chunk_carry[(size_t)img * n_chunks + c] = acc;
+        const uint32_t a = chunk_agg[(size_t)img * n_chunks + c];
+        acc = (MODE == 0) ? max(acc, a) : acc + a;
+    }
+    if (total) total[img] = acc;
 }
 
 // position range of deflate block b of an image (the last block may be empty)

@@ -66,3 +66,30 @@ def test_png_fuzz(proj):
             handled += 1
             assert got == ref_png(img), (i, w, h, kind)
     assert handled >= 30
+
+
+def test_front_end_png_files_equal_imwrite(pkg, tmp_path):
+    """The default output format through every front door: the .png files are the bytes cv2.imwrite writes for the same
+    views (device-encoded where the encoder handles the view, cv2 otherwise), for png and jpg inputs, fractional yaws too."""
+    src = tmp_path / "in"
+    src.mkdir()
+    pano = synth.smooth(1024, 512, 31)
+    cv2.imwrite(str(src / "a.png"), pano)
+    cv2.imwrite(str(src / "b.jpg"), pano[::-1].copy())
+    cv2.imwrite(str(src / "n.png"), synth.noise(1024, 512, 2))          # noise views: the device encoder declines them
+    W, H, fov, yaws, pitches = 200, 120, 100, [0, 90, 30], [60, 120]       # yaw 30 is fractional on Wp = 1024
+    out_dir, out_single = tmp_path / "dir", tmp_path / "single"
+    pkg.main(str(src), str(out_dir), yaws, pitches, W, H, num_workers=3, fov_deg=fov)           # png is the default
+    out_single.mkdir()
+    pkg.process_single_image(src / "b.jpg", out_single, yaws, pitches, W, H, num_workers=2, fov_deg=fov)
+    assert len(list(out_dir.iterdir())) == 3 * len(yaws) * len(pitches)
+    for name in ("a.png", "b.jpg", "n.png"):
+        img = cv2.imread(str(src / name))
+        stem = name.split(".")[0]
+        for y in yaws:
+            views = pkg.process_yaw_and_pitchs(img, y, pitches, W, H, fov)
+            for p, view in zip(pitches, views):
+                want = cv2.imencode(".png", view)[1].tobytes()
+                assert (out_dir / f"{stem}_{W}x{H}_yaw_{y}_pitch_{p}.png").read_bytes() == want, (name, y, p)
+                if stem == "b":
+                    assert (out_single / f"{stem}_{W}x{H}_yaw_{y}_pitch_{p}.png").read_bytes() == want
