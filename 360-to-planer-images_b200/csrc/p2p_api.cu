@@ -877,12 +877,18 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
     G.z_cap = (((size_t)G.N + G.N / 8 + 1024) + 15) & ~(size_t)15;
     G.out_cap = (G.z_cap + (G.z_cap / kIdat + 2) * 12 + 64 + 15) & ~(size_t)15;
     if (!ctx->d_crc_table) {
-        uint32_t table[256];
+        uint32_t table[5 * 256];   // CRC-32 byte table + the 4 byte tables of "advance the register by 256 zero bytes"
         for (uint32_t i = 0; i < 256; ++i) {
             uint32_t c = i;
             for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
             table[i] = c;
         }
+        for (int j = 0; j < 4; ++j)
+            for (uint32_t b = 0; b < 256; ++b) {
+                uint32_t c = b << (8 * j);
+                for (int k = 0; k < 256; ++k) c = table[c & 0xFFu] ^ (c >> 8);
+                table[256 * (j + 1) + b] = c;
+            }
         CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_crc_table), sizeof(table)));
         CK(cudaMemcpy(ctx->d_crc_table, table, sizeof(table), cudaMemcpyHostToDevice));
     }
@@ -930,7 +936,7 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
     png_adler_kernel<<<dim3(64, n), 256, 0, st>>>(s.pg_F, sums, G);
     png_pack_kernel<<<dim3(128, n), 256, 0, st>>>(s.pg_Z, zbits, sums, s.j_out, G);
     const unsigned max_chunks = (unsigned)(G.z_cap / kIdat + 1);
-    png_finish_kernel<<<dim3((max_chunks + 127) / 128, n), 128, 0, st>>>(s.j_out, zbits, ctx->d_crc_table, s.j_sizes_d, G);
+    png_finish_kernel<<<dim3((max_chunks + 7) / 8, n), 256, 0, st>>>(s.j_out, zbits, ctx->d_crc_table, s.j_sizes_d, G);
     ctx->launches += 14;
     CK(cudaGetLastError());
     return P2P_OK;

@@ -268,7 +268,9 @@ struct TreeWork {
     uint32_t freq[kHeapSize];
     uint16_t len[kHeapSize], dad[kHeapSize];
     uint8_t depth[kHeapSize];
-    uint16_t heap[kHeapSize + 1];
+    // heap entries carry their sort key: (freq << 8 | depth) << 16 | node, so that trees.c's smaller(n, m) =
+    // "freq[n] < freq[m] || (freq[n] == freq[m] && depth[n] <= depth[m])" is one compare of the keys (no indirection)
+    unsigned long long heap[kHeapSize + 1];
     uint16_t bl_count[kMaxBits + 1];
 };
 
@@ -292,60 +294,66 @@ __device__ __forceinline__ uint32_t bi_reverse(uint32_t code, int len) {
 __device__ int build_tree(TreeWork &t, int elems, const uint8_t *stree_len, const uint8_t *extra, int base, int max_length,
                           long long &opt_len, long long &static_len, uint16_t *codes) {
     int heap_len = 0, heap_max = kHeapSize, max_code = -1;
+    auto entry = [&](int n) { return ((((unsigned long long)t.freq[n] << 8) | t.depth[n]) << 16) | (unsigned long long)n; };
     for (int n = 0; n < elems; ++n) {
         if (t.freq[n] != 0) {
-            t.heap[++heap_len] = (uint16_t)(max_code = n);
             t.depth[n] = 0;
+            t.heap[++heap_len] = entry(max_code = n);
         } else {
             t.len[n] = 0;
         }
     }
     while (heap_len < 2) {
         const int node = (max_code < 2) ? ++max_code : 0;
-        t.heap[++heap_len] = (uint16_t)node;
         t.freq[node] = 1;
         t.depth[node] = 0;
+        t.heap[++heap_len] = entry(node);
         opt_len--;
         if (stree_len) static_len -= stree_len[node];
     }
-    auto smaller = [&](int n, int m) {
-        return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && t.depth[n] <= t.depth[m]);
-    };
     auto pqdownheap = [&](int k) {
-        const int v = t.heap[k];
+        const unsigned long long v = t.heap[k];
         int j = k << 1;
         while (j <= heap_len) {
-            if (j < heap_len && smaller(t.heap[j + 1], t.heap[j])) j++;
-            if (smaller(v, t.heap[j])) break;
-            t.heap[k] = t.heap[j];
+            unsigned long long hj = t.heap[j];
+            if (j < heap_len) {
+                const unsigned long long hj1 = t.heap[j + 1];
+                if ((hj1 >> 16) <= (hj >> 16)) {   // smaller(heap[j + 1], heap[j])
+                    hj = hj1;
+                    j++;
+                }
+            }
+            if ((v >> 16) <= (hj >> 16)) break;   // smaller(v, heap[j])
+            t.heap[k] = hj;
             k = j;
             j <<= 1;
         }
-        t.heap[k] = (uint16_t)v;
+        t.heap[k] = v;
     };
     for (int n = heap_len / 2; n >= 1; --n) pqdownheap(n);
     int node = elems;
     do {
-        const int n = t.heap[1];
+        const int n = (int)(t.heap[1] & 0xFFFFu);
         t.heap[1] = t.heap[heap_len--];
         pqdownheap(1);
-        const int m = t.heap[1];
-        t.heap[--heap_max] = (uint16_t)n;
-        t.heap[--heap_max] = (uint16_t)m;
+        const int m = (int)(t.heap[1] & 0xFFFFu);
+        t.heap[--heap_max] = (unsigned long long)n;   // below heap_max only the node numbers are used
+        t.heap[--heap_max] = (unsigned long long)m;
         t.freq[node] = t.freq[n] + t.freq[m];
         t.depth[node] = (uint8_t)((t.depth[n] >= t.depth[m] ? t.depth[n] : t.depth[m]) + 1);
         t.dad[n] = t.dad[m] = (uint16_t)node;
-        t.heap[1] = (uint16_t)node++;
+        t.heap[1] = entry(node);
+        node++;
         pqdownheap(1);
     } while (heap_len >= 2);
-    t.heap[--heap_max] = t.heap[1];
+    t.heap[--heap_max] = t.heap[1] & 0xFFFFu;
     // gen_bitlen
     for (int b = 0; b <= kMaxBits; ++b) t.bl_count[b] = 0;
     int overflow = 0;
-    t.len[t.heap[heap_max]] = 0;
+    t.len[(int)t.heap[heap_max]] = 0;
     int h;
     for (h = heap_max + 1; h < kHeapSize; ++h) {
-        const int n = t.heap[h];
+        const int n = (int)t.heap[h];
         int bits = t.len[t.dad[n]] + 1;
         if (bits > max_length) {
             bits = max_length;
@@ -371,7 +379,7 @@ __device__ int build_tree(TreeWork &t, int elems, const uint8_t *stree_len, cons
         for (int bits = max_length; bits != 0; --bits) {
             int n = t.bl_count[bits];
             while (n != 0) {
-                const int m = t.heap[--h];
+                const int m = (int)t.heap[--h];
                 if (m > max_code) continue;
                 if (t.len[m] != bits) {
                     opt_len += ((long long)bits - t.len[m]) * t.freq[m];
@@ -451,7 +459,8 @@ __device__ void walk_tree(const uint16_t *lens, int max_code, uint32_t *blfreq, 
 
 __device__ __forceinline__ int static_l_len(int n) { return n < 144 ? 8 : (n < 256 ? 9 : (n < 280 ? 7 : 8)); }
 
-// _tr_flush_block for one block: trees, static / dynamic decision, header bits, code tables
+// _tr_flush_block for one block: trees, static / dynamic decision, header bits, code tables (one thread per block:
+// the work is one long data-dependent sequential loop nest)
 __global__ void __launch_bounds__(32)
 png_tree_kernel(const uint32_t *__restrict__ lfreq, const uint32_t *__restrict__ ntok, const uint32_t *__restrict__ blockpos,
                 BlockInfo *__restrict__ info, const Geom G) {
@@ -695,32 +704,55 @@ __device__ __forceinline__ uint32_t crc_update(uint32_t crc, uint8_t byte, const
     return table[(crc ^ byte) & 0xFFu] ^ (crc >> 8);
 }
 
-// chunk lengths, types and CRCs (thread per chunk: 8 KiB sequential), signature, IHDR, IEND, file size
-__global__ void __launch_bounds__(128)
+// chunk lengths, types and CRCs, signature, IHDR, IEND, file size.  One warp per IDAT chunk: a full chunk's 8192 data
+// bytes are 32 segments of 256 bytes, every lane runs the CRC register over its segment from state 0, and lane 0 folds
+// the partial states with the linear "advance by 256 zero bytes" operator (crc_table[256 ..] = its 4 byte tables):
+//   state(s, A || B) = advance_|B|(state(s, A)) ^ state(0, B).
+// The last (short) chunk is done by lane 0 alone.
+__device__ __forceinline__ uint32_t crc_advance256(uint32_t c, const uint32_t *__restrict__ t) {
+    return t[256 + (c & 0xFFu)] ^ t[512 + ((c >> 8) & 0xFFu)] ^ t[768 + ((c >> 16) & 0xFFu)] ^ t[1024 + (c >> 24)];
+}
+
+__global__ void __launch_bounds__(256)
 png_finish_kernel(uint8_t *__restrict__ out, const unsigned long long *__restrict__ zbits,
                   const uint32_t *__restrict__ crc_table, unsigned long long *__restrict__ sizes, const Geom G) {
     const int img = blockIdx.y;
     const unsigned long long zb = zbits[img];
+    const int lane = threadIdx.x & 31;
+    const size_t c = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // chunk = warp
     if (zb == 0ull) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) sizes[img] = 0ull;
+        if (c == 0 && lane == 0) sizes[img] = 0ull;
         return;
     }
     const size_t L = zlib_len(zb);
     const size_t nchunks = (L + kIdat - 1) / kIdat;
     uint8_t *o = out + (size_t)img * G.out_cap;
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < nchunks) {
         uint8_t *ch = o + 33 + c * (kIdat + 12);
         const uint32_t len = (uint32_t)((c + 1 < nchunks) ? kIdat : L - c * kIdat);
-        ch[0] = (uint8_t)(len >> 24); ch[1] = (uint8_t)(len >> 16); ch[2] = (uint8_t)(len >> 8); ch[3] = (uint8_t)len;
-        ch[4] = 'I'; ch[5] = 'D'; ch[6] = 'A'; ch[7] = 'T';
         uint32_t crc = 0xFFFFFFFFu;
-        for (uint32_t k = 4; k < 8 + len; ++k) crc = crc_update(crc, ch[k], crc_table);
-        crc ^= 0xFFFFFFFFu;
-        uint8_t *e = ch + 8 + len;
-        e[0] = (uint8_t)(crc >> 24); e[1] = (uint8_t)(crc >> 16); e[2] = (uint8_t)(crc >> 8); e[3] = (uint8_t)crc;
+        const uint8_t typ[4] = {'I', 'D', 'A', 'T'};
+        for (int k = 0; k < 4; ++k) crc = crc_update(crc, typ[k], crc_table);
+        if (len == kIdat) {
+            const uint8_t *seg = ch + 8 + lane * 256;
+            uint32_t r = 0;
+            for (int k = 0; k < 256; ++k) r = crc_update(r, seg[k], crc_table);
+            for (int k = 0; k < 32; ++k) {
+                const uint32_t rk = __shfl_sync(0xffffffffu, r, k);
+                crc = crc_advance256(crc, crc_table) ^ rk;
+            }
+        } else if (lane == 0) {
+            for (uint32_t k = 0; k < len; ++k) crc = crc_update(crc, ch[8 + k], crc_table);
+        }
+        if (lane == 0) {
+            ch[0] = (uint8_t)(len >> 24); ch[1] = (uint8_t)(len >> 16); ch[2] = (uint8_t)(len >> 8); ch[3] = (uint8_t)len;
+            ch[4] = 'I'; ch[5] = 'D'; ch[6] = 'A'; ch[7] = 'T';
+            crc ^= 0xFFFFFFFFu;
+            uint8_t *e = ch + 8 + len;
+            e[0] = (uint8_t)(crc >> 24); e[1] = (uint8_t)(crc >> 16); e[2] = (uint8_t)(crc >> 8); e[3] = (uint8_t)crc;
+        }
     }
-    if (c == 0) {
+    if (c == 0 && lane == 0) {
         const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
         for (int k = 0; k < 8; ++k) o[k] = sig[k];
         uint8_t *h = o + 8;
