@@ -118,34 +118,34 @@ def main():
                           "this_framework_first_s": t_gpu[0], "this_framework_s": min(t_gpu[1:]),
                           "same_pixels": bool(np.array_equal(got, want))}), flush=True)
 
-        # ---- a folder of JPEG panoramas -> jpg views (the codec rows either side of the path on the GPU) ----
+        # ---- a folder of JPEG panoramas -> jpg / png views (the codec rows either side of the path on the GPU) ----
         n_files = 8
         folder = td / "folder"
         folder.mkdir()
         for i in range(n_files):
             cv2.imwrite(str(folder / f"p{i}.jpg"), synth.smooth(c["Wp"], c["Hp"], 100 + i))
-        out_cpu, out_gpu = td / "folder_cpu", td / "folder_gpu"
-        out_cpu.mkdir()
-        ref_port.clear_caches()
-        t0 = time.perf_counter()
-        for f in sorted(folder.iterdir()):           # ref main :320-341: one image after the other
-            img = cv2.imread(str(f))
-            views = ref_port.process_image_views(img, c["yaws"], c["pitches"], c["W"], c["H"], c["fov"])
-            for k, yaw in enumerate(c["yaws"]):
-                for j, p in enumerate(c["pitches"]):
-                    cv2.imwrite(str(out_cpu / f"{f.stem}_{c['W']}x{c['H']}_yaw_{yaw}_pitch_{p}.jpg"), views[k][j])
-        cpu_s = time.perf_counter() - t0
-        pkg.main(str(folder), str(td / "warm"), c["yaws"], c["pitches"], c["W"], c["H"], num_workers=info["workers"],
-                 output_format="jpg", fov_deg=c["fov"])        # warm-up: allocations, tables
-        t0 = time.perf_counter()
-        pkg.main(str(folder), str(out_gpu), c["yaws"], c["pitches"], c["W"], c["H"], num_workers=info["workers"],
-                 output_format="jpg", fov_deg=c["fov"])
-        gpu_s = time.perf_counter() - t0
-        same = all((out_cpu / f.name).read_bytes() == f.read_bytes() for f in out_gpu.iterdir())
-        print(json.dumps({"folder": f"{n_files} x 8192x4096 jpg -> {n_files * 12} x 1920x1080 jpg",
-                          "reference_flow_s": cpu_s, "this_framework_s": gpu_s, "speedup": cpu_s / gpu_s,
-                          "files_byte_identical": bool(same), "n_files_out": len(list(out_gpu.iterdir()))}), flush=True)
-
+        for fmt in ("jpg", "png"):
+            out_cpu, out_gpu = td / f"folder_cpu_{fmt}", td / f"folder_gpu_{fmt}"
+            out_cpu.mkdir()
+            ref_port.clear_caches()
+            t0 = time.perf_counter()
+            for f in sorted(folder.iterdir()):           # ref main :320-341: one image after the other
+                img = cv2.imread(str(f))
+                views = ref_port.process_image_views(img, c["yaws"], c["pitches"], c["W"], c["H"], c["fov"])
+                for k, yaw in enumerate(c["yaws"]):
+                    for j, p in enumerate(c["pitches"]):
+                        cv2.imwrite(str(out_cpu / f"{f.stem}_{c['W']}x{c['H']}_yaw_{yaw}_pitch_{p}.{fmt}"), views[k][j])
+            cpu_s = time.perf_counter() - t0
+            pkg.main(str(folder), str(td / f"warm_{fmt}"), c["yaws"], c["pitches"], c["W"], c["H"], num_workers=info["workers"],
+                     output_format=fmt, fov_deg=c["fov"])        # warm-up: allocations, tables
+            t0 = time.perf_counter()
+            pkg.main(str(folder), str(out_gpu), c["yaws"], c["pitches"], c["W"], c["H"], num_workers=info["workers"],
+                     output_format=fmt, fov_deg=c["fov"])
+            gpu_s = time.perf_counter() - t0
+            same = all((out_cpu / f.name).read_bytes() == f.read_bytes() for f in out_gpu.iterdir())
+            print(json.dumps({"folder": f"{n_files} x 8192x4096 jpg -> {n_files * 12} x 1920x1080 {fmt}",
+                              "reference_flow_s": cpu_s, "this_framework_s": gpu_s, "speedup": cpu_s / gpu_s,
+                              "files_byte_identical": bool(same), "n_files_out": len(list(out_gpu.iterdir()))}), flush=True)
 
 if __name__ == "__main__":
     main()
