@@ -379,9 +379,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
 def files_extras(pkg, proj, pano, shifts, consts):
     """Side measurement (not the headline metric): the codec rows either side of the path.  One 8192x4096
-    JPEG file in host memory -> the 12 views as JPEG files in host memory, (a) decoded (host Huffman stage + device),
-    projected and encoded on the GPU, 4 images in flight on 4 host threads; (b) the reference's flow on the host cores:
-    cv2.imdecode -> oracle port of the projection -> cv2.imencode per view.  Same bytes out (checked)."""
+    JPEG file in host memory -> the 12 views as jpg / png files in host memory, (a) decoded, projected and encoded on the
+    GPU, 4 images in flight on 4 host threads; (b) the reference's flow on the host cores: cv2.imdecode -> oracle port of
+    the projection -> cv2.imencode per view.  Same bytes out (checked)."""
     import cv2
     from concurrent.futures import ThreadPoolExecutor
 
@@ -389,34 +389,39 @@ def files_extras(pkg, proj, pano, shifts, consts):
 
     data = cv2.imencode(".jpg", pano)[1].tobytes()
     n_img, n_thr = 8, 4
+    out = {}
+    for fmt in ("jpg", "png"):
+        def gpu_one(_):
+            with proj.slots(1) as (s,):
+                proj.upload_jpeg(s, data)
+                if fmt == "jpg":
+                    return proj.project_jpeg(s, shifts, consts, W, H)
+                return proj.process_image_png(s, None, shifts, consts, W, H, want_pixels=False)[0]
 
-    def gpu_one(_):
-        with proj.slots(1) as (s,):
-            proj.upload_jpeg(s, data)
-            return proj.project_jpeg(s, shifts, consts, W, H)
-
-    with ThreadPoolExecutor(n_thr) as ex:
-        first = list(ex.map(gpu_one, range(n_thr)))[0]
-        t0 = time.perf_counter()
-        list(ex.map(gpu_one, range(n_img)))
-        gpu_s = (time.perf_counter() - t0) / n_img
-    ref_port.clear_caches()
-    ref_files = None
-    cpu_s = []
-    for _ in range(2):  # second pass = warm map caches
-        t0 = time.perf_counter()
-        img = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
-        views = ref_port.process_image_views(img, YAWS, PITCHES, W, H, FOV)
-        ref_files = [cv2.imencode(".jpg", v)[1].tobytes() for per_yaw in views for v in per_yaw]
-        cpu_s.append(time.perf_counter() - t0)
-    ref_port.clear_caches()
-    return {"jpeg_files": {
-        "what": "8192x4096 JPEG bytes (host) -> 12 x 1920x1080 JPEG files (host); decode, projection and encode on the GPU "
-                "(host Huffman stage), 4 images in flight; CPU = cv2.imdecode + oracle port + cv2.imencode, warm maps",
-        "byte_identical_to_cpu_flow": bool(first == ref_files),
-        "gpu_ms_per_image": gpu_s * 1e3, "gpu_mpix_s": PX_PER_IMAGE / gpu_s / 1e6,
-        "cpu_ms_per_image": min(cpu_s) * 1e3, "cpu_mpix_s": PX_PER_IMAGE / min(cpu_s) / 1e6,
-        "input_file_bytes": len(data), "output_file_bytes": sum(len(f) for f in first)}}
+        with ThreadPoolExecutor(n_thr) as ex:
+            first = list(ex.map(gpu_one, range(n_thr)))[0]
+            t0 = time.perf_counter()
+            list(ex.map(gpu_one, range(n_img)))
+            gpu_s = (time.perf_counter() - t0) / n_img
+        ref_port.clear_caches()
+        ref_files = None
+        cpu_s = []
+        for _ in range(2):  # second pass = warm map caches
+            t0 = time.perf_counter()
+            img = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+            views = ref_port.process_image_views(img, YAWS, PITCHES, W, H, FOV)
+            ref_files = [cv2.imencode("." + fmt, v)[1].tobytes() for per_yaw in views for v in per_yaw]
+            cpu_s.append(time.perf_counter() - t0)
+        ref_port.clear_caches()
+        out[fmt + "_files"] = {
+            "what": f"8192x4096 JPEG bytes (host) -> 12 x 1920x1080 {fmt} files (host); decode (Huffman stage included), "
+                    f"projection and encode on the GPU, 4 images in flight; CPU = cv2.imdecode + oracle port + cv2.imencode, "
+                    f"warm maps",
+            "byte_identical_to_cpu_flow": bool(first == ref_files),
+            "gpu_ms_per_image": gpu_s * 1e3, "gpu_mpix_s": PX_PER_IMAGE / gpu_s / 1e6,
+            "cpu_ms_per_image": min(cpu_s) * 1e3, "cpu_mpix_s": PX_PER_IMAGE / min(cpu_s) / 1e6,
+            "input_file_bytes": len(data), "output_file_bytes": sum(len(f) for f in first)}
+    return out
 
 
 _REAL_STDOUT = None
