@@ -53,6 +53,7 @@ def test_decoder_fuzz(proj):
 def test_largest_shapes(proj):
     view = synth.smooth(3840, 2160, 5)                                  # a C4 view
     assert proj.encode_jpeg(view)[0] == cv2.imencode(".jpg", view)[1].tobytes()
+    assert proj.encode_png(view)[0] == cv2.imencode(".png", view)[1].tobytes()
     pano = synth.smooth(16384, 8192, 6)                                 # the C4 panorama as a JPEG file
     data = cv2.imencode(".jpg", pano, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes()
     ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
