@@ -196,9 +196,11 @@ int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
  * if coef != NULL the quantised coefficients (int16, natural order, component planes [by][bx][64], Y then Cb then Cr;
  * capacity in elements) exactly as jdhuff.c decodes them. */
 int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t capacity, int32_t *layout);
-/* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, bit-identical pixels): the Huffman
- * stage runs on the calling CPU thread (outside the context lock), inverse DCT, chroma upsampling and colour
- * conversion on the device; the pixels never exist in host memory. */
+/* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, bit-identical pixels): Huffman
+ * decoding (self-synchronising subsequences; P2P_OPT_GPU_HUFFMAN), inverse DCT, chroma upsampling and colour
+ * conversion all run on the device, the host only removes the FF 00 byte stuffing; the pixels never exist in host
+ * memory.  If the device Huffman stage does not converge the library's own host decoder (calling thread, outside the
+ * context lock) takes over. */
 int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp);
 /* Same decoder, pixels returned to the host (BGR, row_stride bytes per row, at least capacity_rows rows): the array
  * cv2.imread / cv2.imdecode would return.  Synchronous; the slot's panorama is invalidated. */
