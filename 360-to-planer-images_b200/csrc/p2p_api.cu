@@ -85,7 +85,7 @@ struct Slot {
     int32_t *jd_dc = nullptr;                 // [2][3][dc_stride]: DC differences, exclusive sums
     size_t jd_dc_cap = 0;
     unsigned long long *jd_tot_d = nullptr;   // scan totals (device) [4]
-    struct JdFlags { int changed[8]; int bad; int pad; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
+    struct JdFlags { int changed[8]; int bad; int out_of_range; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
     uint8_t *jd_sub = nullptr;                // subsequence layout + first subsequence of every restart interval
     size_t jd_sub_cap = 0;
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
@@ -602,6 +602,14 @@ int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8
 // Huffman stage on the device (p2pjdec::huff_*): fills s.jd_coef_d.  Returns P2P_OK, an error, or 1 = "not handled"
 // (no convergence, inconsistent block counts, unexpected markers): the caller then runs the host decoder.
 // The destuffing pass runs on the calling thread; the lock is held only while enqueueing.
+int ensure_jd_flags(p2p_ctx *ctx, Slot &s) {
+    if (s.jd_flags_h) return P2P_OK;
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&s.jd_flags_h), sizeof(*s.jd_flags_h), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(s.jd_flags_h, 0, sizeof(*s.jd_flags_h));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.jd_flags_d), s.jd_flags_h, 0));
+    return P2P_OK;
+}
+
 int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p2pjdec::Parsed &P) {
     using namespace p2pjdec;
     const Info &I = P.info;
@@ -630,6 +638,7 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
                 dst[n++] = 0xFF;
                 p = ff + 2;
             } else if (m >= 0xD0 && m <= 0xD7 && P.dri) {
+                if (m != 0xD0 + ((ivl_byte.size() - 1) & 7)) return 1;   // out of sequence: damaged (see decode_scan)
                 if (n >= (1ull << 29)) return 1;
                 ivl_byte.push_back((uint32_t)n);
                 p = ff + 2;
@@ -715,10 +724,8 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
         d_ivl_first = reinterpret_cast<uint32_t *>(s.jd_sub + sub_bytes);
         if (!s.jd_tables) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tables), 3 * sizeof(DevHuff)));
         if (!s.jd_tot_d) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tot_d), 4 * sizeof(unsigned long long)));
-        if (!s.jd_flags_h) {
-            CK(cudaHostAlloc(reinterpret_cast<void **>(&s.jd_flags_h), sizeof(*s.jd_flags_h), cudaHostAllocMapped | cudaHostAllocPortable));
-            CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.jd_flags_d), s.jd_flags_h, 0));
-        }
+        int frc = ensure_jd_flags(ctx, s);
+        if (frc) return frc;
         CK(cudaMemcpyAsync(s.jd_stream, w, n_words * 4, cudaMemcpyHostToDevice, st));
         // the tables below live in pageable memory: cudaMemcpyAsync stages them before it returns
         CK(cudaMemcpyAsync(s.jd_tables, T, sizeof(T), cudaMemcpyHostToDevice, st));
@@ -770,7 +777,7 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     int32_t *dcdiff = s.jd_dc;
     uint32_t *dcsum = reinterpret_cast<uint32_t *>(s.jd_dc + 3 * (size_t)G.dc_stride);
     huff_write_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, d_ivl_first, s.jd_states, s.jd_nblk + nsub4,
-                                           s.jd_coef_d, dcdiff);
+                                           s.jd_coef_d, dcdiff, &s.jd_flags_d->out_of_range);
     // per component: exclusive sums of the DC differences in scan order (mod 2^32 arithmetic = two's complement sums)
     CK(cudaMemcpyAsync(s.jd_nblk, G.dc_count, 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // reuse as n_per_image
     p2pjpeg::jpeg_scan_kernel<<<3, 1024, 0, st>>>(reinterpret_cast<const uint32_t *>(dcdiff), dcsum, s.jd_nblk, 0u,
@@ -797,6 +804,8 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
         if (rc) return rc;
         CK(cudaSetDevice(ctx->device));
         use_gpu = ctx->opt_gpu_huffman;
+        rc = ensure_jd_flags(ctx, s);
+        if (rc) return rc;
         const size_t bytes = I.n_coef * sizeof(int16_t);
         if (s.jd_coef_h_cap < bytes) {
             CK(cudaStreamSynchronize(s.stream));  // an earlier upload may still read the old staging buffer
@@ -808,6 +817,7 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
         } else {
             CK(cudaStreamSynchronize(s.stream));
         }
+        s.jd_flags_h->out_of_range = 0;   // "damaged data" flag of the write pass and the IDCT; the stream is drained
     }
     bool coef_on_device = false;
     if (use_gpu) {
@@ -841,7 +851,7 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
         memcpy(Q.q, I.quant[k], sizeof(Q.q));
         const int nb = I.bw[k] * I.bh[k];
         jpegdec_idct_kernel<<<(nb + 31) / 32, 256, 0, s.stream>>>(s.jd_coef_d + I.coef_off[k], s.jd_planes + plane_off[k], Q, nb,
-                                                                  I.bw[k], I.bw[k] * 8);
+                                                                  I.bw[k], I.bw[k] * 8, &s.jd_flags_d->out_of_range);
     }
     ColorParams C;
     C.y = s.jd_planes + plane_off[0];
@@ -1501,14 +1511,26 @@ int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len
     int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride);
     if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
-    rc = prepare_slot(ctx, s, P.info.W, P.info.H);
-    if (rc) return rc;
-    *Wp = P.info.W;
-    *Hp = P.info.H;
-    return launch_pack(ctx, s, s.d_bgr, dstride, 0, P.info.H);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CK(cudaSetDevice(ctx->device));
+        rc = prepare_slot(ctx, s, P.info.W, P.info.H);
+        if (rc) return rc;
+        *Wp = P.info.W;
+        *Hp = P.info.H;
+        rc = launch_pack(ctx, s, s.d_bgr, dstride, 0, P.info.H);
+        if (rc) return rc;
+    }
+    // the IDCT reports coefficient blocks no 8-bit encoder produces (damaged data): wait for it outside the lock
+    cudaSetDevice(ctx->device);
+    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "JPEG decoder: CUDA error");
+    if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->out_of_range)) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        s.valid = false;
+        return fail(ctx, P2P_ERR_UNSUPPORTED, "JPEG data out of range (damaged file: fall back to cv2.imread)");
+    }
+    return P2P_OK;
 }
 
 int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
@@ -1531,6 +1553,8 @@ int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uin
     }
     cudaSetDevice(ctx->device);
     if (cudaStreamSynchronize(s.stream) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "JPEG decoder: CUDA error");
+    if (*reinterpret_cast<volatile int *>(&s.jd_flags_h->out_of_range))
+        return fail(ctx, P2P_ERR_UNSUPPORTED, "JPEG data out of range (damaged file: fall back to cv2.imread)");
     return P2P_OK;
 }
 

@@ -33,6 +33,11 @@ struct Info {
     size_t n_coef = 0;
 };
 
+// The DCT of 8-bit samples has an L2 norm <= 1024 per block (Parseval), quantisation adds at most 1020: a block of
+// dequantised coefficients beyond this norm is damaged data.  libjpeg-turbo's SIMD IDCT (16-bit lanes) wraps on such
+// blocks in ways this decoder does not restate, so the file is declined (cv2.imread handles it).
+constexpr float kMaxBlockNorm = 2048.f;
+
 // ---- host: markers + Huffman decoding ---------------------------------------------------------------------------
 static const uint8_t kNat[64 + 16] = {  // zigzag position -> natural index (+ 16 safety entries like jpeg_natural_order)
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
@@ -56,6 +61,9 @@ inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, Huff
     memcpy(t.vals, vals, (size_t)nvals);
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
+        // jdhuff.c jpeg_make_d_derived_tbl: the codes of a length must fit with the all-ones code left unused
+        // (checked before any table write: an over-subscribed length would index past look[])
+        if (bits[l - 1] && code + bits[l - 1] >= (1 << l)) return false;
         if (bits[l - 1]) {
             t.valoff[l] = k - code;
             for (int i = 0; i < bits[l - 1]; ++i, ++k, ++code) {
@@ -68,7 +76,6 @@ inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, Huff
         } else {
             t.maxcode[l] = -1;
         }
-        if (code > (1 << l)) return false;
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
@@ -162,18 +169,18 @@ inline int exif_orientation(const uint8_t *seg, size_t len) {
     const uint8_t *t = seg + 6;
     const size_t n = len - 6;
     const bool le = (t[0] == 'I' && t[1] == 'I'), be = (t[0] == 'M' && t[1] == 'M');
-    if (!le && !be) return 0;
+    if (!le && !be) return -1;
     auto r16 = [&](size_t o) -> uint32_t { return le ? (uint32_t)(t[o] | (t[o + 1] << 8)) : (uint32_t)((t[o] << 8) | t[o + 1]); };
     auto r32 = [&](size_t o) -> uint32_t {
         return le ? (uint32_t)t[o] | ((uint32_t)t[o + 1] << 8) | ((uint32_t)t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24)
                   : ((uint32_t)t[o] << 24) | ((uint32_t)t[o + 1] << 16) | ((uint32_t)t[o + 2] << 8) | (uint32_t)t[o + 3];
     };
     const size_t ifd = r32(4);
-    if (ifd + 2 > n) return 0;
+    if (ifd + 2 > n) return -1;
     const uint32_t cnt = r16(ifd);
     for (uint32_t i = 0; i < cnt; ++i) {
         const size_t e = ifd + 2 + 12 * (size_t)i;
-        if (e + 12 > n) return 0;
+        if (e + 12 > n) return -1;
         if (r16(e) == 0x0112) return (int)r16(e + 8);
     }
     return 0;
@@ -203,8 +210,10 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
         if (i + 4 > len) return 1;
         const int m = d[i + 1];
         i += 2;
-        if (m == 0xD9) return 1;
-        if ((m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+        // only the segments a baseline JFIF / EXIF file is made of; libjpeg rejects or special-cases the rest
+        const bool known = (m >= 0xE0 && m <= 0xEF) || m == 0xFE || m == 0xDB || m == 0xC4 || m == 0xC0 || m == 0xC1 ||
+                           m == 0xDD || m == 0xDA;
+        if (!known) return 1;
         const size_t L = ((size_t)d[i] << 8) | d[i + 1];
         if (L < 2 || i + L > len) return 1;
         const uint8_t *seg = d + i + 2;
@@ -215,12 +224,11 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
             while (j < sl) {
                 const int pq = seg[j] >> 4, t = seg[j] & 15;
                 ++j;
-                if (t > 3 || pq > 1 || j + (pq ? 128 : 64) > sl) return 1;
+                if (t > 3 || pq != 0 || j + 64 > sl) return 1;   // 16-bit tables are not baseline
                 for (int k = 0; k < 64; ++k) {
-                    const uint32_t v = pq ? (uint32_t)((seg[j + 2 * k] << 8) | seg[j + 2 * k + 1]) : seg[j + k];
-                    qt[t][kNat[k]] = (uint16_t)v;
+                    qt[t][kNat[k]] = seg[j + k];
                 }
-                j += pq ? 128 : 64;
+                j += 64;
                 have_qt[t] = true;
             }
         } else if (m == 0xC4) {
@@ -231,14 +239,17 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 int nv = 0;
                 for (int k = 0; k < 16; ++k) nv += seg[j + 1 + k];
                 if (tc > 1 || th > 3 || nv > 256 || j + 17 + nv > sl) return 1;
+                if (!tc)   // jdhuff.c jpeg_make_d_derived_tbl: DC symbols are categories 0..15
+                    for (int k = 0; k < nv; ++k)
+                        if (seg[j + 17 + k] > 15) return 1;
                 if (!build_huff(seg + j + 1, seg + j + 17, nv, tc ? P.ac[th] : P.dc[th])) return 1;
                 j += 17 + (size_t)nv;
             }
         } else if (m == 0xC0 || m == 0xC1) {
-            if (have_frame || sl < 6 || seg[0] != 8 || seg[5] != 3 || sl < 6 + 9) return 1;
+            if (have_frame || sl != 6 + 9 || seg[0] != 8 || seg[5] != 3) return 1;
             I.H = (seg[1] << 8) | seg[2];
             I.W = (seg[3] << 8) | seg[4];
-            if (I.W <= 0 || I.H <= 0) return 1;
+            if (I.W <= 0 || I.H <= 0 || I.W > 65500 || I.H > 65500) return 1;   // JPEG_MAX_DIMENSION
             for (int k = 0; k < 3; ++k) {
                 cid[k] = seg[6 + 3 * k];
                 hs[k] = seg[7 + 3 * k] >> 4;
@@ -246,21 +257,22 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 tq[k] = seg[8 + 3 * k];
                 if (tq[k] > 3) return 1;
             }
+            if (cid[0] == cid[1] || cid[0] == cid[2] || cid[1] == cid[2]) return 1;
             have_frame = true;
         } else if (m >= 0xC2 && m <= 0xCF) {
             return 1;  // progressive, lossless, arithmetic, hierarchical
         } else if (m == 0xDD) {
-            if (sl < 2) return 1;
+            if (sl != 2) return 1;
             P.dri = (seg[0] << 8) | seg[1];
         } else if (m == 0xE0) {
             if (sl >= 5 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
         } else if (m == 0xE1) {
             const int o = exif_orientation(seg, sl);
-            if (o > 1) return 1;  // cv2.imread rotates / flips such files
+            if (o > 1 || o < 0) return 1;  // cv2.imread rotates / flips such files; -1 = malformed EXIF: leave it to cv2
         } else if (m == 0xEE) {
             if (sl >= 5 && memcmp(seg, "Adobe", 5) == 0) return 1;
         } else if (m == 0xDA) {
-            if (!have_frame || sl < 1 + 6 + 3 || seg[0] != 3) return 1;
+            if (!have_frame || sl != 1 + 6 + 3 || seg[0] != 3) return 1;
             for (int k = 0; k < 3; ++k) {
                 if (seg[1 + 2 * k] != cid[k]) return 1;
                 P.td[k] = seg[2 + 2 * k] >> 4;
@@ -304,6 +316,7 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
     int pred[3] = {0, 0, 0};
     const int nblk[3] = {I.hmax * I.vmax, 1, 1};
     int togo = P.dri;
+    int next_rst = 0;   // restart markers must come in sequence: libjpeg resynchronises by its own heuristics otherwise
     for (int my = 0; my < I.mcuy; ++my) {
         for (int mx = 0; mx < I.mcux; ++mx) {
             if (P.dri) {
@@ -314,7 +327,8 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                     br.n = 0;
                     br.marker = false;
                     br.zero_bits = 0;
-                    if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] < 0xD0 || br.p[1] > 0xD7) return 1;
+                    if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] != 0xD0 + next_rst) return 1;
+                    next_rst = (next_rst + 1) & 7;
                     br.p += 2;
                     pred[0] = pred[1] = pred[2] = 0;
                     togo = P.dri;
@@ -333,6 +347,9 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                     if (s < 0 || s > 11) return 1;
                     if (s) pred[c] += receive_extend(br, s);
                     blk[0] = (int16_t)pred[c];
+                    const uint16_t *q = I.quant[c];
+                    float e = (float)blk[0] * q[0];   // L2 norm of the dequantised block (see kMaxBlockNorm)
+                    e *= e;
                     for (int k = 1; k < 64;) {
                         if (br.n < 32) br.fill();
                         const int32_t fa = act.fast_ac[br.peek(kFastBits)];
@@ -341,6 +358,8 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                             if (k > 63) return 1;
                             br.skip(fa & 15);
                             blk[kNat[k]] = (int16_t)(fa >> 8);
+                            const float v = (float)(fa >> 8) * q[kNat[k]];
+                            e += v * v;
                             ++k;
                             continue;
                         }
@@ -356,8 +375,11 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                         k += r;
                         if (k > 63) return 1;
                         blk[kNat[k]] = (int16_t)receive_extend(br, s);
+                        const float v = (float)blk[kNat[k]] * q[kNat[k]];
+                        e += v * v;
                         ++k;
                     }
+                    if (e > kMaxBlockNorm * kMaxBlockNorm) return 1;
                 }
             }
         }
@@ -431,7 +453,8 @@ __device__ __forceinline__ int extend_bits(uint32_t v, int s) {   // jdhuff.c HU
     return ((int)v < (1 << (s - 1))) ? (int)v - (1 << s) + 1 : (int)v;
 }
 
-// symbol and code length for the code at the top of `win`; an invalid code (garbage decoding) consumes 16 bits
+// symbol and code length for the code at the top of `win`; -1 = no such code (garbage decoding or damaged data):
+// it consumes 16 bits
 __device__ __forceinline__ int slow_symbol(uint32_t win, const int32_t *maxcode, const int32_t *valoff,
                                            const uint8_t *vals, int nvals_mask, int &len) {
     const uint32_t w16 = win >> 16;
@@ -443,7 +466,7 @@ __device__ __forceinline__ int slow_symbol(uint32_t win, const int32_t *maxcode,
         }
     }
     len = 16;
-    return 0;
+    return -1;
 }
 
 struct HState {
@@ -463,12 +486,14 @@ __device__ __forceinline__ HState unpack_state(unsigned long long v) {
 
 // Decode from state `st` until the bit position reaches `end`.  WRITE: coefficients (natural order, DC = difference)
 // go to their block, starting with scan-order block `blk` and stopping at block `blk_limit`; returns the number of blocks
-// completed.
+// completed.  The synchronisation passes decode garbage by design and tolerate everything; the WRITE pass follows the
+// true trajectory, so what decode_scan declines (no such code, DC category > 11, a coefficient index past 63) is
+// damaged data there too: `damaged` is set and the file is left to libjpeg.
 template <bool WRITE>
 __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T,
                                                       const HuffGeom &G, HState &st, uint32_t end, uint32_t blk,
                                                       uint32_t blk_limit, int16_t *__restrict__ coef,
-                                                      int32_t *__restrict__ dcdiff) {
+                                                      int32_t *__restrict__ dcdiff, bool &damaged) {
     uint32_t done = 0;
     int16_t *cur = nullptr;
     int comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
@@ -494,7 +519,8 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
             } else {
                 s = slow_symbol(win, H.dc_maxcode, H.dc_valoff, H.dc_vals, 15, len);
             }
-            s = (s > 15) ? 15 : s;
+            if (WRITE && (s < 0 || s > 11)) damaged = true;
+            s = (s < 0) ? 0 : (s > 15) ? 15 : s;
             if (WRITE) {
                 const int diff = s ? extend_bits((win << len) >> (32 - s), s) : 0;
                 const uint32_t mcu = blk / (uint32_t)G.nb;
@@ -509,6 +535,7 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
         const int32_t fa = H.ac_fast[win >> (32 - kFastBits)];
         if (fa) {
             st.z += (fa >> 4) & 15;
+            if (WRITE && st.z > 63) damaged = true;
             if (WRITE && st.z < 64) cur[kNatDev[st.z]] = (int16_t)(fa >> 8);
             st.z += 1;
             st.pos += (uint32_t)(fa & 15);
@@ -520,6 +547,10 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
                 rs = e & 0xFF;
             } else {
                 rs = slow_symbol(win, H.ac_maxcode, H.ac_valoff, H.ac_vals, 255, len);
+                if (rs < 0) {
+                    if (WRITE) damaged = true;
+                    rs = 0;
+                }
             }
             const int r = rs >> 4, s = rs & 15;
             if (s == 0) {
@@ -527,6 +558,7 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
                 st.pos += (uint32_t)len;
             } else {
                 st.z += r;
+                if (WRITE && st.z > 63) damaged = true;
                 if (WRITE && st.z < 64) cur[kNatDev[st.z]] = (int16_t)extend_bits((win << len) >> (32 - s), s);
                 st.z += 1;
                 st.pos += (uint32_t)(len + s);
@@ -569,7 +601,8 @@ huff_sync_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, 
         st = unpack_state(prev);
         *changed = 1;
     }
-    nblk[i] = huff_decode_range<false>(w, T, G, st, q.end, 0u, 0u, nullptr, nullptr);
+    bool unused = false;
+    nblk[i] = huff_decode_range<false>(w, T, G, st, q.end, 0u, 0u, nullptr, nullptr, unused);
     endst[i] = pack_state(st);
 }
 
@@ -592,7 +625,7 @@ __global__ void __launch_bounds__(128)
 huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
                   const SubSeq *__restrict__ sub, const uint32_t *__restrict__ ivl_first,
                   const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
-                  int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff) {
+                  int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.n_sub) return;
     const SubSeq q = sub[i];
@@ -601,7 +634,12 @@ huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T,
     const uint32_t first_blk = q.ivl * G.ivl_blocks;
     const uint32_t blk = first_blk + (blkoff[i] - blkoff[ivl_first[q.ivl]]);
     const uint32_t limit = (first_blk + G.ivl_blocks <= G.total_blocks) ? first_blk + G.ivl_blocks : G.total_blocks;
-    huff_decode_range<true>(w, T, G, st, q.end, blk, limit, coef, dcdiff);
+    bool damaged = false;
+    huff_decode_range<true>(w, T, G, st, q.end, blk, limit, coef, dcdiff, damaged);
+    // the last block of an interval must end inside it: libjpeg feeds zero bits past a marker, this reader would
+    // continue into the next interval
+    if (i + 1 == ivl_first[q.ivl + 1] && st.pos > q.end) damaged = true;
+    if (damaged) *damaged_flag = 1;
 }
 
 // DC value of block idx of component c = sum of the differences since the start of its restart interval
@@ -681,7 +719,7 @@ struct Quant {
 // 8 threads per block, 32 blocks per CTA; plane[(by * 8 + r) * pitch + bx * 8 + c]
 __global__ void __launch_bounds__(256)
 jpegdec_idct_kernel(const int16_t *__restrict__ coef, uint8_t *__restrict__ plane, const __grid_constant__ Quant Q,
-                    int n_blocks, int bw, int pitch) {
+                    int n_blocks, int bw, int pitch, int *__restrict__ out_of_range) {
     __shared__ int ws[32][8][9];
     const int lb = threadIdx.x >> 3, l8 = threadIdx.x & 7;
     const int blk = blockIdx.x * 32 + lb;
@@ -691,6 +729,15 @@ jpegdec_idct_kernel(const int16_t *__restrict__ coef, uint8_t *__restrict__ plan
         const int16_t *c = coef + (size_t)blk * 64;
 #pragma unroll
         for (int k = 0; k < 8; ++k) in[k] = (int)c[k * 8 + l8] * (int)Q.q[k * 8 + l8];   // column l8
+        // damaged data check (kMaxBlockNorm)
+        float e = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e += (float)in[k] * (float)in[k];
+        const unsigned group = 0xFFu << (threadIdx.x & 24);   // the 8 lanes of this block
+        e += __shfl_xor_sync(group, e, 1);
+        e += __shfl_xor_sync(group, e, 2);
+        e += __shfl_xor_sync(group, e, 4);
+        if (l8 == 0 && e > kMaxBlockNorm * kMaxBlockNorm) *out_of_range = 1;
         idct_pass<13 - 2>(in, out);
 #pragma unroll
         for (int k = 0; k < 8; ++k) ws[lb][k][l8] = out[k];

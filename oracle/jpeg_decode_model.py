@@ -297,8 +297,16 @@ def decode(data: bytes) -> np.ndarray:
     comps = f["comps"]
     if len(comps) != 3:
         raise Unsupported("not a 3-component YCbCr file")
+    planes, _ = entropy_decode(p)
+    return reconstruct(p, planes)
+
+
+def reconstruct(p, planes) -> np.ndarray:
+    """Pixels from the coefficient planes of ``entropy_decode`` (dequantisation, IDCT, upsampling, colour)."""
+    f = p["frame"]
+    comps = f["comps"]
     W, H = f["W"], f["H"]
-    planes, (mcux, mcuy, hmax, vmax) = entropy_decode(p)
+    hmax, vmax = max(c[1] for c in comps), max(c[2] for c in comps)
     if (comps[0][1], comps[0][2]) != (hmax, vmax) or any((c[1], c[2]) != (1, 1) for c in comps[1:]):
         raise Unsupported("sampling factors")
     if (hmax, vmax) not in ((1, 1), (2, 1), (2, 2)):

@@ -1,0 +1,35 @@
+"""Damaged JPEG files for the decoder tests: seeded bit flips, overwritten, deleted and inserted bytes in the headers
+or in the entropy-coded scan of files written by cv2.  The rule under test: the device decoder either declines such a
+file (status -6, the caller falls back to cv2.imread as the reference does for every file) or returns exactly the
+pixels cv2.imdecode returns; a file cv2 cannot read at all must be declined."""
+import cv2
+import numpy as np
+
+from oracle import synth
+
+SAMPLING = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+
+
+def damaged_files(seed: int, count: int, max_wh=(120, 90)):
+    """Yields (label, bytes)."""
+    rng = np.random.default_rng(seed)
+    for i in range(count):
+        w, h = int(rng.integers(16, max_wh[0])), int(rng.integers(16, max_wh[1]))
+        img = synth.smooth(w, h, i) if i % 2 else synth.noise(w, h, i)
+        rst, q = int(rng.integers(0, 4)), int(rng.integers(5, 100))
+        samp = SAMPLING[int(rng.integers(0, 3))]
+        data = bytearray(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,
+                                                    cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp])[1].tobytes())
+        sos = data.find(b"\xff\xda")
+        lo, hi = ((2, sos + 14), (sos + 14, len(data) - 2), (2, len(data) - 2))[int(rng.integers(0, 3))]
+        mode = int(rng.integers(0, 3))
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                data[int(rng.integers(lo, hi))] ^= 1 << int(rng.integers(0, 8))
+        elif mode == 1:
+            data[int(rng.integers(lo, hi))] = int(rng.integers(0, 256))
+        elif rng.integers(0, 2):
+            del data[int(rng.integers(lo, hi))]
+        else:
+            data.insert(int(rng.integers(lo, hi)), int(rng.integers(0, 256)))
+        yield f"{i}:{w}x{h} q{q} rst{rst} mode{mode} [{lo},{hi})", bytes(data)

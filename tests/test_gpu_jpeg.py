@@ -176,6 +176,42 @@ def test_front_end_jpeg_input_equals_imread_path(pkg, tmp_path):
     assert np.array_equal(one, pkg.process_yaw_and_pitchs(cv2.imread(str(src / "a.jpg")), 90, [60], W, H, fov)[0])
 
 
+def test_front_end_with_damaged_jpeg_files_equals_imread_path(pkg, tmp_path, capfd):
+    """Damaged .jpg panoramas in the directory pipeline: the device decoder declines them (restart marker out of
+    sequence, a block of out-of-range coefficients, a truncated scan) or decodes them like libjpeg (a flipped value bit);
+    either way the files equal what the reference's cv2.imread pixels give, and a file cv2 cannot read is skipped."""
+    src = tmp_path / "in"
+    src.mkdir()
+    pano = synth.smooth(1024, 512, 33)
+    good = cv2.imencode(".jpg", pano, [cv2.IMWRITE_JPEG_RST_INTERVAL, 8])[1].tobytes()
+    sos = good.find(b"\xff\xda")
+    rst = good.find(b"\xff\xd2", sos)
+    files = {"seq": bytearray(good), "cut": bytearray(good[:len(good) * 2 // 3]), "junk": bytearray(b"\xff\xd8" + bytes(200))}
+    files["seq"][rst + 1] = 0xD5
+    rng = np.random.default_rng(3)
+    for k in range(6):                       # random single-bit damage in the scan: some declined, some decodable
+        d = bytearray(good)
+        d[int(rng.integers(sos + 14, len(good) - 2))] ^= 1 << int(rng.integers(0, 8))
+        files[f"bit{k}"] = d
+    for name, d in files.items():
+        (src / f"{name}.jpg").write_bytes(bytes(d))
+    W, H, fov, yaws, pitches = 160, 96, 100, [0, 180], [60, 90]
+    out = tmp_path / "out"
+    pkg.main(str(src), str(out), yaws, pitches, W, H, num_workers=3, output_format="png", fov_deg=fov)
+    for name in files:
+        img = cv2.imread(str(src / f"{name}.jpg"))
+        for y in yaws:
+            for p in pitches:
+                f = out / f"{name}_{W}x{H}_yaw_{y}_pitch_{p}.png"
+                if img is None:
+                    assert not f.exists(), name
+                    continue
+                view = pkg.process_yaw_and_pitchs(img, y, [p], W, H, fov)[0]
+                assert np.array_equal(cv2.imread(str(f)), view), (name, y, p)
+    assert cv2.imread(str(src / "junk.jpg")) is None and cv2.imread(str(src / "seq.jpg")) is not None
+    capfd.readouterr()
+
+
 def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
     """Files without restart markers are Huffman-decoded on the device (self-synchronising subsequences); the pixels
     must equal the host decoder's (= cv2's), the fallback must work, and the option must switch the stage off."""

@@ -111,3 +111,85 @@ def test_unsupported_files_are_reported(pkg):
     seg = b"\xff\xe1" + (len(exif) + 2).to_bytes(2, "big") + exif
     rotated = ok[:2] + seg + ok[2:]
     assert lib.p2p_jpeg_probe(rotated, len(rotated), C.byref(w), C.byref(h)) == -6
+
+
+def _host_stage(lib, data):
+    """(status, coefficient planes as the oracle lays them out) of the library's host entropy decoder."""
+    import ctypes as C
+
+    lay = (C.c_int32 * 10)()
+    st = lib.p2p_jpeg_coefficients(data, len(data), None, 0, lay)
+    if st:
+        return st, None
+    shapes = [(lay[5 + 2 * k], lay[4 + 2 * k], 64) for k in range(3)]
+    coef = np.zeros(sum(a * b * c for a, b, c in shapes), np.int16)
+    st = lib.p2p_jpeg_coefficients(data, len(data), coef.ctypes.data, coef.size, lay)
+    if st:
+        return st, None
+    planes, off = [], 0
+    for sh in shapes:
+        n = sh[0] * sh[1] * 64
+        planes.append(coef[off:off + n].astype(np.int64).reshape(sh))
+        off += n
+    return 0, planes
+
+
+def test_damaged_files_are_declined_or_decode_like_cv2(pkg, capfd):
+    """Seeded damage in headers and scans (tests/jpeg_damage.py): the host stage declines, or its coefficients give
+    cv2.imdecode's pixels; what cv2 cannot read is always declined.  (libjpeg has its own recovery heuristics - restart
+    resynchronisation, zero feeding, 16-bit SIMD wrap-around on out-of-range blocks - which are left to it.)"""
+    from jpeg_damage import damaged_files
+    from oracle import jpeg_decode_model as jd
+
+    lib = pkg._lib.load()
+    declined = same = 0
+    for label, data in damaged_files(2025, 400):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        st, planes = _host_stage(lib, data)
+        if st:
+            assert st == -6, label
+            declined += 1
+            continue
+        assert ref is not None, label
+        assert np.array_equal(jd.reconstruct(jd.parse(data), planes), ref), label
+        same += 1
+    capfd.readouterr()               # libjpeg's warnings about the damaged files
+    assert declined > 50 and same > 50
+
+
+def test_known_damage_patterns_are_declined(pkg):
+    import ctypes as C
+
+    lib = pkg._lib.load()
+    w, h = C.c_int(), C.c_int()
+
+    def probe(d):
+        return lib.p2p_jpeg_probe(bytes(d), len(d), C.byref(w), C.byref(h))
+
+    img = synth.noise(64, 48, 3)
+    ok = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_RST_INTERVAL, 1])[1].tobytes()
+    assert probe(ok) == 0
+    dht = ok.find(b"\xff\xc4")
+    # a DC symbol > 15 (libjpeg: bogus Huffman table), an over-subscribed code length (would index past the lookup
+    # table), the all-ones code in use
+    bad = bytearray(ok); bad[dht + 5 + 16 + 3] = 0x23
+    assert probe(bad) == -6
+    bad = bytearray(ok); bad[dht + 5] = 200
+    assert probe(bad) == -6
+    bad = bytearray(ok); bad[dht + 5:dht + 5 + 16] = bytes([2] + [0] * 15); bad[dht + 2:dht + 4] = (2 + 17 + 2).to_bytes(2, "big")
+    bad[dht + 5 + 16 + 2:dht + 5 + 16 + 12] = b""
+    assert probe(bad) == -6
+    # an unknown marker segment, a 16-bit quantisation table, a restart marker out of sequence
+    bad = bytearray(ok); bad[3] = 0xF0
+    assert probe(bad) == -6
+    dqt = ok.find(b"\xff\xdb")
+    bad = bytearray(ok); bad[dqt + 4] |= 0x10
+    assert probe(bad) == -6
+    sos = ok.find(b"\xff\xda")
+    rst = ok.find(b"\xff\xd1", sos)
+    bad = bytearray(ok); bad[rst + 1] = 0xD3
+    lay = (C.c_int32 * 10)()
+    assert lib.p2p_jpeg_coefficients(bytes(bad), len(bad), None, 0, lay) == 0
+    coef = np.zeros(sum(lay[4 + 2 * k] * lay[5 + 2 * k] * 64 for k in range(3)), np.int16)
+    assert lib.p2p_jpeg_coefficients(ok, len(ok), coef.ctypes.data, coef.size, lay) == 0
+    assert lib.p2p_jpeg_coefficients(bytes(bad), len(bad), coef.ctypes.data, coef.size, lay) == -6
