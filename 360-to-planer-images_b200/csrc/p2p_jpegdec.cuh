@@ -249,7 +249,8 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
             if (have_frame || sl != 6 + 9 || seg[0] != 8 || seg[5] != 3) return 1;
             I.H = (seg[1] << 8) | seg[2];
             I.W = (seg[3] << 8) | seg[4];
-            if (I.W <= 0 || I.H <= 0 || I.W > 65500 || I.H > 65500) return 1;   // JPEG_MAX_DIMENSION
+            // libjpeg stops at 65500 (JPEG_MAX_DIMENSION); a panorama slot (like cv2.remap's source) at 32766
+            if (I.W <= 0 || I.H <= 0 || I.W >= 32767 || I.H >= 32767) return 1;
             for (int k = 0; k < 3; ++k) {
                 cid[k] = seg[6 + 3 * k];
                 hs[k] = seg[7 + 3 * k] >> 4;

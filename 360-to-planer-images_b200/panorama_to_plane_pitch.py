@@ -83,10 +83,10 @@ def get_pitch_mapping(output_width, output_height, pitch_angle, pano_width, pano
 class _JpegSource:
     """A JPEG panorama the device decoder handles, still as file bytes (the pixels will only exist on the GPU)."""
 
-    __slots__ = ("data", "Wp", "Hp")
+    __slots__ = ("data", "Wp", "Hp", "path")
 
-    def __init__(self, data, dims):
-        self.data, (self.Wp, self.Hp) = data, dims
+    def __init__(self, data, dims, path):
+        self.data, (self.Wp, self.Hp), self.path = data, dims, path
 
 
 def _open_image(path):
@@ -103,7 +103,7 @@ def _open_image(path):
             data = b""
         dims = _engine.jpeg_probe(data) if data else None
         if dims is not None:
-            return _JpegSource(data, dims)
+            return _JpegSource(data, dims, path)
     return cv2.imread(str(path))
 
 
@@ -118,7 +118,9 @@ def _decode_source(proj, src):
     except _engine.P2PError as e:
         if e.code != -6:
             raise
-    img = cv2.imdecode(np.frombuffer(src.data, np.uint8), cv2.IMREAD_COLOR)
+    # the reference's own call: cv2.imread, not imdecode (for a truncated file libjpeg's file reader pads the scan and
+    # returns an image where its memory reader gives up)
+    img = cv2.imread(str(src.path))
     if img is None:
         raise ValueError("Failed to decode image")
     return img
