@@ -200,7 +200,9 @@ int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t
  * decoding (self-synchronising subsequences; P2P_OPT_GPU_HUFFMAN), inverse DCT, chroma upsampling and colour
  * conversion all run on the device, the host only removes the FF 00 byte stuffing; the pixels never exist in host
  * memory.  If the device Huffman stage does not converge the library's own host decoder (calling thread, outside the
- * context lock) takes over. */
+ * context lock) takes over.  Returns after the decode has finished on the device: a damaged file (truncated scan,
+ * restart markers out of sequence, codes or coefficient blocks no 8-bit encoder writes) gives P2P_ERR_UNSUPPORTED
+ * and leaves the slot without a panorama - such files are decoded like libjpeg or not at all, never differently. */
 int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp);
 /* Same decoder, pixels returned to the host (BGR, row_stride bytes per row, at least capacity_rows rows): the array
  * cv2.imread / cv2.imdecode would return.  Synchronous; the slot's panorama is invalidated. */

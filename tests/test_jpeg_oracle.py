@@ -193,3 +193,39 @@ def test_known_damage_patterns_are_declined(pkg):
     coef = np.zeros(sum(lay[4 + 2 * k] * lay[5 + 2 * k] * 64 for k in range(3)), np.int16)
     assert lib.p2p_jpeg_coefficients(ok, len(ok), coef.ctypes.data, coef.size, lay) == 0
     assert lib.p2p_jpeg_coefficients(bytes(bad), len(bad), coef.ctypes.data, coef.size, lay) == -6
+
+
+def test_host_decoder_under_address_sanitizer(tmp_path):
+    """The header parser and the host Huffman decoder, built with ASan + UBSan (tools/asan_jpeg_host.cu), on seeded
+    damaged files incl. garbage runs and truncations: no out-of-bounds access, no undefined behaviour."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    from jpeg_damage import damaged_files
+
+    root = Path(__file__).resolve().parents[1]
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = tmp_path / "asan_jpeg_host"
+    build = subprocess.run(["nvcc", "-O1", "-g", "-Xcompiler", "-fsanitize=address,-fsanitize=undefined,-fno-omit-frame-pointer",
+                            "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), str(root / "tools" / "asan_jpeg_host.cu"),
+                            "-lasan", "-lubsan"], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + build.stderr[-300:])
+    rng = np.random.default_rng(9)
+    names = []
+    for k, (label, data) in enumerate(damaged_files(301, 600)):
+        d = bytearray(data)
+        if k % 3 == 0:                                     # heavier damage: garbage runs, truncation
+            for _ in range(int(rng.integers(1, 6))):
+                a, n = int(rng.integers(2, len(d))), int(rng.integers(1, 24))
+                d[a:a + n] = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+            if rng.integers(0, 3) == 0:
+                d = d[:int(rng.integers(2, len(d)))]
+        f = tmp_path / f"{k:04d}.jpg"
+        f.write_bytes(bytes(d))
+        names.append(str(f))
+    run = subprocess.run([str(exe)] + names, capture_output=True, text=True, env={"ASAN_OPTIONS": "detect_leaks=0"})
+    assert run.returncode == 0 and "runtime error" not in run.stderr and "ERROR" not in run.stderr, run.stderr[-2000:]
+    assert run.stdout.startswith("decoded ")
