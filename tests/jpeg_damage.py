@@ -5,7 +5,7 @@ pixels cv2.imdecode returns; a file cv2 cannot read at all must be declined."""
 import cv2
 import numpy as np
 
-from oracle import synth
+from tools import synth_inputs as synth
 
 SAMPLING = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
 
