@@ -1563,10 +1563,6 @@ int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, in
                    uint8_t *out_host, size_t out_stride, size_t *sizes) {
     if (!slot_ok(ctx, slot) || !bgr || n_images <= 0 || W <= 0 || H <= 0 || !out_host || !sizes)
         return fail(ctx, P2P_ERR_INVALID, "bad argument");
-    if ((unsigned long long)H * (1ull + 3ull * W) <= 16384ull) {   // libpng shrinks the zlib window for such images
-        for (int i = 0; i < n_images; ++i) sizes[i] = 0;
-        return P2P_OK;
-    }
     p2ppng::Geom G;
     Slot &s = ctx->slots[slot];
     {
@@ -1598,7 +1594,6 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
     p2ppng::Geom G;
     Slot &s = ctx->slots[slot];
     const int n = n_yaw * n_pitch;
-    const bool tiny = (unsigned long long)H * (1ull + 3ull * W) <= 16384ull;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         CK(cudaSetDevice(ctx->device));
@@ -1626,19 +1621,12 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
         uint8_t *outs[1] = {s.d_out};
         rc = launch_project(ctx, sl, 1, n_yaw, yaw_shift, n_pitch, pitch, W, H, outs);
         if (rc) return rc;
-        if (!tiny) {
-            rc = enqueue_png(ctx, s, s.d_out, n, W, H, G);
-            if (rc) return rc;
-        }
+        rc = enqueue_png(ctx, s, s.d_out, n, W, H, G);
+        if (rc) return rc;
         // the pixels too, if the caller wants them (needed for the views the device encoder does not handle)
         if (pixels_host) CK(cudaMemcpyAsync(pixels_host, s.d_out, (size_t)n * W * H * 3, cudaMemcpyDeviceToHost, s.stream));
     }
     cudaSetDevice(ctx->device);
-    if (tiny) {
-        for (int i = 0; i < n; ++i) sizes[i] = 0;
-        if (cudaStreamSynchronize(s.stream) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "PNG encoder: CUDA error");
-        return P2P_OK;
-    }
     int rc = collect_png(s, n, G.out_cap, out_host, out_stride, sizes);
     if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a PNG file does not fit its output buffer (out_stride)");
     if (rc) return fail(ctx, rc, "PNG encoder: CUDA error");

@@ -42,7 +42,7 @@ struct BlockInfo {
     uint32_t hdr[kHdrWords];     // header bits, LSB first
     uint32_t hdr_bits;           // 3 block-type bits + tree description
     uint32_t bits;               // whole block: header + symbols + end-of-block
-    uint32_t kind;               // 1 static, 2 dynamic, 0 stored (not handled)
+    uint32_t kind;               // 1 static, 2 dynamic, 0 stored
     uint32_t pad;
 };
 
@@ -62,7 +62,8 @@ __device__ __forceinline__ int length_code(int lc) {
 }
 
 // ---- filter ---------------------------------------------------------------------------------------------------------
-// F[y][0] = 1 (Sub), F[y][1 + i] = rgb[i] - rgb[i - 3] (mod 256), RGB order (png_set_bgr)
+// F[y][0] = 1 (Sub), F[y][1 + i] = rgb[i] - rgb[i - 3] (mod 256), RGB order (png_set_bgr).  Images one pixel wide get
+// filter type 0: libpng drops Sub / Avg / Paeth for width 1 (same bytes, other type)
 __global__ void __launch_bounds__(256)
 png_filter_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ F, const Geom G) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;   // pixel
@@ -77,7 +78,7 @@ png_filter_kernel(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ F, cons
         g -= p[-2];
         b -= p[-3];
     } else {
-        o[-1] = 1;
+        o[-1] = (G.W == 1) ? 0 : 1;
     }
     o[0] = (uint8_t)r;
     o[1] = (uint8_t)g;
@@ -511,9 +512,13 @@ png_tree_kernel(const uint32_t *__restrict__ lfreq, const uint32_t *__restrict__
     out.w = bi.hdr;
     out.nbits = 0;
     if (stored_len + 4 <= opt_lenb) {
-        bi.kind = 0;   // zlib would (probably) store this block: not handled here
-        bi.bits = 0;
-        bi.hdr_bits = 0;
+        // trees.c _tr_stored_block: 3 header bits, pad to a byte, LEN, ~LEN, the bytes.  (zlib also needs the block's
+        // bytes to be still in its window, block_start >= 0: a block chosen here has < 16383 + 1300 bytes - more match
+        // bytes and the Huffman form is shorter -, far less than the 32506 that could slide out.)
+        bi.kind = 0;
+        bi.bits = (uint32_t)stored_len;   // bytes; png_layout_kernel knows the alignment and turns this into bits
+        out.send((0u << 1) + last, 3);
+        bi.hdr_bits = out.nbits;
         return;
     }
     if (static_lenb == opt_lenb) {
@@ -555,14 +560,19 @@ __global__ void png_layout_kernel(BlockInfo *__restrict__ info, const uint32_t *
     unsigned long long off = 16;   // CMF + FLG
     bool ok = true;
     for (uint32_t b = 0; b < nblk; ++b) {
-        const BlockInfo &bi = info[(size_t)img * G.max_blk + b];
+        BlockInfo &bi = info[(size_t)img * G.max_blk + b];
         blkoff[(size_t)img * G.max_blk + b] = (uint32_t)off;
-        ok = ok && bi.kind != 0;
+        if (bi.kind == 0) {   // stored: header, padding to the next byte, LEN + ~LEN, data
+            const uint32_t pad = (8u - (uint32_t)((off + 3ull) & 7ull)) & 7u;
+            bi.bits = 3u + pad + 32u + 8u * bi.bits;
+        }
         off += bi.bits;
+        if (off + 64 > (unsigned long long)G.z_cap * 8ull) {
+            ok = false;
+            break;
+        }
     }
-    if (off + 64 > (unsigned long long)G.z_cap * 8ull) ok = false;
-    if (ok && ((((off + 7) >> 3) + 4) % (unsigned long long)kIdat) == 0ull) ok = false;   // stream ends exactly on an IDAT boundary
-    zbits[img] = ok ? off : 0ull;   // 0 = not handled (a stored block, or the stream would not fit)
+    zbits[img] = ok ? off : 0ull;   // 0 = not handled (the stream would not fit its buffer)
 }
 
 // ---- emission: one CTA per deflate block ------------------------------------------------------------------------------
@@ -592,11 +602,18 @@ png_emit_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen
         const int nb = (bi.hdr_bits - w * 32 < 32) ? (int)(bi.hdr_bits - w * 32) : 32;
         or_bits(z, base + (unsigned long long)w * 32, bi.hdr[w], nb);
     }
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     uint32_t p0, p1;
     block_range(blockpos + (size_t)img * G.max_blk, T, G.N, b, p0, p1);
     const uint8_t *f = F + (size_t)img * G.Npad;
+    if (bi.kind == 0) {   // stored block: LEN, ~LEN and the filtered bytes themselves, byte aligned
+        const unsigned long long data = (base + 3ull + 7ull) & ~7ull;
+        const uint32_t len = p1 - p0;
+        if (threadIdx.x == 0) or_bits(z, data, (unsigned long long)((len & 0xFFFFu) | ((~len & 0xFFFFu) << 16)), 32);
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) or_bits(z, data + 32ull + 8ull * i, f[p0 + i], 8);
+        return;
+    }
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
     const uint16_t *tl = tlen + (size_t)img * G.Npad;
     const uint32_t d0 = bi.dcode0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -674,8 +691,23 @@ png_adler_kernel(const uint8_t *__restrict__ F, unsigned long long *__restrict__
 }
 
 // ---- file assembly ------------------------------------------------------------------------------------------------
-// zlib stream = 78 01 | deflate bits | Adler-32 (big endian); PNG = signature | IHDR | IDAT x k (8192 bytes each) | IEND
+// zlib stream = CMF FLG (78 01) | deflate bits | Adler-32 (big endian); PNG = signature | IHDR | IDAT x k (8192 bytes each) | IEND
 __device__ __forceinline__ size_t zlib_len(unsigned long long zb) { return (size_t)((zb + 7) >> 3) + 4; }
+
+// CMF (low byte) and FLG (high byte): 78 01, or the smaller window libpng writes into the header of a stream of at most
+// 16384 bytes of data (pngwutil.c optimize_cmf); the deflate bits do not depend on it (every match has distance 1)
+__device__ __forceinline__ uint32_t zlib_header(uint32_t data_size) {
+    uint32_t cinfo = 7, half = 1u << 14;
+    if (data_size <= 16384u) {
+        do {
+            half >>= 1;
+            --cinfo;
+        } while (cinfo > 0 && data_size <= half);
+    }
+    const uint32_t cmf = 0x08u | (cinfo << 4);
+    const uint32_t flg = 0x1Fu - ((cmf << 8) % 0x1Fu);
+    return cmf | (flg << 8);
+}
 
 __global__ void __launch_bounds__(256)
 png_pack_kernel(const uint32_t *__restrict__ Z, const unsigned long long *__restrict__ zbits,
@@ -691,8 +723,8 @@ png_pack_kernel(const uint32_t *__restrict__ Z, const unsigned long long *__rest
     const uint32_t adler = (s2 << 16) | s1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (size_t)gridDim.x * blockDim.x) {
         uint8_t v;
-        if (i == 0) v = 0x78;
-        else if (i == 1) v = 0x01;
+        if (i == 0) v = (uint8_t)zlib_header(G.N);
+        else if (i == 1) v = (uint8_t)(zlib_header(G.N) >> 8);
         else if (i >= L - 4) v = (uint8_t)(adler >> (8 * (L - 1 - i)));
         else v = z[i];
         const size_t c = i / kIdat;

@@ -175,8 +175,9 @@ int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, i
 /* ---- PNG files of the views (replaces cv2.imwrite(<name>.png, view), ref :277: the default --output_format) ---- */
 /* PNG files of n_images images (BGR u8, tightly packed, host or device memory), encoded on the GPU and byte-identical
  * to cv2.imwrite / cv2.imencode('.png') at OpenCV's defaults (filter Sub, zlib level 1, strategy Z_RLE, 8192-byte IDAT
- * chunks).  sizes[i] = 0 means "not handled on the device": images whose filtered data is <= 16384 bytes, images zlib
- * would store uncompressed (white noise), a stream ending exactly on an IDAT boundary - use cv2.imwrite for those.
+ * chunks), including libpng's small-image cases (window bits in the zlib header of images with at most 16384 bytes
+ * of data, filter type 0 for images one pixel wide) and the blocks zlib stores uncompressed (white noise).  sizes[i] = 0
+ * is kept as the "not handled on the device, use cv2.imwrite" signal; no input produces it any more.
  * Synchronous.  P2P_ERR_LIMIT if a file does not fit out_stride bytes (W * H * 4 + 4096 always suffices). */
 int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H,
                    uint8_t *out_host, size_t out_stride, size_t *sizes);

@@ -258,13 +258,32 @@ def deflate_rle(data, lit_bufsize=16384):
     return bytes(out.buf), kinds
 
 def sub_filter(bgr: np.ndarray) -> bytes:
-    """PNG rows of an 8-bit BGR image as OpenCV writes them: RGB order (png_set_bgr), filter type 1 (Sub) on every row."""
+    """PNG rows of an 8-bit BGR image as OpenCV writes them: RGB order (png_set_bgr), filter type 1 (Sub) on every row -
+    type 0 (None) for images one pixel wide, where libpng drops the Sub filter (pngwrite.c png_set_filter /
+    png_write_start_row: ``width == 1`` clears SUB, AVG and PAETH; the bytes are the same, only the type differs)."""
     H, W, _ = bgr.shape
     rgb = bgr[..., ::-1].astype(np.int16)
     f = rgb.copy()
     f[:, 1:] -= rgb[:, :-1]
-    rows = np.concatenate([np.ones((H, 1), np.uint8), (f & 255).astype(np.uint8).reshape(H, 3 * W)], axis=1)
+    ftype = np.full((H, 1), 0 if W == 1 else 1, np.uint8)
+    rows = np.concatenate([ftype, (f & 255).astype(np.uint8).reshape(H, 3 * W)], axis=1)
     return rows.tobytes()
+
+
+def zlib_header(data_size: int) -> bytes:
+    """CMF / FLG of the stream: 78 01 (32 KB window, level flags 0), with the window bits libpng writes for small
+    images (pngwutil.c optimize_cmf: for at most 16384 bytes of data, the smallest window that still holds them)."""
+    cinfo = 7
+    half = 1 << (cinfo + 7)
+    if data_size <= 16384 and data_size <= half:
+        while True:
+            half >>= 1
+            cinfo -= 1
+            if not (cinfo > 0 and data_size <= half):
+                break
+    cmf = 0x08 | (cinfo << 4)
+    flg = 0x1F - ((cmf << 8) % 0x1F)
+    return bytes([cmf, flg])
 
 
 def encode_png(bgr: np.ndarray) -> bytes:
@@ -272,7 +291,9 @@ def encode_png(bgr: np.ndarray) -> bytes:
     import struct
 
     H, W, _ = bgr.shape
-    z, _ = deflate_rle(sub_filter(bgr))
+    raw = sub_filter(bgr)
+    z, _ = deflate_rle(raw)
+    z = zlib_header(len(raw)) + z[2:]
 
     def chunk(typ, data):
         return struct.pack(">I", len(data)) + typ + data + struct.pack(">I", zlib.crc32(typ + data) & 0xFFFFFFFF)

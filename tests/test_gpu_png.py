@@ -36,36 +36,67 @@ def test_encode_png_equals_cv2(proj, w, h, kind):
     assert got == ref_png(img)
 
 
-def test_encode_png_batch_and_declined_images(proj):
+def test_encode_png_batch_with_noise(proj):
     imgs = np.stack([synth.smooth(320, 200, 1), textured(320, 200, 2), np.zeros((200, 320, 3), np.uint8),
                      synth.noise(320, 200, 3)])
     files = proj.encode_png(imgs)
-    for f, img in zip(files[:3], imgs[:3]):
+    for f, img in zip(files, imgs):    # white noise: every deflate block is one zlib stores uncompressed
         assert f == ref_png(img)
-    assert files[3] is None            # white noise: zlib stores such blocks uncompressed, left to cv2
-    assert proj.encode_png(synth.smooth(40, 30, 1))[0] is None   # tiny image: libpng shrinks the zlib window
+
+
+@pytest.mark.parametrize("w,h,kind", [(1, 1, "noise"), (1, 40, "noise"), (1, 300, "smooth"), (50, 1, "noise"), (2, 2, "smooth"),
+                                      (5, 3, "noise"), (10, 10, "smooth"), (40, 30, "smooth"), (60, 50, "textured"),
+                                      (73, 74, "noise"), (80, 68, "smooth"), (100, 54, "textured"), (128, 42, "flat"),
+                                      (102, 80, "noise"), (640, 480, "noise"), (400, 300, "mixed"), (500, 300, "noise+runs")])
+def test_small_images_stored_blocks_and_chunk_boundaries(proj, w, h, kind):
+    """libpng's small-image cases (zlib window bits in the stream header for <= 16384 bytes of data, filter type 0 for
+    width 1), blocks zlib stores uncompressed (noise, also mixed with compressible blocks and with runs inside), and a
+    stream that ends exactly on an IDAT chunk boundary (102 x 80 noise: 24576 bytes = 3 full chunks, no empty one)."""
+    if kind == "noise":
+        img = synth.noise(w, h, w + h)
+    elif kind == "smooth":
+        img = synth.smooth(w, h, w)
+    elif kind == "textured":
+        img = textured(w, h, h)
+    elif kind == "flat":
+        img = np.full((h, w, 3), 99, np.uint8)
+    elif kind == "mixed":
+        img = synth.smooth(w, h, 3)
+        img[:h // 2] = synth.noise(w, h // 2, 4)
+    else:
+        img = synth.noise(w, h, 5)
+        img[:, ::7] = 128
+        img[100:110] = 7
+    got = proj.encode_png(img)[0]
+    assert got is not None
+    assert got == ref_png(img)
 
 
 def test_png_fuzz(proj):
     rng = np.random.default_rng(77)
-    handled = 0
-    for i in range(40):
-        w, h = int(rng.integers(80, 400)), int(rng.integers(70, 300))
-        kind = int(rng.integers(0, 4))
+    for i in range(80):
+        if i % 4 == 3:
+            w, h = int(rng.integers(1, 90)), int(rng.integers(1, 70))       # small: <= 16384 bytes of filtered data
+        else:
+            w, h = int(rng.integers(80, 400)), int(rng.integers(70, 300))
+        kind = int(rng.integers(0, 6))
         if kind == 0:
             img = synth.smooth(w, h, i)
         elif kind == 1:
             img = textured(w, h, i, amp=int(rng.integers(1, 30)))
         elif kind == 2:
             img = np.repeat(np.repeat(rng.integers(0, 256, ((h + 7) // 8, (w + 7) // 8, 3), dtype=np.uint8), 8, axis=0), 8, axis=1)[:h, :w].copy()
-        else:
+        elif kind == 3:
             img = np.full((h, w, 3), rng.integers(0, 256, 3), np.uint8)
             img[rng.integers(0, h):, rng.integers(0, w):] = rng.integers(0, 256, 3)
+        elif kind == 4:
+            img = synth.noise(w, h, i)
+        else:                                                               # noise with compressible rows in between
+            img = synth.noise(w, h, i)
+            img[rng.integers(0, h)::3] = rng.integers(0, 256, 3)
         got = proj.encode_png(img)[0]
-        if got is not None:
-            handled += 1
-            assert got == ref_png(img), (i, w, h, kind)
-    assert handled >= 30
+        assert got is not None, (i, w, h, kind)
+        assert got == ref_png(img), (i, w, h, kind)
 
 
 def test_front_end_png_files_equal_imwrite(pkg, tmp_path):

@@ -30,3 +30,27 @@ def test_deflate_model_equals_zlib(name, img):
 @pytest.mark.parametrize("name,img", list(images()), ids=[n for n, _ in images()])
 def test_png_oracle_equals_cv2_imencode(name, img):
     assert pm.encode_png(img) == cv2.imencode(".png", img)[1].tobytes()
+
+
+def test_small_images_stored_blocks_and_chunk_boundaries():
+    """libpng's small-image cases (window bits in the zlib header for <= 16384 bytes of data, filter type 0 for width 1),
+    blocks zlib stores uncompressed, and a stream ending exactly on an IDAT boundary (102 x 80 noise = 3 full chunks)."""
+    rng = np.random.default_rng(0)
+    for t in range(150):
+        w, h = int(rng.integers(1, 120)), int(rng.integers(1, 90))
+        if t % 10 == 0:
+            w = 1
+        if t % 10 == 1:
+            h = 1
+        k = t % 3
+        img = synth.noise(w, h, t) if k == 0 else synth.smooth(w, h, t) if k == 1 else np.full((h, w, 3), int(rng.integers(0, 256)), np.uint8)
+        assert pm.encode_png(img) == cv2.imencode(".png", img)[1].tobytes(), (w, h, k)
+    boundary = synth.noise(102, 80, 1)
+    png = pm.encode_png(boundary)
+    assert png == cv2.imencode(".png", boundary)[1].tobytes()
+    assert png.count(b"IDAT") == 3 and len(png) == 8 + 25 + 3 * (8192 + 12) + 12
+    mixed = synth.smooth(400, 300, 3)
+    mixed[:150] = synth.noise(400, 150, 4)
+    _, kinds = pm.deflate_rle(pm.sub_filter(mixed))
+    assert "stored" in kinds and "dynamic" in kinds
+    assert pm.encode_png(mixed) == cv2.imencode(".png", mixed)[1].tobytes()
