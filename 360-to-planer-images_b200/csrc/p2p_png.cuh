@@ -11,9 +11,10 @@
 //              send_tree / build_bl_tree exactly (heap order and depth tie-breaks included) and picks static / dynamic
 //   emission   one CTA per block: local prefix sum of code lengths, LSB-first bits OR-ed into the stream
 //   pngwrite.c Adler-32, 8192-byte IDAT chunks, CRC-32 per chunk, IHDR / IEND
-// Not handled (the caller falls back to cv2.imwrite): images whose filtered data is <= 16384 bytes (libpng then shrinks
-// the zlib window) and images with a block zlib would store uncompressed (white noise): that decision depends on
-// zlib's sliding-window state.
+// Also restated: blocks zlib stores uncompressed (_tr_stored_block: white noise), the window bits libpng writes into the
+// zlib header of small images (optimize_cmf, <= 16384 bytes of data), filter type 0 for images one pixel wide, streams
+// ending exactly on an IDAT boundary.  sizes[i] = 0 ("fall back to cv2.imwrite") is only left for a stream that would
+// not fit its buffer, which the buffer sizing excludes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

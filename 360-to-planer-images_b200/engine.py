@@ -321,8 +321,8 @@ class Projector:
     # -- PNG files (cv2.imwrite(<name>.png), ref :277: the default output format) -------------------
     def encode_png(self, images: np.ndarray, slot: int | None = None) -> list:
         """PNG files (bytes) of ``images`` u8 [n, H, W, 3] (BGR), encoded on the GPU; byte-identical to
-        ``cv2.imencode('.png', image)``.  ``None`` for an image the device encoder does not handle (tiny images, blocks
-        zlib would store uncompressed): encode those with cv2."""
+        ``cv2.imencode('.png', image)`` (small images and incompressible content included).  ``None`` would mean "not
+        handled on the device, encode it with cv2" (``sizes[i] = 0`` of the ABI); no input produces it any more."""
         images = np.ascontiguousarray(images, np.uint8)
         if images.ndim == 3:
             images = images[None]

@@ -178,7 +178,7 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
 
 def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
     """([n_yaw][n_pitch] PNG files (bytes) or None, views or None): projection and PNG encoder on the device.  A None file
-    is a view the device encoder does not handle (tiny output, incompressible content): ``views`` then holds the pixels
+    is a view the device encoder did not handle (the ABI's ``sizes[i] = 0``; not produced any more): ``views`` then holds the pixels
     of all views so that ``cv2.imwrite`` can write those, exactly as the reference would."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
