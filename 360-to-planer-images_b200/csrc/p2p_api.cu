@@ -167,6 +167,14 @@ int ensure(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
     return P2P_OK;
 }
 
+// for buffers whose size follows the CONTENT of a file (compressed scan length ...): grow with 50 % headroom, so that a
+// folder of similar files does not free / allocate (= synchronise the device) on every slightly larger one
+template <typename T>
+int ensure_grow(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *ptr) return P2P_OK;
+    return ensure(ctx, ptr, cap, bytes + bytes / 2);
+}
+
 int slot_ok(p2p_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < ctx->n_slots; }
 
 int check_dims(p2p_ctx *ctx, int Wp, int Hp) {
@@ -713,12 +721,12 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
         std::lock_guard<std::mutex> lk(ctx->mu);
         CK(cudaSetDevice(ctx->device));
         const size_t sub_bytes = ((size_t)G.n_sub * sizeof(SubSeq) + 15) & ~(size_t)15;
-        int rc = ensure(ctx, &s.jd_stream, &s.jd_stream_cap, n_words * 4);
-        if (!rc) rc = ensure(ctx, &s.jd_states, &s.jd_states_cap, 2 * (size_t)G.n_sub * sizeof(unsigned long long));
-        if (!rc) rc = ensure(ctx, &s.jd_nblk, &s.jd_nblk_cap, 2 * nsub4 * sizeof(uint32_t));
+        int rc = ensure_grow(ctx, &s.jd_stream, &s.jd_stream_cap, n_words * 4);
+        if (!rc) rc = ensure_grow(ctx, &s.jd_states, &s.jd_states_cap, 2 * (size_t)G.n_sub * sizeof(unsigned long long));
+        if (!rc) rc = ensure_grow(ctx, &s.jd_nblk, &s.jd_nblk_cap, 2 * nsub4 * sizeof(uint32_t));
         if (!rc) rc = ensure(ctx, &s.jd_dc, &s.jd_dc_cap, 2 * 3 * (size_t)G.dc_stride * sizeof(int32_t));
         if (!rc) rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
-        if (!rc) rc = ensure(ctx, &s.jd_sub, &s.jd_sub_cap, sub_bytes + ((size_t)n_ivl + 1) * sizeof(uint32_t));
+        if (!rc) rc = ensure_grow(ctx, &s.jd_sub, &s.jd_sub_cap, sub_bytes + ((size_t)n_ivl + 1) * sizeof(uint32_t));
         if (rc) return rc;
         d_sub = reinterpret_cast<SubSeq *>(s.jd_sub);
         d_ivl_first = reinterpret_cast<uint32_t *>(s.jd_sub + sub_bytes);

@@ -242,6 +242,14 @@ class Projector:
             pb = cache[slot] = PinnedBuffer((n, stride))
         return pb.array[:n]
 
+    @staticmethod
+    def _files(buf: np.ndarray, sizes, copy: bool) -> list:
+        """The files of a slot's file buffer: ``bytes`` (copy) or zero-copy ``memoryview`` slices of the page-locked
+        buffer, valid until the slot is used again (size 0 = not handled on the device -> None)."""
+        if copy:
+            return [buf[i, :sizes[i]].tobytes() if sizes[i] else None for i in range(len(sizes))]
+        return [memoryview(buf[i, :sizes[i]]) if sizes[i] else None for i in range(len(sizes))]
+
     def _jpeg_buffer(self, slot: int, n: int, W: int, H: int) -> np.ndarray:
         return self._file_buffer(slot, n, W * H * 3 + 4096)
 
@@ -267,9 +275,10 @@ class Projector:
                 return run(s)
         return run(slot)
 
-    def project_jpeg(self, slot: int, shifts, consts, W: int, H: int, quality: int = 95) -> list:
+    def project_jpeg(self, slot: int, shifts, consts, W: int, H: int, quality: int = 95, copy: bool = True) -> list:
         """The n_yaw x n_pitch views of the panorama in ``slot`` as JPEG files (bytes, yaw-major): projection and
-        encoder both run on the device, only the files cross PCIe."""
+        encoder both run on the device, only the files cross PCIe.  ``copy=False``: memoryviews of the slot's page-locked
+        file buffer instead of bytes (valid until the slot is used again)."""
         shifts = np.ascontiguousarray(shifts, np.int32)
         n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
         n = n_yaw * n_pitch
@@ -278,11 +287,13 @@ class Projector:
         sizes = (C.c_size_t * n)()
         self._ck(self.lib.p2p_project_views_jpeg(self.ctx, slot, n_yaw, shifts.ctypes.data_as(C.POINTER(C.c_int32)),
                                                  n_pitch, pc, W, H, int(quality), buf.ctypes.data, buf.strides[0], sizes))
-        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+        return self._files(buf, sizes, copy)
 
-    def process_image_jpeg(self, slot: int, pano: np.ndarray, shifts, consts, W: int, H: int, quality: int = 95) -> list:
-        """upload (the rows the views touch) + project + JPEG-encode in one ABI call: the files (bytes, yaw-major)
-        of all n_yaw x n_pitch views.  Blocks this thread only; other slots keep running."""
+    def process_image_jpeg(self, slot: int, pano: np.ndarray, shifts, consts, W: int, H: int, quality: int = 95,
+                           copy: bool = True) -> list:
+        """upload (the rows the views touch) + project + JPEG-encode in one ABI call: the files (bytes, yaw-major;
+        ``copy=False``: memoryviews of the slot's file buffer) of all n_yaw x n_pitch views.  Blocks this thread only;
+        other slots keep running."""
         pano = _as_u8_image(pano)
         Hp, Wp, _ = pano.shape
         shifts = np.ascontiguousarray(shifts, np.int32)
@@ -294,7 +305,7 @@ class Projector:
         self._ck(self.lib.p2p_process_image_jpeg(self.ctx, slot, pano.ctypes.data, Wp, Hp, pano.strides[0], n_yaw,
                                                  shifts.ctypes.data_as(C.POINTER(C.c_int32)), n_pitch, pc, W, H,
                                                  int(quality), buf.ctypes.data, buf.strides[0], sizes))
-        return [buf[i, :sizes[i]].tobytes() for i in range(n)]
+        return self._files(buf, sizes, copy)
 
     def project_image_jpeg(self, pano: np.ndarray, yaw_angles, pitch_angles, W: int, H: int, fov_deg=90,
                            consts=None, tables=None, quality: int = 95) -> list:
@@ -341,9 +352,11 @@ class Projector:
                 return run(s)
         return run(slot)
 
-    def process_image_png(self, slot: int, pano, shifts, consts, W: int, H: int, want_pixels: bool = True):
+    def process_image_png(self, slot: int, pano, shifts, consts, W: int, H: int, want_pixels: bool = True,
+                          copy: bool = True):
         """upload (``pano`` = None: use the panorama resident in ``slot``) + project + PNG-encode in one ABI call.
-        Returns (files, pixels): files[i] is bytes or None (view not handled by the device encoder); pixels is the
+        Returns (files, pixels): files[i] is bytes (``copy=False``: a memoryview of the slot's page-locked file buffer,
+        valid until the slot is used again) or None (view not handled by the device encoder); pixels is the
         [n_yaw, n_pitch, H, W, 3] array when ``want_pixels`` (so the caller can ``cv2.imwrite`` the None views)."""
         shifts = np.ascontiguousarray(shifts, np.int32)
         n_yaw, n_pitch = int(shifts.shape[0]), len(consts)
@@ -363,7 +376,7 @@ class Projector:
                                                 shifts.ctypes.data_as(C.POINTER(C.c_int32)), n_pitch, pc, W, H,
                                                 buf.ctypes.data, buf.strides[0], sizes,
                                                 pixels.ctypes.data if want_pixels else None))
-        return [buf[i, :sizes[i]].tobytes() if sizes[i] else None for i in range(n)], pixels
+        return self._files(buf, sizes, copy), pixels
 
     # -- JPEG panoramas decoded on the device (the decode side of cv2.imread, ref :244) ----------
     def jpeg_probe(self, data: bytes):

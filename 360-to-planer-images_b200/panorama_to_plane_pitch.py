@@ -24,6 +24,7 @@ few files / views outside the device codecs' subsets.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import logging
 import os
 import threading
@@ -158,15 +159,29 @@ def _is_jpeg(output_format) -> bool:
     return str(output_format).lower() in ("jpg", "jpeg")
 
 
-def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
-    """[n_yaw][n_pitch] JPEG files (bytes) through the device projection + encoder, using the module caches."""
+def _slot(proj, lease):
+    """A slot for one image: released when the ``with`` block ends, or - with a ``lease`` (an ``ExitStack`` the caller
+    closes after the files are written) - kept until then, so that the files can be written straight from the slot's
+    page-locked file buffer instead of being copied into ``bytes`` first."""
+    import contextlib
+
+    if lease is None:
+        return proj.slots(1)
+    (s,) = lease.enter_context(proj.slots(1))
+    return contextlib.nullcontext((s,))
+
+
+def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None):
+    """[n_yaw][n_pitch] JPEG files (bytes; with a ``lease`` zero-copy views of the slot's file buffer, see ``_slot``) through
+    the device projection + encoder, using the module caches."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
     if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
         try:  # JPEG in, JPEG out: no pixel ever crosses PCIe
-            with proj.slots(1) as (s,):
+            with _slot(proj, lease) as (s,):
                 proj.upload_jpeg(s, src.data)
-                flat = proj.project_jpeg(s, [t[2] for t in tables], consts, output_width, output_height)
+                flat = proj.project_jpeg(s, [t[2] for t in tables], consts, output_width, output_height,
+                                         copy=lease is None)
             n_p = len(pitch_angles)
             return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
         except _engine.P2PError as e:
@@ -176,8 +191,9 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
                                    fov_deg, consts=consts, tables=tables)
 
 
-def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
-    """([n_yaw][n_pitch] PNG files (bytes) or None, views or None): projection and PNG encoder on the device.  A None file
+def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None):
+    """([n_yaw][n_pitch] PNG files (bytes; with a ``lease`` zero-copy views of the slot's file buffer, see ``_slot``) or
+    None, views or None): projection and PNG encoder on the device.  A None file
     is a view the device encoder did not handle (the ABI's ``sizes[i] = 0``; not produced any more): ``views`` then holds the pixels
     of all views so that ``cv2.imwrite`` can write those, exactly as the reference would."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
@@ -185,7 +201,7 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
     n_p = len(pitch_angles)
     if yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
         shifts = [t[2] for t in tables]
-        with proj.slots(1) as (s,):
+        with _slot(proj, lease) as (s,):
             pano = src
             if isinstance(src, _JpegSource):
                 try:
@@ -195,7 +211,8 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
                     if e.code != -6:
                         raise
                     pano = _decode_source(proj, src)
-            flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False)
+            flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False,
+                                             copy=lease is None)
             views = None
             if any(f is None for f in flat):         # read the pixels back only when cv2 has to write some views
                 views = proj.project(s, shifts, consts, output_width, output_height)
@@ -284,22 +301,22 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
     pitch_angles = list(pitch_angles)
     jpeg = _is_jpeg(output_format)
     png = str(output_format).lower() == "png"
-    try:
-        if jpeg:  # projected and encoded on the device: only the files come back
-            files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
-                                  fov_deg)
-        elif png:
-            files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
-                                        output_height, fov_deg)
-        else:
-            views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
-                             fov_deg)
-    except Exception as e:
-        for yaw_angle in yaw_angles:
-            logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
-        return
-
-    with ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
+    # the slot stays leased until the files are on disk: they are written straight from its page-locked buffer
+    with contextlib.ExitStack() as lease, ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
+        try:
+            if jpeg:  # projected and encoded on the device: only the files come back
+                files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
+                                      output_height, fov_deg, lease=lease)
+            elif png:
+                files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
+                                            output_height, fov_deg, lease=lease)
+            else:
+                views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
+                                 fov_deg)
+        except Exception as e:
+            for yaw_angle in yaw_angles:
+                logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
+            return
         if jpeg:
             tasks = _save_files(files, base_name, output_dir, yaw_angles, pitch_angles, output_width, output_height,
                                 output_format, executor)
@@ -375,6 +392,11 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
         jpeg_out = _is_jpeg(output_format)
 
         def one(f, writers):
+            # the slot stays leased until this image's files are on disk (written straight from its page-locked buffer)
+            with contextlib.ExitStack() as lease:
+                one_leased(f, writers, lease)
+
+        def one_leased(f, writers, lease):
             logging.info(f"Loading image: {f}")
             src = _open_image(f)
             if src is None:
@@ -382,10 +404,10 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
                 return
             try:
                 if jpeg_out:
-                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease)
                     futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
                 elif str(output_format).lower() == "png":
-                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease)
                     futs = _save_png(cv2, files_, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
                                      writers)
                 else:
