@@ -379,8 +379,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
 def files_extras(pkg, proj, pano, shifts, consts):
     """Side measurement (not the headline metric): the codec rows either side of the path.  One 8192x4096
-    JPEG file in host memory -> the 12 views as jpg / png files in host memory, (a) decoded, projected and encoded on the
-    GPU, 4 images in flight on 4 host threads; (b) the reference's flow on the host cores: cv2.imdecode -> oracle port of
+    JPEG file in host memory -> the 12 views as jpg / png files in (page-locked) host memory, (a) decoded, projected and
+    encoded on the GPU, 4 images in flight on 4 host threads; (b) the reference's flow on the host cores: cv2.imdecode -> oracle port of
     the projection -> cv2.imencode per view.  Same bytes out (checked)."""
     import cv2
     from concurrent.futures import ThreadPoolExecutor
@@ -391,17 +391,21 @@ def files_extras(pkg, proj, pano, shifts, consts):
     n_img, n_thr = 8, 4
     out = {}
     for fmt in ("jpg", "png"):
-        def gpu_one(_):
+        def gpu_one(keep):
+            # the files land in the slot's page-locked host buffer; the front end writes them to disk from there
+            # (copy=False), the identity check below takes a copy
             with proj.slots(1) as (s,):
                 proj.upload_jpeg(s, data)
                 if fmt == "jpg":
-                    return proj.project_jpeg(s, shifts, consts, W, H)
-                return proj.process_image_png(s, None, shifts, consts, W, H, want_pixels=False)[0]
+                    files = proj.project_jpeg(s, shifts, consts, W, H, copy=False)
+                else:
+                    files = proj.process_image_png(s, None, shifts, consts, W, H, want_pixels=False, copy=False)[0]
+                return [bytes(f) for f in files] if keep else sum(len(f) for f in files)
 
         with ThreadPoolExecutor(n_thr) as ex:
-            first = list(ex.map(gpu_one, range(n_thr)))[0]
+            first = list(ex.map(gpu_one, [True] * n_thr))[0]
             t0 = time.perf_counter()
-            list(ex.map(gpu_one, range(n_img)))
+            list(ex.map(gpu_one, [False] * n_img))
             gpu_s = (time.perf_counter() - t0) / n_img
         ref_port.clear_caches()
         ref_files = None
