@@ -47,7 +47,9 @@ def test_encode_png_batch_with_noise(proj):
 @pytest.mark.parametrize("w,h,kind", [(1, 1, "noise"), (1, 40, "noise"), (1, 300, "smooth"), (50, 1, "noise"), (2, 2, "smooth"),
                                       (5, 3, "noise"), (10, 10, "smooth"), (40, 30, "smooth"), (60, 50, "textured"),
                                       (73, 74, "noise"), (80, 68, "smooth"), (100, 54, "textured"), (128, 42, "flat"),
-                                      (102, 80, "noise"), (640, 480, "noise"), (400, 300, "mixed"), (500, 300, "noise+runs")])
+                                      (102, 80, "noise"), (640, 480, "noise"), (400, 300, "mixed"), (500, 300, "noise+runs"),
+                                      (85, 1, "smooth"), (85, 2, "smooth"), (85, 8, "noise"), (85, 32, "smooth"), (85, 64, "smooth"),
+                                      (85, 65, "smooth"), (86, 63, "textured"), (21, 1, "noise")])
 def test_small_images_stored_blocks_and_chunk_boundaries(proj, w, h, kind):
     """libpng's small-image cases (zlib window bits in the stream header for <= 16384 bytes of data, filter type 0 for
     width 1), blocks zlib stores uncompressed (noise, also mixed with compressible blocks and with runs inside), and a

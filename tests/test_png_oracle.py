@@ -54,3 +54,15 @@ def test_small_images_stored_blocks_and_chunk_boundaries():
     _, kinds = pm.deflate_rle(pm.sub_filter(mixed))
     assert "stored" in kinds and "dynamic" in kinds
     assert pm.encode_png(mixed) == cv2.imencode(".png", mixed)[1].tobytes()
+
+
+@pytest.mark.parametrize("w,h", [(85, 1), (85, 2), (85, 4), (85, 8), (85, 16), (85, 32), (85, 64), (85, 65), (86, 63), (86, 1), (21, 1), (21, 2)])
+def test_window_bits_at_the_power_of_two_boundaries(w, h):
+    """85 pixels make a 256-byte row: data sizes of exactly 256 ... 16384 bytes and their neighbours hit every step of
+    libpng's window-bits rule (optimize_cmf)."""
+    img = synth.smooth(w, h, w + h)
+    png = pm.encode_png(img)
+    assert png == cv2.imencode(".png", img)[1].tobytes()
+    n = h * (1 + 3 * w)
+    assert pm.zlib_header(n) == png[41:43]          # signature 8 + IHDR 25 + IDAT length / type 8
+    assert (pm.zlib_header(n) == b"\x78\x01") == (n > 16384)
