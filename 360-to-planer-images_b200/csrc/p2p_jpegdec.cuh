@@ -11,7 +11,7 @@
 //          jdsample.c h2v2 / h2v1 fancy upsampling (triangle filters, alternating rounding; replication when the
 //                     chroma plane is at most 2 samples wide), jdcolor.c ycc_rgb_convert   (jpegdec_color_kernel)
 // Supported: 8-bit, 3 components (YCbCr), 4:4:4 / 4:2:2 / 4:2:0, SOF0 / SOF1, one interleaved scan, restart markers.
-// Anything else (progressive, CMYK / grayscale, Adobe marker, EXIF orientation != 1, damaged data) is reported as
+// Anything else (progressive, CMYK / grayscale, RGB-coded files, EXIF orientation != 1, damaged data) is reported as
 // unsupported and the caller falls back to cv2.imread, as the reference does for every file.
 #pragma once
 #include <cuda_runtime.h>
@@ -201,7 +201,8 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
     size_t i = 2;
     uint16_t qt[4][64];
     bool have_qt[4] = {false, false, false, false};
-    bool jfif = false, have_frame = false;
+    bool jfif = false, adobe = false, have_frame = false;
+    int adobe_transform = 0;
     int cid[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, hs[3] = {1, 1, 1}, vs[3] = {1, 1, 1};
     Info &I = P.info;
     while (i + 4 <= len) {
@@ -266,12 +267,15 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
             if (sl != 2) return 1;
             P.dri = (seg[0] << 8) | seg[1];
         } else if (m == 0xE0) {
-            if (sl >= 5 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;
+            if (sl >= 14 && memcmp(seg, "JFIF\0", 5) == 0) jfif = true;   // jdmarker.c examine_app0 (APP0_DATA_LEN)
         } else if (m == 0xE1) {
             const int o = exif_orientation(seg, sl);
             if (o > 1 || o < 0) return 1;  // cv2.imread rotates / flips such files; -1 = malformed EXIF: leave it to cv2
         } else if (m == 0xEE) {
-            if (sl >= 5 && memcmp(seg, "Adobe", 5) == 0) return 1;
+            if (sl >= 12 && memcmp(seg, "Adobe", 5) == 0) {   // jdmarker.c examine_app14 (APP14_DATA_LEN)
+                adobe = true;
+                adobe_transform = seg[11];
+            }
         } else if (m == 0xDA) {
             if (!have_frame || sl != 1 + 6 + 3 || seg[0] != 3) return 1;
             for (int k = 0; k < 3; ++k) {
@@ -281,8 +285,15 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 if (P.td[k] > 3 || P.ta[k] > 3 || !P.dc[P.td[k]].present || !P.ac[P.ta[k]].present) return 1;
             }
             if (seg[7] != 0 || seg[8] != 63 || seg[9] != 0) return 1;
-            // colour space as libjpeg guesses it (jdapimin.c): JFIF -> YCbCr; else by component ids
-            if (!jfif && cid[0] == 'R' && cid[1] == 'G' && cid[2] == 'B') return 1;
+            // colour space as libjpeg guesses it (jdapimin.c default_decompress_parms): JFIF -> YCbCr; else the Adobe
+            // marker's transform flag (0 = RGB, anything else YCbCr for 3 components); else by component ids
+            if (!jfif) {
+                if (adobe) {
+                    if (adobe_transform == 0) return 1;
+                } else if (cid[0] == 'R' && cid[1] == 'G' && cid[2] == 'B') {
+                    return 1;
+                }
+            }
             if (hs[1] != 1 || vs[1] != 1 || hs[2] != 1 || vs[2] != 1) return 1;
             if (!((hs[0] == 1 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 2))) return 1;
             I.hmax = hs[0];

@@ -190,7 +190,8 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
 
 /* ---- JPEG panoramas decoded on the device (replaces cv2.imread(path) of a .jpg / .jpeg input, ref :244) ---- */
 /* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr, 4:4:4 / 4:2:2 / 4:2:0,
- * baseline or extended sequential Huffman, one interleaved scan, restart markers allowed, no Adobe marker, EXIF
+ * baseline or extended sequential Huffman, one interleaved scan, restart markers allowed, YCbCr by libjpeg's own rule (JFIF marker, or an Adobe marker with a non-zero transform flag
+ * as Photoshop / Lightroom write it, or component ids other than 'R' 'G' 'B'), EXIF
  * orientation 1 or absent), else P2P_ERR_UNSUPPORTED - the caller then reads the file with cv2.imread as before. */
 int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
 /* Host stage only (no GPU, debug / tests): layout[10] = {W, H, hmax, vmax, blocks per row and column of Y, Cb, Cr};

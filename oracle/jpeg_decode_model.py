@@ -33,6 +33,7 @@ def parse(data: bytes):
     i = 2
     qt, huff = {}, {}
     frame, scan, dri = None, None, 0
+    jfif, adobe = False, None
     while i < len(data):
         if data[i] != 0xFF:
             raise Unsupported("marker expected")
@@ -80,13 +81,20 @@ def parse(data: bytes):
             raise Unsupported("not a baseline / extended sequential Huffman JPEG")
         elif m == 0xDD:
             dri = (seg[0] << 8) | seg[1]
-        elif m == 0xEE and seg[:5] == b"Adobe":
-            raise Unsupported("Adobe colour transform marker")
+        elif m == 0xE0 and len(seg) >= 14 and seg[:5] == b"JFIF\x00":
+            jfif = True
+        elif m == 0xEE and len(seg) >= 12 and seg[:5] == b"Adobe":
+            adobe = seg[11]
         elif m == 0xDA:
             ns = seg[0]
             scan = [(seg[1 + 2 * k], seg[2 + 2 * k] >> 4, seg[2 + 2 * k] & 15) for k in range(ns)]
             if frame is None or ns != len(frame["comps"]):
                 raise Unsupported("non-interleaved scans")
+            # jdapimin.c default_decompress_parms, 3 components: JFIF -> YCbCr; else Adobe transform 0 -> RGB, other ->
+            # YCbCr; else component ids 'R','G','B' -> RGB, anything else YCbCr
+            ids = bytes(c[0] for c in frame["comps"])
+            if len(ids) == 3 and not jfif and (adobe == 0 if adobe is not None else ids == b"RGB"):
+                raise Unsupported("RGB-coded file")
             return dict(frame=frame, qt=qt, huff=huff, scan=scan, dri=dri, ecs=data[i:])
     raise Unsupported("no scan")
 

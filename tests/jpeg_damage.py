@@ -33,3 +33,38 @@ def damaged_files(seed: int, count: int, max_wh=(120, 90)):
         else:
             data.insert(int(rng.integers(lo, hi)), int(rng.integers(0, 256)))
         yield f"{i}:{w}x{h} q{q} rst{rst} mode{mode} [{lo},{hi})", bytes(data)
+
+
+def colour_space_variants(img):
+    """(label, file bytes, YCbCr?) - one 4:4:4 file with its JFIF / Adobe markers rearranged: libjpeg guesses the colour space
+    from them (jdapimin.c default_decompress_parms): JFIF -> YCbCr; else Adobe transform 0 -> RGB, other -> YCbCr; else by
+    component ids."""
+    base = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])[1].tobytes()
+    assert base[2:4] == b"\xff\xe0"
+    n0 = (base[4] << 8) | base[5]
+    jfif, rest = base[2:4 + n0], base[4 + n0:]
+
+    def adobe(transform, size=12):
+        body = (b"Adobe" + b"\x00\x64" + b"\x00\x00" + b"\x00\x00" + bytes([transform]))[:size]
+        return b"\xff\xee" + (len(body) + 2).to_bytes(2, "big") + body
+
+    soi = base[:2]
+    sof = rest.find(b"\xff\xc0")
+    rgb_ids = bytearray(rest)
+    for k, cid in enumerate(b"RGB"):                     # component ids in SOF0 and SOS
+        rgb_ids[sof + 4 + 6 + 3 * k] = cid
+    sos = bytes(rgb_ids).find(b"\xff\xda")
+    for k, cid in enumerate(b"RGB"):
+        rgb_ids[sos + 5 + 2 * k] = cid
+    rgb_ids = bytes(rgb_ids)
+    yield "jfif", base, True
+    yield "jfif+adobe1", soi + jfif + adobe(1) + rest, True
+    yield "jfif+adobe0", soi + jfif + adobe(0) + rest, True
+    yield "adobe1", soi + adobe(1) + rest, True
+    yield "adobe2", soi + adobe(2) + rest, True
+    yield "adobe0", soi + adobe(0) + rest, False
+    yield "short adobe segment", soi + adobe(0, size=7) + rest, True
+    yield "no marker", soi + rest, True
+    yield "no marker, ids RGB", soi + rgb_ids, False
+    yield "jfif, ids RGB", soi + jfif + rgb_ids, True
+    yield "adobe1, ids RGB", soi + adobe(1) + rgb_ids, True

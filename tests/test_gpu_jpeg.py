@@ -212,6 +212,22 @@ def test_front_end_with_damaged_jpeg_files_equals_imread_path(pkg, tmp_path, cap
     capfd.readouterr()
 
 
+def test_adobe_marked_files_follow_libjpegs_colour_space_rule(pkg, proj):
+    """Photoshop / Lightroom style files (Adobe APP14 marker, no JFIF) are decoded on the device when libjpeg takes them
+    for YCbCr, declined (cv2 fallback) when it takes them for RGB."""
+    from jpeg_damage import colour_space_variants
+
+    img = synth.smooth(640, 320, 3)
+    for label, data, ycc in colour_space_variants(img):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        if ycc:
+            assert np.array_equal(proj.decode_jpeg(data), ref), label
+        else:
+            with pytest.raises(pkg.P2PError) as e:
+                proj.decode_jpeg(data)
+            assert e.value.code == -6, label
+
+
 def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
     """Files without restart markers are Huffman-decoded on the device (self-synchronising subsequences); the pixels
     must equal the host decoder's (= cv2's), the fallback must work, and the option must switch the stage off."""

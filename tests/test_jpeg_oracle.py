@@ -229,3 +229,31 @@ def test_host_decoder_under_address_sanitizer(tmp_path):
     run = subprocess.run([str(exe)] + names, capture_output=True, text=True, env={"ASAN_OPTIONS": "detect_leaks=0"})
     assert run.returncode == 0 and "runtime error" not in run.stderr and "ERROR" not in run.stderr, run.stderr[-2000:]
     assert run.stdout.startswith("decoded ")
+
+
+def test_colour_space_rule_follows_libjpeg(pkg):
+    """Adobe-marked files (Photoshop / Lightroom), files without any marker, RGB component ids: decoded when libjpeg
+    takes them for YCbCr (same pixels as cv2), declined when it takes them for RGB - oracle, probe and host stage."""
+    import ctypes as C
+
+    from jpeg_damage import colour_space_variants
+    from oracle import jpeg_decode_model as jd
+
+    lib = pkg._lib.load()
+    w, h = C.c_int(), C.c_int()
+    img = synth.smooth(96, 64, 3)
+    base_pixels = None
+    for label, data, ycc in colour_space_variants(img):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert ref is not None, label
+        if base_pixels is None:
+            base_pixels = ref
+        assert np.array_equal(ref, base_pixels) == ycc, label          # cv2 itself follows the rule
+        assert (lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h)) == 0) == ycc, label
+        if ycc:
+            assert np.array_equal(jd.decode(data), ref), label
+            st, planes = _host_stage(lib, data)
+            assert st == 0 and np.array_equal(jd.reconstruct(jd.parse(data), planes), ref), label
+        else:
+            with pytest.raises(jd.Unsupported):
+                jd.decode(data)
