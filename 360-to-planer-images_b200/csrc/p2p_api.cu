@@ -621,7 +621,7 @@ int ensure_jd_flags(p2p_ctx *ctx, Slot &s) {
 int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p2pjdec::Parsed &P) {
     using namespace p2pjdec;
     const Info &I = P.info;
-    const uint32_t nb = (uint32_t)(I.hmax * I.vmax + 2);
+    const uint32_t nb = (I.ncomp == 1) ? 1u : (uint32_t)(I.hmax * I.vmax + 2);
     const uint32_t total_mcus = (uint32_t)I.mcux * I.mcuy;
     const uint32_t total_blocks = total_mcus * nb;
     const uint32_t ivl_mcus = P.dri ? (uint32_t)P.dri : total_mcus;
@@ -687,6 +687,7 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     G.n_bits = (uint32_t)(n * 8);
     G.n_sub = (uint32_t)subs.size();
     G.nb = (int)nb;
+    G.n_luma = I.hmax * I.vmax;
     G.hmax = I.hmax; G.vmax = I.vmax; G.mcux = I.mcux;
     G.total_blocks = total_blocks;
     G.n_ivl = n_ivl;
@@ -695,7 +696,7 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     for (int c = 0; c < 3; ++c) {
         G.bw[c] = I.bw[c];
         G.coef_off[c] = I.coef_off[c];
-        G.dc_count[c] = total_mcus * (c ? 1u : (uint32_t)(I.hmax * I.vmax));
+        G.dc_count[c] = (c >= I.ncomp) ? 0u : total_mcus * (c ? 1u : (uint32_t)(I.hmax * I.vmax));
         max_dc = G.dc_count[c] > max_dc ? G.dc_count[c] : max_dc;
     }
     G.dc_stride = (max_dc + 3) & ~3u;

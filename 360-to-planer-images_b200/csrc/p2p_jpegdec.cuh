@@ -10,8 +10,8 @@
 //   device jidctint.c jpeg_idct_islow on dequantised coefficients, + 128, clamp            (jpegdec_idct_kernel)
 //          jdsample.c h2v2 / h2v1 fancy upsampling (triangle filters, alternating rounding; replication when the
 //                     chroma plane is at most 2 samples wide), jdcolor.c ycc_rgb_convert   (jpegdec_color_kernel)
-// Supported: 8-bit, 3 components (YCbCr), 4:4:4 / 4:2:2 / 4:2:0, SOF0 / SOF1, one interleaved scan, restart markers.
-// Anything else (progressive, CMYK / grayscale, RGB-coded files, EXIF orientation != 1, damaged data) is reported as
+// Supported: 8-bit, 3 components (YCbCr; 4:4:4 / 4:2:2 / 4:2:0) or 1 (grayscale), SOF0 / SOF1, one scan, restart markers.
+// Anything else (progressive, CMYK, RGB-coded files, EXIF orientation != 1, damaged data) is reported as
 // unsupported and the caller falls back to cv2.imread, as the reference does for every file.
 #pragma once
 #include <cuda_runtime.h>
@@ -24,6 +24,9 @@ namespace p2pjdec {
 
 struct Info {
     int W = 0, H = 0;
+    int ncomp = 3;                   // 3 = YCbCr; 1 = grayscale: one block per MCU, and the two chroma planes are kept as
+                                     // all-zero coefficient planes (= 128 after the IDCT), for which jdcolor.c's YCbCr ->
+                                     // RGB gives R = G = B = Y, the same pixels as its gray_rgb_convert
     int hmax = 1, vmax = 1;          // luma sampling factors (chroma is 1 x 1)
     int mcux = 0, mcuy = 0;
     int bw[3] = {0, 0, 0}, bh[3] = {0, 0, 0};   // blocks per row / column of each component plane (MCU padded)
@@ -247,19 +250,20 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 j += 17 + (size_t)nv;
             }
         } else if (m == 0xC0 || m == 0xC1) {
-            if (have_frame || sl != 6 + 9 || seg[0] != 8 || seg[5] != 3) return 1;
+            if (have_frame || sl < 6 || seg[0] != 8 || (seg[5] != 3 && seg[5] != 1) || sl != 6 + 3 * (size_t)seg[5]) return 1;
+            I.ncomp = seg[5];
             I.H = (seg[1] << 8) | seg[2];
             I.W = (seg[3] << 8) | seg[4];
             // libjpeg stops at 65500 (JPEG_MAX_DIMENSION); a panorama slot (like cv2.remap's source) at 32766
             if (I.W <= 0 || I.H <= 0 || I.W >= 32767 || I.H >= 32767) return 1;
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < I.ncomp; ++k) {
                 cid[k] = seg[6 + 3 * k];
                 hs[k] = seg[7 + 3 * k] >> 4;
                 vs[k] = seg[7 + 3 * k] & 15;
                 tq[k] = seg[8 + 3 * k];
-                if (tq[k] > 3) return 1;
+                if (tq[k] > 3 || hs[k] < 1 || hs[k] > 4 || vs[k] < 1 || vs[k] > 4) return 1;
             }
-            if (cid[0] == cid[1] || cid[0] == cid[2] || cid[1] == cid[2]) return 1;
+            if (I.ncomp == 3 && (cid[0] == cid[1] || cid[0] == cid[2] || cid[1] == cid[2])) return 1;
             have_frame = true;
         } else if (m >= 0xC2 && m <= 0xCF) {
             return 1;  // progressive, lossless, arithmetic, hierarchical
@@ -277,14 +281,38 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 adobe_transform = seg[11];
             }
         } else if (m == 0xDA) {
-            if (!have_frame || sl != 1 + 6 + 3 || seg[0] != 3) return 1;
-            for (int k = 0; k < 3; ++k) {
+            const int nc = I.ncomp;
+            if (!have_frame || sl != 1 + 2 * (size_t)nc + 3 || seg[0] != nc) return 1;
+            for (int k = 0; k < nc; ++k) {
                 if (seg[1 + 2 * k] != cid[k]) return 1;
                 P.td[k] = seg[2 + 2 * k] >> 4;
                 P.ta[k] = seg[2 + 2 * k] & 15;
                 if (P.td[k] > 3 || P.ta[k] > 3 || !P.dc[P.td[k]].present || !P.ac[P.ta[k]].present) return 1;
             }
-            if (seg[7] != 0 || seg[8] != 63 || seg[9] != 0) return 1;
+            if (seg[1 + 2 * nc] != 0 || seg[2 + 2 * nc] != 63 || seg[3 + 2 * nc] != 0) return 1;
+            if (nc == 1) {
+                // a single-component scan is not interleaved: one block per MCU, ceil(W / 8) x ceil(H / 8) blocks whatever
+                // sampling factors the frame header declares; the chroma planes are zero coefficients on the same grid
+                I.hmax = I.vmax = 1;
+                I.mcux = (I.W + 7) / 8;
+                I.mcuy = (I.H + 7) / 8;
+                if (!have_qt[tq[0]]) return 1;
+                size_t off = 0;
+                for (int k = 0; k < 3; ++k) {
+                    memcpy(I.quant[k], qt[tq[0]], sizeof(I.quant[k]));
+                    I.bw[k] = I.mcux;
+                    I.bh[k] = I.mcuy;
+                    I.coef_off[k] = off;
+                    off += (size_t)I.bw[k] * I.bh[k] * 64;
+                    P.td[k] = P.td[0];
+                    P.ta[k] = P.ta[0];
+                }
+                I.n_coef = off;
+                I.cw = I.W;
+                I.ch = I.H;
+                P.ecs = i;
+                return 0;
+            }
             // colour space as libjpeg guesses it (jdapimin.c default_decompress_parms): JFIF -> YCbCr; else the Adobe
             // marker's transform flag (0 = RGB, anything else YCbCr for 3 components); else by component ids
             if (!jfif) {
@@ -327,6 +355,7 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
     br.end = d + len;
     int pred[3] = {0, 0, 0};
     const int nblk[3] = {I.hmax * I.vmax, 1, 1};
+    if (I.ncomp == 1) memset(coef + I.coef_off[1], 0, (I.n_coef - I.coef_off[1]) * sizeof(int16_t));   // "chroma" of a gray file
     int togo = P.dri;
     int next_rst = 0;   // restart markers must come in sequence: libjpeg resynchronises by its own heuristics otherwise
     for (int my = 0; my < I.mcuy; ++my) {
@@ -347,7 +376,7 @@ inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *c
                 }
                 --togo;
             }
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < I.ncomp; ++c) {
                 const HuffTable &dct = P.dc[P.td[c]], &act = P.ac[P.ta[c]];
                 for (int b = 0; b < nblk[c]; ++b) {
                     const int by = c ? my : my * I.vmax + b / I.hmax;
@@ -434,7 +463,8 @@ struct DevHuff {                 // one per component: its DC and AC table
 struct HuffGeom {
     uint32_t n_bits;             // bits of the destuffed scan
     uint32_t n_sub;              // subsequences
-    int nb;                      // blocks per MCU (hmax * vmax + 2)
+    int nb;                      // blocks per MCU (hmax * vmax + 2; 1 for a grayscale file)
+    int n_luma;                  // ... of which belong to component 0 (hmax * vmax)
     int hmax, vmax, mcux;
     uint32_t total_blocks;
     int bw[3];
@@ -508,12 +538,12 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
                                                       int32_t *__restrict__ dcdiff, bool &damaged) {
     uint32_t done = 0;
     int16_t *cur = nullptr;
-    int comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
+    int comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
     auto locate = [&]() {   // address of the block being written
         const uint32_t mcu = blk / (uint32_t)G.nb;
         const int k = (int)(blk - mcu * (uint32_t)G.nb);
         const uint32_t my = mcu / (uint32_t)G.mcux, mx = mcu - my * (uint32_t)G.mcux;
-        const int c = (k < G.nb - 2) ? 0 : k - (G.nb - 2) + 1;
+        const int c = (k < G.n_luma) ? 0 : k - G.n_luma + 1;
         const uint32_t by = c ? my : my * G.vmax + k / G.hmax, bx = c ? mx : mx * G.hmax + k % G.hmax;
         cur = coef + G.coef_off[c] + ((size_t)by * G.bw[c] + bx) * 64;
     };
@@ -537,7 +567,7 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
                 const int diff = s ? extend_bits((win << len) >> (32 - s), s) : 0;
                 const uint32_t mcu = blk / (uint32_t)G.nb;
                 const int k = (int)(blk - mcu * (uint32_t)G.nb);
-                const uint32_t idx = comp ? mcu : mcu * (uint32_t)(G.nb - 2) + (uint32_t)k;
+                const uint32_t idx = comp ? mcu : mcu * (uint32_t)G.n_luma + (uint32_t)k;
                 dcdiff[(size_t)comp * G.dc_stride + idx] = diff;
             }
             st.pos += (uint32_t)(len + s);
@@ -579,7 +609,7 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
         if (st.z >= 64) {   // block complete
             st.z = 0;
             st.b = (st.b + 1 == G.nb) ? 0 : st.b + 1;
-            comp = (st.b < G.nb - 2) ? 0 : st.b - (G.nb - 2) + 1;
+            comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
             ++done;
             if (WRITE) {
                 ++blk;
@@ -662,7 +692,7 @@ huff_dc_kernel(const int32_t *__restrict__ dcdiff, const uint32_t *__restrict__ 
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (idx >= G.dc_count[c]) return;
-    const uint32_t per = c ? 1u : (uint32_t)(G.nb - 2);              // blocks of this component per MCU
+    const uint32_t per = c ? 1u : (uint32_t)G.n_luma;              // blocks of this component per MCU
     const uint32_t seg = (G.ivl_blocks / (uint32_t)G.nb) * per;      // ... and per restart interval
     const uint32_t seg0 = (idx / seg) * seg;
     const size_t base = (size_t)c * G.dc_stride;

@@ -166,6 +166,8 @@ def entropy_decode(p):
     """Coefficient planes per component: [blocks_y, blocks_x, 64] natural order, on the MCU-padded block grid."""
     f = p["frame"]
     comps = f["comps"]
+    if len(comps) == 1:          # a single-component scan is not interleaved: one block per MCU whatever the sampling factors
+        comps = [(comps[0][0], 1, 1, comps[0][3])]
     hmax, vmax = max(c[1] for c in comps), max(c[2] for c in comps)
     mcux = -(-f["W"] // (8 * hmax))
     mcuy = -(-f["H"] // (8 * vmax))
@@ -303,8 +305,8 @@ def decode(data: bytes) -> np.ndarray:
     p = parse(data)
     f = p["frame"]
     comps = f["comps"]
-    if len(comps) != 3:
-        raise Unsupported("not a 3-component YCbCr file")
+    if len(comps) not in (1, 3):
+        raise Unsupported("not a grayscale or 3-component YCbCr file")
     planes, _ = entropy_decode(p)
     return reconstruct(p, planes)
 
@@ -314,6 +316,9 @@ def reconstruct(p, planes) -> np.ndarray:
     f = p["frame"]
     comps = f["comps"]
     W, H = f["W"], f["H"]
+    if len(comps) == 1:          # grayscale: jdcolor.c gray_rgb_convert, B = G = R = Y
+        y = plane_from_blocks(idct_islow(planes[0], p["qt"][comps[0][3]]))[:H, :W]
+        return np.repeat(y[..., None], 3, axis=2).astype(np.uint8)
     hmax, vmax = max(c[1] for c in comps), max(c[2] for c in comps)
     if (comps[0][1], comps[0][2]) != (hmax, vmax) or any((c[1], c[2]) != (1, 1) for c in comps[1:]):
         raise Unsupported("sampling factors")

@@ -10,12 +10,14 @@ from tools import synth_inputs as synth
 SAMPLING = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
 
 
-def damaged_files(seed: int, count: int, max_wh=(120, 90)):
-    """Yields (label, bytes)."""
+def damaged_files(seed: int, count: int, max_wh=(120, 90), gray_every: int = 0):
+    """Yields (label, bytes).  ``gray_every`` = k: every k-th file is a grayscale JPEG."""
     rng = np.random.default_rng(seed)
     for i in range(count):
         w, h = int(rng.integers(16, max_wh[0])), int(rng.integers(16, max_wh[1]))
         img = synth.smooth(w, h, i) if i % 2 else synth.noise(w, h, i)
+        if gray_every and i % gray_every == 0:
+            img = np.ascontiguousarray(img[..., 0])
         rst, q = int(rng.integers(0, 4)), int(rng.integers(5, 100))
         samp = SAMPLING[int(rng.integers(0, 3))]
         data = bytearray(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,

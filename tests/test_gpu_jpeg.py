@@ -228,6 +228,31 @@ def test_adobe_marked_files_follow_libjpegs_colour_space_rule(pkg, proj):
             assert e.value.code == -6, label
 
 
+def test_grayscale_files_decode_like_cv2_imread(pkg, proj, tmp_path):
+    """Grayscale JPEG panoramas: B = G = R = Y as cv2.imread returns them, with the Huffman stage on the device and on the
+    host, with restart intervals, and through the front end."""
+    L = pkg._lib
+    rng = np.random.default_rng(8)
+    for k, (w, h) in enumerate([(1, 1), (9, 7), (200, 64), (1024, 512), (2048, 1024), (1001, 333)]):
+        g = synth.smooth(w, h, k)[..., 1] if k % 2 else np.clip(synth.smooth(w, h, k)[..., 0].astype(int) + rng.integers(-9, 10, (h, w)), 0, 255).astype(np.uint8)
+        for params in ([cv2.IMWRITE_JPEG_QUALITY, 95], [cv2.IMWRITE_JPEG_QUALITY, 70, cv2.IMWRITE_JPEG_RST_INTERVAL, 3]):
+            data = cv2.imencode(".jpg", g, params)[1].tobytes()
+            ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+            n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
+            assert np.array_equal(proj.decode_jpeg(data), ref), (w, h, params)
+            assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1, "the device Huffman stage did not run"
+            proj.set_option(L.OPT_GPU_HUFFMAN, 0)
+            try:
+                assert np.array_equal(proj.decode_jpeg(data), ref), (w, h, params, "host stage")
+            finally:
+                proj.set_option(L.OPT_GPU_HUFFMAN, 1)
+    pano = synth.smooth(1024, 512, 5)[..., 0].copy()
+    path = tmp_path / "gray.jpg"
+    cv2.imwrite(str(path), pano)
+    view = pkg.panorama_to_plane(path, 100, (200, 120), 90, 60)
+    assert np.array_equal(view, pkg.process_yaw_and_pitchs(cv2.imread(str(path)), 90, [60], 200, 120, 100)[0])
+
+
 def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
     """Files without restart markers are Huffman-decoded on the device (self-synchronising subsequences); the pixels
     must equal the host decoder's (= cv2's), the fallback must work, and the option must switch the stage off."""

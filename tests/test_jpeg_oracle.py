@@ -92,8 +92,10 @@ def test_unsupported_files_are_reported(pkg):
     gray = cv2.imencode(".jpg", img[..., 0])[1].tobytes()
     png = cv2.imencode(".png", img)[1].tobytes()
     ok = cv2.imencode(".jpg", img)[1].tobytes()
-    for data in (prog, gray, png, ok[:300], b""):
+    cmyk = ok.replace(b"\xff\xc0\x00\x11\x08", b"\xff\xc0\x00\x14\x08", 1)   # a frame header announcing more data
+    for data in (prog, png, ok[:300], cmyk, b""):
         assert lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h)) == -6
+    assert lib.p2p_jpeg_probe(gray, len(gray), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
     assert lib.p2p_jpeg_probe(ok, len(ok), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
     # a truncated scan must not be decoded with made-up bits: libjpeg has its own recovery, the file is left to it
     lay = (C.c_int32 * 10)()
@@ -143,7 +145,7 @@ def test_damaged_files_are_declined_or_decode_like_cv2(pkg, capfd):
 
     lib = pkg._lib.load()
     declined = same = 0
-    for label, data in damaged_files(2025, 400):
+    for label, data in damaged_files(2025, 400, gray_every=4):
         ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
         st, planes = _host_stage(lib, data)
         if st:
@@ -215,7 +217,7 @@ def test_host_decoder_under_address_sanitizer(tmp_path):
         pytest.skip("sanitizer runtime not available: " + build.stderr[-300:])
     rng = np.random.default_rng(9)
     names = []
-    for k, (label, data) in enumerate(damaged_files(301, 600)):
+    for k, (label, data) in enumerate(damaged_files(301, 600, gray_every=3)):
         d = bytearray(data)
         if k % 3 == 0:                                     # heavier damage: garbage runs, truncation
             for _ in range(int(rng.integers(1, 6))):
@@ -257,3 +259,26 @@ def test_colour_space_rule_follows_libjpeg(pkg):
         else:
             with pytest.raises(jd.Unsupported):
                 jd.decode(data)
+
+
+def gray_files():
+    rng = np.random.default_rng(23)
+    for k, (h, w) in enumerate([(1, 1), (7, 9), (8, 8), (17, 33), (40, 56), (47, 95), (64, 200)]):
+        for q, rst in ((95, 0), (60, 2), (15, 1)):
+            g = synth.noise(w, h, k)[..., 0] if q != 60 else synth.smooth(w, h, k)[..., 1]
+            yield f"{w}x{h}_q{q}_rst{rst}", cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst])[1].tobytes()
+
+
+@pytest.mark.parametrize("name,data", list(gray_files()), ids=[n for n, _ in gray_files()])
+def test_grayscale_files_decode_like_cv2_imread(pkg, name, data):
+    """cv2.imread(path) of a grayscale JPEG returns B = G = R = Y (libjpeg's gray -> RGB conversion); a single-component
+    scan has one block per MCU.  Oracle against cv2, host stage against the oracle (luma plane; the chroma planes the
+    device pipeline keeps for such files are all zero)."""
+    from oracle import jpeg_decode_model as jd
+
+    ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    assert ref.shape[2] == 3 and np.array_equal(ref[..., 0], ref[..., 1]) and np.array_equal(ref[..., 0], ref[..., 2])
+    assert np.array_equal(jd.decode(data), ref)
+    st, planes = _host_stage(pkg._lib.load(), data)
+    oracle_planes, _ = jd.entropy_decode(jd.parse(data))
+    assert st == 0 and np.array_equal(planes[0], oracle_planes[0]) and not planes[1].any() and not planes[2].any()
