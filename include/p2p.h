@@ -189,8 +189,8 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
                           uint8_t *out_host, size_t out_stride, size_t *sizes, uint8_t *pixels_host);
 
 /* ---- JPEG panoramas decoded on the device (replaces cv2.imread(path) of a .jpg / .jpeg input, ref :244) ---- */
-/* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr, 4:4:4 / 4:2:2 / 4:2:0,
- * baseline or extended sequential Huffman, one interleaved scan, restart markers allowed, YCbCr by libjpeg's own rule (JFIF marker, or an Adobe marker with a non-zero transform flag
+/* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr 4:4:4 / 4:2:2 / 4:2:0 or
+ * grayscale, baseline or extended sequential Huffman, one scan, restart markers allowed, YCbCr by libjpeg's own rule (JFIF marker, or an Adobe marker with a non-zero transform flag
  * as Photoshop / Lightroom write it, or component ids other than 'R' 'G' 'B'), EXIF
  * orientation 1 or absent), else P2P_ERR_UNSUPPORTED - the caller then reads the file with cv2.imread as before. */
 int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
