@@ -108,14 +108,15 @@ def _open_image(path):
     return cv2.imread(str(path))
 
 
-def _decode_source(proj, src):
-    """Host pixels of a source (fractional-yaw path, or a damaged file the device decoder gave up on)."""
+def _decode_source(proj, src, slot=None):
+    """Host pixels of a source (fractional-yaw path, or a damaged file the device decoder gave up on).  ``slot``: the slot
+    the caller already holds (no second one is taken)."""
     import cv2
 
     if not isinstance(src, _JpegSource):
         return src
     try:
-        return proj.decode_jpeg(src.data)
+        return proj.decode_jpeg(src.data, slot=slot)
     except _engine.P2PError as e:
         if e.code != -6:
             raise
@@ -176,17 +177,24 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
     the device projection + encoder, using the module caches."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
-    if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
-        try:  # JPEG in, JPEG out: no pixel ever crosses PCIe
-            with _slot(proj, lease) as (s,):
-                proj.upload_jpeg(s, src.data)
-                flat = proj.project_jpeg(s, [t[2] for t in tables], consts, output_width, output_height,
-                                         copy=lease is None)
-            n_p = len(pitch_angles)
-            return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
-        except _engine.P2PError as e:
-            if e.code != -6:
-                raise
+    if yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
+        shifts = [t[2] for t in tables]
+        with _slot(proj, lease) as (s,):
+            pano = src
+            if isinstance(src, _JpegSource):
+                try:  # JPEG in, JPEG out: no pixel ever crosses PCIe
+                    proj.upload_jpeg(s, src.data)
+                    pano = None                      # the panorama is resident in the slot
+                except _engine.P2PError as e:
+                    if e.code != -6:
+                        raise
+                    pano = _decode_source(proj, src, slot=s)
+            if pano is None:
+                flat = proj.project_jpeg(s, shifts, consts, output_width, output_height, copy=lease is None)
+            else:
+                flat = proj.process_image_jpeg(s, pano, shifts, consts, output_width, output_height, copy=lease is None)
+        n_p = len(pitch_angles)
+        return [flat[k * n_p:(k + 1) * n_p] for k in range(len(yaw_angles))]
     return proj.project_image_jpeg(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height,
                                    fov_deg, consts=consts, tables=tables)
 
@@ -210,7 +218,7 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
                 except _engine.P2PError as e:
                     if e.code != -6:
                         raise
-                    pano = _decode_source(proj, src)
+                    pano = _decode_source(proj, src, slot=s)
             flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False,
                                              copy=lease is None)
             views = None
