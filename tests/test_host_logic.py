@@ -169,3 +169,45 @@ def test_header_is_plain_c_and_links(pkg, tmp_path):
         # no GPU here: the program must fail loudly at p2p_create, not crash
         run = subprocess.run([str(exe), "64", "32", "16", "8", "90", str(tmp_path / "o.bin")], capture_output=True, text=True)
         assert run.returncode == 2 and "p2p_create" in run.stderr
+
+
+def test_slot_lease_keeps_the_slot_until_the_files_are_written(pkg):
+    """``_slot``: without a lease the slot goes back when the ``with`` block ends; with a lease (an ExitStack) it stays taken
+    until the caller closes the stack - also when the work in between raises - so files can be written straight from the
+    slot's page-locked buffer.  (Pure host logic, checked with a stand-in for the projector's slot pool.)"""
+    import contextlib
+
+    front = pkg.panorama_to_plane_pitch
+
+    class Pool:
+        def __init__(self):
+            self.free, self.log = [2, 1, 0], []
+
+        @contextlib.contextmanager
+        def slots(self, n):
+            got = tuple(self.free.pop() for _ in range(n))
+            self.log.append(("take", got))
+            try:
+                yield got
+            finally:
+                self.free.extend(reversed(got))
+                self.log.append(("give", got))
+
+    pool = Pool()
+    with front._slot(pool, None) as (s,):
+        assert s == 0 and pool.free == [2, 1]
+    assert pool.free == [2, 1, 0]
+    with contextlib.ExitStack() as lease:
+        with front._slot(pool, lease) as (s,):
+            assert s == 0
+        assert pool.free == [2, 1], "the leased slot must outlive the with block"
+        with front._slot(pool, lease) as (s2,):        # a second image under the same lease takes another slot
+            assert s2 == 1
+    assert pool.free == [2, 1, 0] or sorted(pool.free) == [0, 1, 2]
+    try:
+        with contextlib.ExitStack() as lease:
+            with front._slot(pool, lease) as (s,):
+                raise RuntimeError("projection failed")
+    except RuntimeError:
+        pass
+    assert sorted(pool.free) == [0, 1, 2], "an exception must not leak the slot"
