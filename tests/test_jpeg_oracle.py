@@ -282,3 +282,33 @@ def test_grayscale_files_decode_like_cv2_imread(pkg, name, data):
     st, planes = _host_stage(pkg._lib.load(), data)
     oracle_planes, _ = jd.entropy_decode(jd.parse(data))
     assert st == 0 and np.array_equal(planes[0], oracle_planes[0]) and not planes[1].any() and not planes[2].any()
+
+
+def test_block_norm_bound_never_declines_valid_extreme_files(pkg):
+    """The damaged-data bound (dequantised block norm <= 2048) against the harshest valid content: checkerboards, 1-pixel
+    stripes, binary noise, hard edges at qualities 1 .. 100 (all-255 quantisation tables at quality 1), colour and
+    grayscale, 4:4:4 / 4:2:2 / 4:2:0 - every file must pass the host stage (measured maximum: 1249, a checkerboard at
+    quality 1)."""
+    import ctypes as C
+
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(0)
+    w, h = 67, 45
+    yy, xx = np.mgrid[0:h, 0:w]
+    pats = {
+        "checker": np.repeat((((xx + yy) & 1) * 255)[..., None], 3, 2),
+        "vstripes": np.repeat(((xx & 1) * 255)[..., None], 3, 2),
+        "hstripes": np.repeat(((yy & 1) * 255)[..., None], 3, 2),
+        "binary": rng.integers(0, 2, (h, w, 3)) * 255,
+        "blocks4": np.repeat(np.repeat(rng.integers(0, 2, (h // 4 + 1, w // 4 + 1, 3)) * 255, 4, 0), 4, 1)[:h, :w],
+        "colour_checker": np.stack([((xx + yy) & 1) * 255, ((xx // 2 + yy) & 1) * 255, ((xx + yy // 2) & 1) * 255], -1),
+        "half": np.concatenate([np.zeros((h, w // 2, 3)), np.full((h, w - w // 2, 3), 255)], 1),
+    }
+    for q in (1, 2, 3, 5, 10, 50, 100):
+        for samp in SAMPLING.values():
+            for name, img in pats.items():
+                img = np.ascontiguousarray(img, dtype=np.uint8)
+                for src in (img, np.ascontiguousarray(img[..., 0])):
+                    data = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp])[1].tobytes()
+                    st, _ = _host_stage(lib, data)
+                    assert st == 0, (q, samp, name, src.ndim)
