@@ -28,6 +28,7 @@ from .panorama_to_plane_pitch import (  # noqa: E402
     process_single_image,
     process_yaw_and_pitchs,
     set_device,
+    set_devices,
     yaw_mapping_cache,
 )
 from ._lib import P2PError, PitchConsts  # noqa: E402

@@ -49,6 +49,8 @@ SIGNATURES = {
     "p2p_rotate_pano": (_i, [_vp, _i, _i, _i32p, _i32p]),
     "p2p_project_views": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _u8p, _i]),
     "p2p_project_batch": (_i, [_vp, _i, _i32p, _i, _i32p, _i, _pcp, _i, _i, C.POINTER(_vp), _i]),
+    "p2p_project_view_list": (_i, [_vp, _i, _i, _i32p, _pcp, _i, _i, _i, _i, _u8p, _i]),
+    "p2p_copy_pano": (_i, [_vp, _i, _vp, _i]),
     "p2p_process_image": (_i, [_vp, _i, _u8p, _i, _i, _sz, _i, _i32p, _i, _pcp, _i, _i, _u8p]),
     "p2p_view_row_range": (_i, [_vp, _i, _pcp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "p2p_encode_jpeg": (_i, [_vp, _i, _u8p, _i, _i, _i, _i, _i, _u8p, _sz, C.POINTER(_sz)]),
@@ -77,6 +79,7 @@ SIGNATURES = {
 OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER_LAUNCH, OPT_MIRROR, OPT_INTERP, OPT_TRIG = 0, 1, 2, 3, 4, 5, 6, 7
 OPT_PARTIAL_UPLOAD = 8
 OPT_GPU_HUFFMAN, OPT_GPU_HUFFMAN_COUNT = 9, 10
+OPT_SEG_CHUNKS = 11
 
 _lib = None
 

@@ -108,12 +108,12 @@ struct p2p_ctx {
     int n_slots = 0;
     Slot *slots = nullptr;
     std::mutex mu;
-    std::string err;
     int opt_sampler = 1;
     int opt_warp_w = 32;
     int opt_ny = 4;
     int opt_nb = 1;
-    int opt_mirror = 1;
+    int opt_mirror = 2;        // 2: row-segment kernel (all-word stores, view groups), 1: round-1 mirror kernel, 0: none
+    int opt_seg_chunks = 4;    // chunks of 32 pixel pairs a warp of the row-segment kernel walks
     int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
     int opt_partial = 1;       // p2p_process_image transfers only the panorama rows its views can touch
@@ -132,13 +132,20 @@ struct p2p_ctx {
 
 namespace {
 
+// The last error is kept PER CALLING THREAD (like errno): a context is driven by many host threads at once (one per image
+// in flight), several entry points fail before or after they hold the context lock, and a message shared through the
+// context could be overwritten - or freed - by another thread between the failing call and p2p_last_error.
+thread_local std::string tl_err;
+thread_local const p2p_ctx *tl_err_ctx = nullptr;
+
 int fail(p2p_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
     if (ctx) {
-        ctx->err = what;
+        tl_err = what;
         if (e != cudaSuccess) {
-            ctx->err += ": ";
-            ctx->err += cudaGetErrorString(e);
+            tl_err += ": ";
+            tl_err += cudaGetErrorString(e);
         }
+        tl_err_ctx = ctx;
     }
     return code;
 }
@@ -156,6 +163,9 @@ template <typename T>
 int ensure(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
     if (*cap >= bytes && *ptr) return P2P_OK;
     if (*ptr) {
+        // a buffer that has to grow (a larger image than this slot has seen) grows with 50 % headroom, and never
+        // shrinks: cudaFree / cudaMalloc synchronise the whole device, so a folder of mixed sizes must not pay them per image
+        bytes += bytes / 2;
         CK(cudaFree(*ptr));
         *ptr = nullptr;
         *cap = 0;
@@ -172,7 +182,7 @@ int ensure(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
 template <typename T>
 int ensure_grow(p2p_ctx *ctx, T **ptr, size_t *cap, size_t bytes) {
     if (*cap >= bytes && *ptr) return P2P_OK;
-    return ensure(ctx, ptr, cap, bytes + bytes / 2);
+    return ensure(ctx, ptr, cap, *ptr ? bytes : bytes + bytes / 2);  // ensure() adds the headroom itself when it regrows
 }
 
 int slot_ok(p2p_ctx *ctx, int slot) { return ctx && slot >= 0 && slot < ctx->n_slots; }
@@ -344,6 +354,96 @@ proj_fn pick_kernel(bool quad, int nb, int warp_w, int ny) {
     }
 }
 
+// ---- row-segment kernel: any flat list of views in one launch ----------------------------------
+typedef void (*rows_fn)(const RowsParams);
+
+template <bool TRIG, bool FULL>
+rows_fn pick_rows_ny(int ny) {
+    switch (ny) {
+        case 1: return project_rows_kernel<1, TRIG, FULL>;
+        case 2: return project_rows_kernel<2, TRIG, FULL>;
+        case 3: return project_rows_kernel<3, TRIG, FULL>;
+        default: return project_rows_kernel<4, TRIG, FULL>;
+    }
+}
+
+rows_fn pick_rows(bool numpy_trig, bool full, int ny) {
+    if (numpy_trig) return full ? pick_rows_ny<true, true>(ny) : pick_rows_ny<true, false>(ny);
+    return full ? pick_rows_ny<false, true>(ny) : pick_rows_ny<false, false>(ny);
+}
+
+bool rows_kernel_usable(const p2p_ctx *ctx, int W, int H, int n_views, const void *d_out) {
+    return ctx->opt_mirror == 2 && ctx->opt_sampler == 1 && ctx->opt_interp == 0 && (W & 7) == 0 &&
+           (reinterpret_cast<uintptr_t>(d_out) & 3) == 0 &&
+           (unsigned long long)W * H * 3 * (unsigned long long)n_views < (1ull << 32);  // 32-bit byte offsets in the kernel
+}
+
+// views[i] = (yaw roll, pitch constants) -> d_out + out_index[i] * W * H * 3.  Views with bit-identical pitch constants
+// share one coordinate evaluation (up to 4 per group: the key of the reference's pitch_mapping_cache, ref :55-73, has no
+// yaw in it); the groups of the whole list go out in one launch (kMaxViewGroups per launch).
+int launch_rows(p2p_ctx *ctx, Slot &s, int n_views, const int32_t *yaw_shift, const p2p_pitch_consts *pitch,
+                const int *out_index, int W, int H, uint8_t *d_out, int row_begin = 0, int row_end = -1) {
+    if (row_end < 0) row_end = H;
+    if (row_begin >= row_end) return P2P_OK;
+    int rc = ensure_texture(ctx, s);
+    if (rc) return rc;
+    const int band = row_end - row_begin;
+    if ((band + 7) / 8 > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+    RowsParams P;
+    memset(&P, 0, sizeof(P));
+    P.tex = s.tex;
+    P.out = d_out;
+    P.W = W;
+    P.H = H;
+    P.v_begin = row_begin;
+    P.v_end = row_end;
+    P.n_chunks = (W / 2 + 1 + 31) / 32;
+    P.seg_chunks = ctx->opt_seg_chunks;
+    P.halfW = (float)(W / 2.0);
+    P.halfH = (float)(H / 2.0);
+    P.Wp_f = (float)s.Wp;
+    P.Hp_f = (float)s.Hp;
+    P.Umax = (float)(s.Wp - 1);
+    P.Vmax = (float)(s.Hp - 1);
+    P.inv_Wp = (float)(1.0 / (double)s.Wp);
+    P.inv_Hp = (float)(1.0 / (double)s.Hp);
+    const unsigned long long view_bytes = (unsigned long long)W * H * 3;
+    std::vector<char> used((size_t)n_views, 0);
+    int ng = 0, ny_max = 0;
+    bool full = true;
+    auto flush = [&]() -> int {
+        if (ng == 0) return P2P_OK;
+        for (int g = 0; g < ng; ++g) full = full && (P.grp[g].ny == ny_max);
+        dim3 grid((P.n_chunks + P.seg_chunks - 1) / P.seg_chunks, (band + 7) / 8, ng);
+        pick_rows(ctx->opt_trig == 0, full, ny_max)<<<grid, 256, 0, s.stream>>>(P);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        ng = 0;
+        ny_max = 0;
+        full = true;
+        return P2P_OK;
+    };
+    for (int i = 0; i < n_views; ++i) {
+        if (used[i]) continue;
+        ViewGroup &G = P.grp[ng];
+        memset(&G, 0, sizeof(G));
+        G.pc = PitchC{pitch[i].f, pitch[i].c, pitch[i].s};
+        for (int k = i; k < n_views && G.ny < 4; ++k) {
+            if (used[k] || memcmp(&pitch[k], &pitch[i], sizeof(p2p_pitch_consts)) != 0) continue;
+            used[k] = 1;
+            G.shift_n[G.ny] = (float)((double)yaw_shift[k] / (double)s.Wp);
+            G.out_off32[G.ny] = (unsigned)((unsigned long long)out_index[k] * view_bytes);
+            G.ny++;
+        }
+        ny_max = (G.ny > ny_max) ? G.ny : ny_max;
+        if (++ng == kMaxViewGroups) {
+            rc = flush();
+            if (rc) return rc;
+        }
+    }
+    return flush();
+}
+
 // One or several (nb = 1, 2, 4) same-sized resident panoramas -> their view batches.  All launches
 // go to the stream of the first slot.
 int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32_t *yaw_shift, int n_pitch,
@@ -365,6 +465,21 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
             int rc = ensure_texture(ctx, *sl[b]);
             if (rc) return rc;
         }
+    }
+    if (nb == 1 && rows_kernel_usable(ctx, W, H, n_yaw * n_pitch, d_out[0])) {
+        // view (k, j) = yaw k, pitch j -> output index k * n_pitch + j, listed pitch-major so that the yaws of one
+        // pitch land in the same group
+        std::vector<int32_t> ys((size_t)n_yaw * n_pitch);
+        std::vector<p2p_pitch_consts> ps((size_t)n_yaw * n_pitch);
+        std::vector<int> oi((size_t)n_yaw * n_pitch);
+        int n = 0;
+        for (int j = 0; j < n_pitch; ++j)
+            for (int k = 0; k < n_yaw; ++k, ++n) {
+                ys[n] = yaw_shift[k];
+                ps[n] = pitch[j];
+                oi[n] = k * n_pitch + j;
+            }
+        return launch_rows(ctx, s, n, ys.data(), ps.data(), oi.data(), W, H, d_out[0]);
     }
     int ny_max = ctx->opt_ny < 1 ? 1 : (ctx->opt_ny > 4 ? 4 : ctx->opt_ny);
     // the kernel adds k * yaw_stride as a 32-bit offset: fall back to fewer yaws per launch for huge outputs
@@ -430,7 +545,7 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
                 continue;
             }
             // mirror-symmetric kernel: texture sampler, one image per launch, vector-store friendly sizes
-            if (ctx->opt_mirror && ctx->opt_sampler == 1 && nb == 1 && quad && (W & 7) == 0) {
+            if (ctx->opt_mirror == 1 && ctx->opt_sampler == 1 && nb == 1 && quad && (W & 7) == 0) {
                 dim3 mgrid((W / 2 + 1 + 31) / 32, (H + kMirRows - 1) / kMirRows, np_l);
                 if (mgrid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
                 if (P.numpy_trig) {
@@ -1096,7 +1211,10 @@ void p2p_destroy(p2p_ctx *ctx) {
     delete ctx;
 }
 
-const char *p2p_last_error(p2p_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char *p2p_last_error(p2p_ctx *ctx) {
+    if (!ctx) return "null context";
+    return (tl_err_ctx == ctx) ? tl_err.c_str() : "";  // valid until this thread's next failing call
+}
 
 int p2p_set_option(p2p_ctx *ctx, int key, int value) {
     if (!ctx) return P2P_ERR_INVALID;
@@ -1119,8 +1237,12 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             ctx->opt_nb = value;
             return P2P_OK;
         case P2P_OPT_MIRROR:
-            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "mirror must be 0 or 1");
+            if (value < 0 || value > 2) return fail(ctx, P2P_ERR_INVALID, "mirror must be 0, 1 or 2");
             ctx->opt_mirror = value;
+            return P2P_OK;
+        case P2P_OPT_SEG_CHUNKS:
+            if (value < 1 || value > 64) return fail(ctx, P2P_ERR_INVALID, "seg_chunks must be 1..64");
+            ctx->opt_seg_chunks = value;
             return P2P_OK;
         case P2P_OPT_INTERP:
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "interp must be 0 (cv2 fixed point) or 1 (exact bilinear)");
@@ -1154,6 +1276,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_COUNT_LAUNCHES: *value = (int)ctx->launches; return P2P_OK;
         case P2P_OPT_IMAGES_PER_LAUNCH: *value = ctx->opt_nb; return P2P_OK;
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
+        case P2P_OPT_SEG_CHUNKS: *value = ctx->opt_seg_chunks; return P2P_OK;
         case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
         case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
         case P2P_OPT_PARTIAL_UPLOAD: *value = ctx->opt_partial; return P2P_OK;
@@ -1365,6 +1488,115 @@ int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_ya
         }
         i += g;
     }
+    return P2P_OK;
+}
+
+// Flat view list, optional row band: view i = (yaw_shift[i], pitch[i]) -> out + i * W * H * 3, rows row_begin .. row_end - 1.
+int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *yaw_shift, const p2p_pitch_consts *pitch,
+                          int W, int H, int row_begin, int row_end, uint8_t *out, int out_on_device) {
+    if (!ctx) return P2P_ERR_INVALID;
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    if (n_views <= 0 || !yaw_shift || !pitch || !out) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
+    if (W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "output size must be positive");
+    if (W >= 32767 || H >= 32767) return fail(ctx, P2P_ERR_LIMIT, "output dimension >= 32767");
+    if (row_begin < 0 || row_end > H || row_begin > row_end) return fail(ctx, P2P_ERR_INVALID, "row band outside [0, H]");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    for (int i = 0; i < n_views; ++i)
+        if (yaw_shift[i] < 0 || yaw_shift[i] >= s.Wp) return fail(ctx, P2P_ERR_INVALID, "yaw_shift outside [0, Wp)");
+    if (row_begin == row_end) return P2P_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t view_bytes = (size_t)W * H * 3;
+    uint8_t *d_out = out;
+    int rc;
+    if (!out_on_device) {
+        rc = ensure(ctx, &s.d_out, &s.out_cap, view_bytes * n_views);
+        if (rc) return rc;
+        d_out = s.d_out;
+    }
+    if (slot_is_partial(s)) {  // a slot filled by p2p_process_image holds only the rows its own views touch
+        if (ctx->opt_interp != 0)
+            return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama: exact interpolation needs a full upload");
+        std::vector<p2p_pitch_consts> uniq;
+        for (int i = 0; i < n_views; ++i) {
+            bool seen = false;
+            for (const p2p_pitch_consts &u : uniq) seen = seen || memcmp(&u, &pitch[i], sizeof(u)) == 0;
+            if (!seen) uniq.push_back(pitch[i]);
+        }
+        int lo = 0, hi = 0;
+        rc = view_row_range(ctx, s.stream, (int)uniq.size(), uniq.data(), W, H, s.Wp, s.Hp, &lo, &hi);
+        if (rc) return rc;
+        if (lo < s.row0 || hi + 1 > s.row1)
+            return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama that does not cover these views: upload it again");
+    }
+    if (rows_kernel_usable(ctx, W, H, n_views, d_out)) {
+        std::vector<int> oi((size_t)n_views);
+        for (int i = 0; i < n_views; ++i) oi[i] = i;
+        rc = launch_rows(ctx, s, n_views, yaw_shift, pitch, oi.data(), W, H, d_out, row_begin, row_end);
+        if (rc) return rc;
+    } else {
+        // geometries the row-segment kernel does not take (W % 8 != 0, LDG sampler, exact-bilinear mode ...): whole views,
+        // one generic launch each; the band is cut out by the copy below
+        Slot *sl[1] = {&s};
+        for (int i = 0; i < n_views; ++i) {
+            uint8_t *o[1] = {d_out + (size_t)i * view_bytes};
+            rc = launch_project(ctx, sl, 1, 1, &yaw_shift[i], 1, &pitch[i], W, H, o);
+            if (rc) return rc;
+        }
+    }
+    if (!out_on_device) {
+        const size_t off = (size_t)row_begin * W * 3, width = (size_t)(row_end - row_begin) * W * 3;
+        CK(cudaMemcpy2DAsync(out + off, view_bytes, d_out + off, view_bytes, width, (size_t)n_views,
+                             cudaMemcpyDeviceToHost, s.stream));
+    }
+    return P2P_OK;
+}
+
+// Replicate the panorama of src's slot into dst's slot (another device of the same box: one PCIe upload + NVLink peer
+// copies instead of one PCIe upload per GPU).  Asynchronous on the destination slot's stream, ordered after
+// everything enqueued on the source slot so far.
+int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
+    if (!dst || !src) return P2P_ERR_INVALID;
+    if (!slot_ok(dst, dst_slot) || !slot_ok(src, src_slot)) return fail(dst, P2P_ERR_INVALID, "bad slot");
+    if (dst == src && dst_slot == src_slot) return fail(dst, P2P_ERR_INVALID, "source and destination are the same slot");
+    std::unique_lock<std::mutex> l1(dst->mu, std::defer_lock), l2(src->mu, std::defer_lock);
+    if (dst == src) l1.lock(); else std::lock(l1, l2);
+    p2p_ctx *ctx = dst;  // CK reports on the destination context
+    Slot &a = src->slots[src_slot];
+    Slot &d = dst->slots[dst_slot];
+    if (!a.valid) return fail(dst, P2P_ERR_STATE, "source slot holds no panorama");
+    cudaEvent_t ev = nullptr;
+    CK(cudaSetDevice(src->device));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, a.stream);
+    if (e == cudaSuccess) e = cudaSetDevice(dst->device);
+    if (e == cudaSuccess && dst->device != src->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);  // direct NVLink path; staged through the host otherwise
+            if (pe != cudaSuccess) cudaGetLastError();                    // already enabled / not supported: the copy still works
+        }
+    }
+    int rc = P2P_OK;
+    if (e == cudaSuccess) rc = prepare_slot(dst, d, a.Wp, a.Hp);
+    if (e == cudaSuccess && rc == P2P_OK) e = cudaStreamWaitEvent(d.stream, ev, 0);
+    if (e == cudaSuccess && rc == P2P_OK) {
+        const size_t row_bytes = (size_t)a.pitch_tex * 4;
+        const size_t off = (size_t)a.row0 * row_bytes, bytes = (size_t)(a.row1 - a.row0 + 1) * row_bytes;
+        e = cudaMemcpyPeerAsync(reinterpret_cast<uint8_t *>(d.d_rgba) + off, dst->device,
+                                reinterpret_cast<const uint8_t *>(a.d_rgba) + off, src->device, bytes, d.stream);
+    }
+    cudaEventDestroy(ev);  // deferred by the runtime until the wait has consumed it
+    if (rc) return rc;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(dst, P2P_ERR_CUDA, "p2p_copy_pano", e);
+    }
+    d.valid = true;
+    d.row0 = a.row0;
+    d.row1 = a.row1;
+    d.tex_current = false;  // the gather array of the destination is refreshed from the linear copy before its next launch
     return P2P_OK;
 }
 

@@ -204,6 +204,35 @@ class Projector:
                                             n_pitch, pc, W, H, dst, on_dev))
         return out
 
+    def project_list(self, slot: int, shifts, consts, W: int, H: int, rows=None, out=None,
+                     out_device_ptr: int | None = None):
+        """Enqueue a flat list of views - view i = (shifts[i], consts[i]) - in one launch; ``rows = (begin, end)`` renders
+        only that band of output rows of every view (the multi-GPU split of a single image).  ``out``: host array
+        [n_views, H, W, 3] (created if None; only the band is written) or ``out_device_ptr``.  Valid after sync."""
+        shifts = np.ascontiguousarray(shifts, np.int32)
+        n = int(shifts.shape[0])
+        if len(consts) != n:
+            raise ValueError("one pitch-constant triple per view")
+        pc = self._consts_array(consts)
+        r0, r1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+        if out_device_ptr is not None:
+            dst, on_dev = C.c_void_p(out_device_ptr), 1
+        else:
+            if out is None:
+                out = np.empty((n, H, W, 3), np.uint8)
+            if out.dtype != np.uint8 or not out.flags.c_contiguous or out.size != n * H * W * 3:
+                raise ValueError("out must be C-contiguous uint8 with n_views * H * W * 3 elements")
+            dst, on_dev = out.ctypes.data, 0
+        self._ck(self.lib.p2p_project_view_list(self.ctx, slot, n, shifts.ctypes.data_as(C.POINTER(C.c_int32)), pc, W, H,
+                                                r0, r1, dst, on_dev))
+        return out
+
+    def copy_pano_from(self, slot: int, src: "Projector", src_slot: int):
+        """Replicate the panorama of ``src``'s slot (another device's context) into ``slot`` over NVLink / PCIe peer copy;
+        asynchronous on this slot's stream, ordered after the source slot's enqueued work."""
+        rc = self.lib.p2p_copy_pano(self.ctx, slot, src.ctx, src_slot)
+        self._ck(rc)
+
     def batch_call(self, slots, shifts, consts, W: int, H: int, out_ptrs, on_device: bool = True):
         """Prebuilt ``p2p_project_batch`` call for resident panoramas: returns a zero-argument
         callable that enqueues one launch per slot (arguments are marshalled once)."""

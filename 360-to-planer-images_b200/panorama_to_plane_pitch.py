@@ -44,6 +44,7 @@ pitch_mapping_cache: dict = {}  # (W, H, pitch, pano_width, pano_height, fov) ->
 _projectors: dict = {}
 _projectors_lock = threading.Lock()
 _default_device = 0
+_default_devices: list | None = None   # several devices: every single image is split over them (set_devices)
 
 
 def get_version():
@@ -54,6 +55,18 @@ def set_device(device: int):
     """Select the CUDA device the module-level entry points use (default 0)."""
     global _default_device
     _default_device = int(device)
+
+
+def set_devices(devices):
+    """Split every image the module-level entry points process over these CUDA devices of one box (None / one device:
+    off).  The panorama is uploaded (or decoded) once and replicated with peer copies; pixel outputs are split by output
+    row bands, encoded outputs by whole views (the reference's unit of parallelism is the yaw task of its
+    thread pool, ref :251-265).  Results are identical to the single-device path."""
+    global _default_devices
+    devs = [int(d) for d in devices] if devices else None
+    _default_devices = devs if devs and len(devs) > 1 else None
+    if devs and len(devs) == 1:
+        set_device(devs[0])
 
 
 def get_projector(device: int | None = None) -> _engine.Projector:
@@ -138,10 +151,14 @@ def _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_de
     return consts, tables
 
 
-def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg):
-    """[n_yaw][n_pitch] views through the batched device path, using the module caches."""
+def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, devices=None):
+    """[n_yaw][n_pitch] views through the batched device path, using the module caches.  ``devices`` (default: the list
+    given to ``set_devices``): split this one image over several GPUs."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    devs = _split_devices(devices, tables, yaw_angles, pitch_angles)
+    if devs:
+        return _project_split(devs, src, consts, tables, yaw_angles, pitch_angles, output_width, output_height)
     if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
         try:  # decode on the device straight into a slot, project from there
             with proj.slots(1) as (s,):
@@ -154,6 +171,89 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
                 raise
     return proj.project_image(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height, fov_deg,
                               consts=consts, tables=tables)
+
+
+def _split_upload(projs, src, stack):
+    """One slot per device, the panorama in all of them: uploaded (or JPEG-decoded) on the first device, replicated to
+    the others with peer copies (NVLink) ordered after it on the device.  Returns the slots."""
+    slots = [stack.enter_context(pr.slots(1))[0] for pr in projs]
+    p0, s0 = projs[0], slots[0]
+    pano = src
+    if isinstance(src, _JpegSource):
+        try:
+            p0.upload_jpeg(s0, src.data)
+            pano = None
+        except _engine.P2PError as e:
+            if e.code != -6:
+                raise
+            pano = _decode_source(p0, src, slot=s0)
+    if pano is not None:
+        stack.callback(lambda keep=p0.upload(s0, pano): None)  # the host array outlives the asynchronous copy
+    for pr, sl in zip(projs[1:], slots[1:]):
+        pr.copy_pano_from(sl, p0, s0)
+    return slots
+
+
+def _project_split(devices, src, consts, tables, yaw_angles, pitch_angles, W, H):
+    """[n_yaw][n_pitch] views of ONE image rendered by several GPUs: device r renders the row band
+    ``shard.shard_rows(H, r, n)`` of every view straight into the shared result array (one host thread per device)."""
+    from . import shard
+
+    projs = [get_projector(d) for d in devices]
+    n = len(projs)
+    n_y, n_p = len(yaw_angles), len(pitch_angles)
+    out = np.empty((n_y, n_p, H, W, 3), np.uint8)
+    flat_shifts = [tables[k][2] for k in range(n_y) for _ in range(n_p)]
+    flat_consts = [consts[j] for _ in range(n_y) for j in range(n_p)]
+    with contextlib.ExitStack() as stack:
+        slots = _split_upload(projs, src, stack)
+
+        def run(r):
+            rows = shard.shard_rows(H, r, n)
+            if rows[0] < rows[1]:
+                projs[r].project_list(slots[r], flat_shifts, flat_consts, W, H, rows=rows, out=out.reshape(-1, H, W, 3))
+            projs[r].sync(slots[r])
+
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            list(ex.map(run, range(n)))
+    return out
+
+
+def _project_files_split(devices, fmt, src, consts, tables, yaw_angles, pitch_angles, W, H):
+    """[n_yaw][n_pitch] encoded files (bytes) of ONE image from several GPUs: the encoders need whole views, so the
+    pitch-major view list is cut into contiguous runs (``shard.shard_views``) and every device projects + encodes its run,
+    one call per pitch it holds (``shard.group_by_pitch``)."""
+    from . import shard
+
+    projs = [get_projector(d) for d in devices]
+    n = len(projs)
+    n_y, n_p = len(yaw_angles), len(pitch_angles)
+    files = [[None] * n_p for _ in range(n_y)]
+    with contextlib.ExitStack() as stack:
+        slots = _split_upload(projs, src, stack)
+
+        def run(r):
+            for j, ks in shard.group_by_pitch(shard.shard_views(n_y, n_p, r, n)).items():
+                shifts = [tables[k][2] for k in ks]
+                if fmt == "png":
+                    got = projs[r].process_image_png(slots[r], None, shifts, [consts[j]], W, H, want_pixels=False)[0]
+                else:
+                    got = projs[r].project_jpeg(slots[r], shifts, [consts[j]], W, H)
+                for k, f in zip(ks, got):
+                    files[k][j] = f
+            projs[r].sync(slots[r])
+
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            list(ex.map(run, range(n)))
+    return files
+
+
+def _split_devices(devices, tables, yaw_angles, pitch_angles):
+    """The device list if this call is to be split over several GPUs (integer-roll yaws only), else None."""
+    devs = _default_devices if devices is None else ([int(d) for d in devices] if devices else None)
+    if not devs or len(devs) < 2 or not yaw_angles or not pitch_angles:
+        return None
+    return devs if all(t[2] is not None for t in tables) else None
 
 
 def _is_jpeg(output_format) -> bool:
@@ -172,11 +272,15 @@ def _slot(proj, lease):
     return contextlib.nullcontext((s,))
 
 
-def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None):
+def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None,
+                  devices=None):
     """[n_yaw][n_pitch] JPEG files (bytes; with a ``lease`` zero-copy views of the slot's file buffer, see ``_slot``) through
     the device projection + encoder, using the module caches."""
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
+    devs = _split_devices(devices, tables, yaw_angles, pitch_angles)
+    if devs:
+        return _project_files_split(devs, "jpg", src, consts, tables, yaw_angles, pitch_angles, output_width, output_height)
     if yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
         shifts = [t[2] for t in tables]
         with _slot(proj, lease) as (s,):
@@ -199,7 +303,8 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
                                    fov_deg, consts=consts, tables=tables)
 
 
-def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None):
+def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, output_height, fov_deg, lease=None,
+                 devices=None):
     """([n_yaw][n_pitch] PNG files (bytes; with a ``lease`` zero-copy views of the slot's file buffer, see ``_slot``) or
     None, views or None): projection and PNG encoder on the device.  A None file
     is a view the device encoder did not handle (the ABI's ``sizes[i] = 0``; not produced any more): ``views`` then holds the pixels
@@ -207,6 +312,13 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
     src = pano_image if isinstance(pano_image, _JpegSource) else _engine._as_u8_image(pano_image, "pano_image")
     consts, tables = _geometry(src, yaw_angles, pitch_angles, output_width, output_height, fov_deg)
     n_p = len(pitch_angles)
+    devs = _split_devices(devices, tables, yaw_angles, pitch_angles)
+    if devs:
+        files = _project_files_split(devs, "png", src, consts, tables, yaw_angles, pitch_angles, output_width, output_height)
+        views = None
+        if any(f is None for per_yaw in files for f in per_yaw):  # (the device encoder handles every image today)
+            views = _project_split(devs, src, consts, tables, yaw_angles, pitch_angles, output_width, output_height)
+        return files, views
     if yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
         shifts = [t[2] for t in tables]
         with _slot(proj, lease) as (s,):
@@ -287,13 +399,14 @@ def panorama_to_plane(path, FOV, output_size, yaw, pitch):
 
 
 def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles, output_width,
-                         output_height, num_workers=4, output_format="png", fov_deg=90):
+                         output_height, num_workers=4, output_format="png", fov_deg=90, devices=None):
     """Read one image, project every yaw x pitch view, save the results (ref :227-280).
 
     The reference submits one thread-pool task per yaw; here all views come from one batched
     device call and ``num_workers`` threads only run the file encoders.  Output names are the
     reference's (ref :275).  An unreadable image is logged and skipped (ref :245-247); a failure
     while saving one yaw's results is logged and the other yaws continue (ref :279-280).
+    ``devices`` (extra): split this one image over several GPUs (same files, see ``set_devices``).
     """
     import cv2
 
@@ -314,13 +427,13 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
         try:
             if jpeg:  # projected and encoded on the device: only the files come back
                 files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
-                                      output_height, fov_deg, lease=lease)
+                                      output_height, fov_deg, lease=lease, devices=devices)
             elif png:
                 files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
-                                            output_height, fov_deg, lease=lease)
+                                            output_height, fov_deg, lease=lease, devices=devices)
             else:
                 views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
-                                 fov_deg)
+                                 fov_deg, devices=devices)
         except Exception as e:
             for yaw_angle in yaw_angles:
                 logging.error(f"Error processing yaw_angle {yaw_angle}: {e}")
@@ -412,14 +525,14 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
                 return
             try:
                 if jpeg_out:
-                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease)
+                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease, devices=[])
                     futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
                 elif str(output_format).lower() == "png":
-                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease)
+                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease, devices=[])
                     futs = _save_png(cv2, files_, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
                                      writers)
                 else:
-                    views = _project(proj, src, yaw_angles, pitch_angles, W, H, fov_deg)
+                    views = _project(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, devices=[])
                     futs = _save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
                                        writers)
             except Exception as e:
@@ -474,11 +587,12 @@ def main(input_path, output_path, yaw_angles, pitch_angles, output_width, output
         logging.info(f"Found {len(all_images)} images in folder: {input_path_obj}")
     else:
         all_images = [input_path_obj]
-    if len(all_images) == 1 and not devices:
+    if len(all_images) == 1:
+        # one image: its views are split over the devices (row bands / view runs), SURVEY 8e
         process_single_image(
             input_image_path=all_images[0], output_dir=output_dir, yaw_angles=yaw_angles,
             pitch_angles=pitch_angles, output_width=output_width, output_height=output_height,
-            num_workers=num_workers, output_format=output_format, fov_deg=fov_deg,
+            num_workers=num_workers, output_format=output_format, fov_deg=fov_deg, devices=devices,
         )
     else:
         process_image_batch(all_images, output_dir, yaw_angles, pitch_angles, output_width, output_height,
@@ -518,7 +632,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--enable_file_logging", action="store_true", help="Enable logging to a file.")
     p.add_argument("--device", type=int, default=0, help="CUDA device index (extra flag; default 0)")
     p.add_argument("--devices", type=int, nargs="+", default=None,
-                   help="several CUDA devices: the files of a folder are sharded round-robin (extra flag)")
+                   help="several CUDA devices: the files of a folder are sharded round-robin, a single image is split "
+                        "by output row bands / views (extra flag)")
     p.add_argument("-v", "--version", action="version", version=f"%(prog)s {get_version()}",
                    help="Show version information")
     return p

@@ -29,6 +29,19 @@ def shard_views(n_yaw: int, n_pitch: int, rank: int, world: int) -> list:
     return flat[lo:hi]
 
 
+def shard_rows(height: int, rank: int, world: int, align: int = 8) -> tuple:
+    """(row_begin, row_end) of ``rank`` when ONE image is split over ``world`` GPUs by output row bands: every GPU renders
+    the same rows of every view, so twelve views balance over eight GPUs (by whole views they would split 2,2,2,2,1,1,1,1,
+    SURVEY 8e).  Bands are multiples of ``align`` rows (the kernel's CTA tile height) except the last one; they cover
+    [0, height) exactly once and may be empty when there are more ranks than tiles."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    tiles = (height + align - 1) // align
+    lo = min(height, ((tiles * rank) // world) * align)
+    hi = min(height, ((tiles * (rank + 1)) // world) * align)
+    return lo, hi
+
+
 def group_by_pitch(views: list) -> dict:
     """{pitch_index: [yaw_index, ...]} preserving order: one launch group per pitch."""
     out: dict = {}

@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - plain C types only; all functions return 0 (P2P_OK) or a negative p2p_status;
- *     p2p_last_error(ctx) returns a human readable message for the last failure on ctx.
+ *     p2p_last_error(ctx) returns a human readable message for the calling thread's last failure on ctx
+ *     (kept per thread, like errno; valid until that thread's next failing call).
  *   - images are 8-bit, 3 channels, interleaved, channel order preserved (the reference keeps
  *     cv2's BGR end to end, ref :244; channels are independent in the arithmetic).
  *   - the caller owns every host buffer; the library owns device memory inside the context.
@@ -58,9 +59,11 @@ typedef enum p2p_option {
     P2P_OPT_COUNT_LAUNCHES = 3,  /* read-only via p2p_get_option: kernels launched so far */
     P2P_OPT_IMAGES_PER_LAUNCH = 4, /* 1 (default), 2 or 4 resident panoramas share one launch (and one
                                      coordinate evaluation) in p2p_project_batch */
-    P2P_OPT_MIRROR = 5            /* 1 (default): with the texture sampler and W % 8 == 0, the pixel pair
-                                     (W/2 + t, W/2 - t) shares one coordinate evaluation; 0: every pixel
-                                     evaluates its own */
+    P2P_OPT_MIRROR = 5            /* with the texture sampler and W % 8 == 0 the pixel pair (W/2 + t, W/2 - t) shares
+                                     one coordinate evaluation.  2 (default): row-segment kernel - a warp walks a
+                                     row segment, every output byte leaves in a packed 32-bit store, any flat view
+                                     list is one launch; 1: the round-1 pair kernel (byte stores for the mirrored
+                                     half, one launch per pitch-list chunk); 0: every pixel evaluates its own */
     ,P2P_OPT_INTERP = 6            /* 0 (default): cv2.remap fixed-point bilinear, the reference's arithmetic
                                      (ref :192-199, :212-218); 1: exact bilinear - un-quantised fractions with the
                                      arithmetic of scipy.ndimage.map_coordinates(order=1) (double precision, round
@@ -72,6 +75,7 @@ typedef enum p2p_option {
                                      subsequences, restart intervals as independent scans); the library's host decoder
                                      takes over when that does not converge; 0: always the host decoder */
     ,P2P_OPT_GPU_HUFFMAN_COUNT = 10 /* read-only: JPEG inputs whose Huffman stage ran on the device so far */
+    ,P2P_OPT_SEG_CHUNKS = 11       /* row-segment kernel: chunks of 32 pixel pairs per warp (default 4, 1..64) */
     ,P2P_OPT_PARTIAL_UPLOAD = 8    /* 1 (default): p2p_process_image copies only the panorama rows its views can
                                      touch (p2p_view_row_range) over PCIe; 0: always the whole panorama */
 
@@ -134,6 +138,24 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
 int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
                       int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
                       int out_on_device);
+
+/* A flat list of views in one launch, optionally only a band of output rows: view i = (yaw_shift[i], pitch[i]) is written
+ * to out + i * W * H * 3 (rows row_begin .. row_end - 1 of it; the other rows of `out` are not touched).  This is the
+ * unit the reference parallelises over (one (yaw, pitch) pair of the nested loops at ref :202-219 / :253-265) without the
+ * yaw x pitch product structure of p2p_project_views: the six cube faces of BASELINE configs[4] - four yaws at pitch 90
+ * plus the two pole pitches - are one call and one kernel launch.  Views whose pitch constants are bit-identical share one
+ * coordinate evaluation (the reference's pitch_mapping_cache key has no yaw, ref :55-73).  The row band is how one image
+ * is split over several GPUs: every device renders rows [H r / n, H (r + 1) / n) of all views into the same
+ * host array.  out_on_device as in p2p_project_views (a host `out` receives only the band, one strided copy). */
+int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *yaw_shift, const p2p_pitch_consts *pitch,
+                          int W, int H, int row_begin, int row_end, uint8_t *out, int out_on_device);
+
+/* Replicate the (possibly partial) panorama held by src's slot into dst's slot; the two contexts may live on different
+ * devices of one box (cudaMemcpyPeerAsync: NVLink when peer access is available, staged by the driver otherwise) - one
+ * PCIe upload plus peer copies instead of one upload per GPU when a single image is split over GPUs.
+ * Asynchronous on the destination slot's stream and ordered after the work enqueued on the source slot; keep the source
+ * slot unchanged until the destination slot has been synchronised. */
+int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot);
 
 /* upload + project + readback of one image in one call (all asynchronous on the slot stream).
  * Because the views are known before the transfer, only the panorama rows they can touch are copied to the

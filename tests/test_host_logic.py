@@ -146,6 +146,18 @@ def test_sharding(pkg):
         sizes = [len(shard.shard_views(ny, npitch, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
     assert shard.group_by_pitch([(0, 1), (1, 1), (0, 2)]) == {1: [0, 1], 2: [0]}
+    # row bands of one image split over GPUs: disjoint, in order, cover [0, H), tile-aligned except the last edge
+    for H in (1, 7, 8, 9, 270, 1080, 2160):
+        for world in (1, 2, 3, 4, 8, 16):
+            bands = [shard.shard_rows(H, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == H
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(lo % 8 == 0 for lo, _ in bands if lo < H)
+            sizes = [hi - lo for lo, hi in bands]
+            assert max(sizes) - min(sizes) <= 8 + 7
+    with pytest.raises(ValueError):
+        shard.shard_rows(8, 2, 2)
     with pytest.raises(ValueError):
         shard.shard_images(4, 2, 2)
 

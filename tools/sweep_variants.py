@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--warp-ws", type=int, nargs="+", default=[32, 8])
     ap.add_argument("--nys", type=int, nargs="+", default=[4])
     ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
-    ap.add_argument("--mirrors", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--mirrors", type=int, nargs="+", default=[0, 1, 2])
+    ap.add_argument("--seg-chunks", type=int, nargs="+", default=[4], help="row-segment kernel (mirror 2): chunks per warp")
+    ap.add_argument("--tag", default="", help="free-form label copied into every line (e.g. the build variant)")
     ap.add_argument("--fov", type=int, default=None, help="override the FOV (locality experiments)")
     args = ap.parse_args()
     import torch
@@ -57,10 +59,12 @@ def main():
         for ww in args.warp_ws:
           for ny in args.nys:
            for nb in args.nbs:
-            for mirror in args.mirrors:
+            for mirror, segc in [(m, sc) for m in args.mirrors for sc in (args.seg_chunks if m == 2 else [0])]:
                 if mirror and (sampler != 1 or nb != 1):
                     continue
                 proj.set_option(L.OPT_MIRROR, mirror)
+                if mirror == 2:
+                    proj.set_option(L.OPT_SEG_CHUNKS, segc)
                 proj.set_option(L.OPT_SAMPLER, sampler)
                 proj.set_option(L.OPT_WARP_W, ww)
                 proj.set_option(L.OPT_YAWS_PER_THREAD, ny)
@@ -75,12 +79,14 @@ def main():
                 proj.sync(0)
                 ms = proj.elapsed_ms(ev0, ev1) / (args.steps * args.batch)
                 torch.cuda.synchronize()
-                chk = int(d_out[0].to(torch.int64).sum().item())
-                ref = chk if ref is None else ref  # (the mirror kernel legitimately differs in a few pixels)
-                print(json.dumps({"sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "mirror": mirror, "image_us": ms * 1e3,
+                cur = d_out[0].clone()
+                same = True if ref is None else bool(torch.equal(cur, ref))
+                ref = cur if ref is None else ref  # every variant must produce the same bytes (bit-exact default mode)
+                print(json.dumps({"tag": args.tag, "sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "mirror": mirror,
+                                  "seg_chunks": segc, "image_us": ms * 1e3,
                                   "gpix_s": bench.PX_PER_IMAGE / (ms * 1e-3) / 1e9,
                                   "roofline_frac": bench.B_ALG_PER_IMAGE / (ms * 1e-3) / 1e9 / bench.read_peaks()[0],
-                                  "same_output": chk == ref}), flush=True)
+                                  "same_output": same}), flush=True)
     proj.close()
 
 
