@@ -68,6 +68,7 @@ SIGNATURES = {
     "p2p_event_create": (_i, [_vp, C.POINTER(_vp)]),
     "p2p_event_destroy": (_i, [_vp, _vp]),
     "p2p_event_record": (_i, [_vp, _vp, _i]),
+    "p2p_event_wait": (_i, [_vp, _vp, _i]),
     "p2p_event_elapsed_ms": (_i, [_vp, _vp, _vp, _f32p]),
     "p2p_flush_l2": (_i, [_vp, _i, _sz]),
     "p2p_selftest": (_i, [_vp, _pcp, _i, _i, _i, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),

@@ -1942,6 +1942,14 @@ int p2p_event_record(p2p_ctx *ctx, void *event, int slot) {
     return P2P_OK;
 }
 
+int p2p_event_wait(p2p_ctx *ctx, void *event, int slot) {
+    if (!slot_ok(ctx, slot) || !event) return fail(ctx, P2P_ERR_INVALID, "bad slot or null event");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamWaitEvent(ctx->slots[slot].stream, static_cast<cudaEvent_t>(event), 0));
+    return P2P_OK;
+}
+
 int p2p_event_elapsed_ms(p2p_ctx *ctx, void *start, void *stop, float *ms) {
     if (!ctx || !start || !stop || !ms) return P2P_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);

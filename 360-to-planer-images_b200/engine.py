@@ -485,6 +485,10 @@ class Projector:
     def record(self, ev, slot: int):
         self._ck(self.lib.p2p_event_record(self.ctx, ev, slot))
 
+    def event_wait(self, ev, slot: int):
+        """Work enqueued on ``slot`` from now on waits for ``ev`` (fork / join of slot streams)."""
+        self._ck(self.lib.p2p_event_wait(self.ctx, ev, slot))
+
     def elapsed_ms(self, start, stop) -> float:
         ms = C.c_float()
         self._ck(self.lib.p2p_event_elapsed_ms(self.ctx, start, stop, C.byref(ms)))

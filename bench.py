@@ -19,12 +19,19 @@ e2e      the same metric through the public API with HOST buffers: every image i
          (74.6 MB) inside the timed region, pipelined over the context's slots (streams).
 roofline HBM: algorithmic bytes per launch (3 * sum(W*H) + 3 * N_T = 141,009,384 B for
          one 12-view image) / average launch duration, against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline  oracle/ref_port.py (NumPy + cv2.remap restatement of the reference, same thread
-         fan-out) timed on this box's host cores on a bounded sample, N = 1 only.
+cpu_baseline  the reference's own script (baseline/_ref/app/panorama_to_plane-pitch.py, a git-ignored copy made by
+         __graft_entry__.build(); kind "reference") under its own thread fan-out, or - when that copy is absent -
+         oracle/ref_port.py (kind "port"), timed on this box's host cores on a bounded sample, N = 1 only.
+e2e.frac_of_transfer_ceiling   time of the bare page-locked copies of the same bytes (no kernels, every rank at once)
+         / time of the e2e step: how close the pipeline is to what PCIe and host memory give N GPUs.
+e2e_files  JPEG file in -> 12 JPEG files out per image (8.6 MB instead of 150 MB over PCIe), every rank, aggregate.
+parity   every rank renders one view of one of ITS OWN seeds and compares it with the CPU oracle outside the timed
+         regions (bit-exact when the host's NumPy takes the SVML path the kernel restates, else >= 96 % of pixels).
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -65,7 +72,7 @@ def workload_config(extra=None):
     }
     if extra:
         cfg.update(extra)
-    return cfg
+    return cfg   # the same dict in both arms (kernel variant keys live in the line's "variant")
 
 
 def read_peaks():
@@ -155,38 +162,74 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU reference arm / baseline (oracle port of the reference, timed on the host cores)
+# CPU reference arm / baseline: the reference's own script when its git-ignored copy travelled with the
+# snapshot (baseline/_ref, made by __graft_entry__.build() where /root/reference exists), else the oracle port
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, budget_s: float | None = None):
-    """Times oracle.ref_port (NumPy + cv2.remap, ThreadPoolExecutor per yaw, like the reference)
-    on one README-example image per step with warm map caches (steady state over a directory of
-    same-sized images, ref :42-73).  Returns (Mpix/s, ms_per_step, steps_done, info)."""
-    import cv2
+REF_SCRIPT = ROOT / "baseline" / "_ref" / "app" / "panorama_to_plane-pitch.py"
 
-    from oracle import ref_port
+
+def load_reference_script():
+    """The UNMODIFIED reference module imported by path (its file name has a hyphen), or None."""
+    if not REF_SCRIPT.exists():
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("ref_panorama_to_plane_pitch", REF_SCRIPT)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception as e:  # noqa: BLE001 - a missing dependency of the script: fall back to the port
+        print(f"reference script not importable ({e}); timing the oracle port instead", file=sys.stderr)
+        return None
+
+
+def cpu_reference_run(steps: int, warmup: int, budget_s: float | None = None):
+    """One README-example image (12 views) per step on the host cores with warm map caches - the steady state over a
+    directory of same-sized images (ref :42-73) - after one cold image that builds the maps.  The fan-out is the
+    reference's: ThreadPoolExecutor(max_workers = int(0.9 * cores)) (ref :304-306), one process_yaw_and_pitchs task
+    per yaw (ref :252-265), results collected in submit order (:268-272).  Returns (Mpix/s, ms_per_step, steps, info)."""
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+
     from tools import synth_inputs as synth
 
     pano = synth.noise(WP, HP, 0)
-    ref_port.clear_caches()
-    workers = ref_port.default_workers()
+    workers = max(1, int((os.cpu_count() or 1) * 0.9))
+    ref = load_reference_script()
+    if ref is not None:
+        kind = "reference"
+
+        def one_image():
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                futs = [ex.submit(ref.process_yaw_and_pitchs, pano, y, PITCHES, W, H, FOV) for y in YAWS]
+                return [f.result() for f in futs]
+    else:
+        from oracle import ref_port
+
+        kind = "port"
+        ref_port.clear_caches()
+
+        def one_image():
+            return ref_port.process_image_views(pano, YAWS, PITCHES, W, H, FOV, num_workers=workers)
+
     t0 = time.perf_counter()
-    ref_port.process_image_views(pano, YAWS, PITCHES, W, H, FOV, num_workers=workers)  # cold: builds the maps
+    one_image()  # cold: builds the yaw / pitch maps
     cold_s = time.perf_counter() - t0
     for _ in range(max(0, warmup - 1)):
-        ref_port.process_image_views(pano, YAWS, PITCHES, W, H, FOV, num_workers=workers)
+        one_image()
     done = 0
     t0 = time.perf_counter()
     for _ in range(steps):
-        ref_port.process_image_views(pano, YAWS, PITCHES, W, H, FOV, num_workers=workers)
+        one_image()
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     el = time.perf_counter() - t0
     info = {
         "cores": os.cpu_count() or 1,
-        "kind": "port",
-        "sample": f"{done} README-example images (12 views 8192x4096 -> 1920x1080) with warm map caches after 1 cold "
-                  f"image ({cold_s:.2f} s incl. map precompute = {PX_PER_IMAGE / cold_s / 1e6:.1f} Mpix/s cold); "
+        "kind": kind,
+        "sample": f"{done} README-example images (12 views 8192x4096 -> 1920x1080), one image per step, with warm map "
+                  f"caches after 1 cold image ({cold_s:.2f} s incl. map precompute = {PX_PER_IMAGE / cold_s / 1e6:.1f} Mpix/s "
+                  f"cold); {'the unmodified reference script baseline/_ref/app/panorama_to_plane-pitch.py' if kind == 'reference' else 'oracle/ref_port.py'}, "
                   f"ThreadPoolExecutor({workers}) one task per yaw, cv2 threads {cv2.getNumThreads()}, "
                   f"numpy {np.__version__}, cv2 {cv2.__version__}",
         "cold_mpix_s": PX_PER_IMAGE / cold_s / 1e6,
@@ -203,7 +246,7 @@ def run_reference_arm(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": workload_config({"step": "one image (12 views) per step: bounded sample of the 32-image batch"}),
+        "config": workload_config(),
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -247,7 +290,15 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     # ---- resident inputs: BATCH packed panoramas per GPU (seeds follow configs[2]: rank-major) ----
     res_slots = list(range(BATCH))
-    proj.share_stream(res_slots, 0)  # one launching stream so a single event pair brackets the steps
+    # The 32 images of a step are independent launches: they alternate over n_streams launching streams (slot i on the
+    # stream of slot i % n_streams), so the tail of one image's grid overlaps the ramp-up of the next one's - with a single
+    # stream every launch pays its own tail and launch gap (58 vs 65-68 us per image).  Two launches are in flight at
+    # most, so the L2 still holds one image's cross-view working set most of the time.  The timed region is bracketed by
+    # ONE event pair on stream 0: the other streams wait for the start event, stream 0 waits for their end events.
+    n_streams = max(1, min(args.streams, BATCH))
+    for i in res_slots:
+        if i >= n_streams:
+            proj.set_stream(i, proj.get_stream(i % n_streams))
     n_distinct = min(BATCH, args.distinct)
     host = [synth.noise(WP, HP, rank * BATCH + i) for i in range(n_distinct)]
     d_stage = torch.empty((HP, WP, 3), dtype=torch.uint8, device=dev)
@@ -267,22 +318,42 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     for _ in range(max(3, args.warmup)):
         resident_step()
-    proj.sync(0)
+    proj.sync(-1)
     ev0, ev1 = proj.event(), proj.event()
+    ev_join = [proj.event() for _ in range(n_streams)]
+
+    def timed_steps(n_steps):
+        """Device time of n_steps steps over all launching streams (fork / join through events on stream 0)."""
+        proj.record(ev0, 0)
+        for st in range(1, n_streams):
+            proj.event_wait(ev0, st)
+        for _ in range(n_steps):
+            resident_step()
+        for st in range(1, n_streams):
+            proj.record(ev_join[st], st)
+            proj.event_wait(ev_join[st], 0)
+        proj.record(ev1, 0)
+        proj.sync(-1)
+        return proj.elapsed_ms(ev0, ev1)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = proj.launches
     barrier()
     torch.cuda.synchronize()
-    proj.record(ev0, 0)
-    for _ in range(args.steps):
-        resident_step()
-    proj.record(ev1, 0)
-    proj.sync(0)
+    ms_local = timed_steps(args.steps)
     torch.cuda.synchronize()
     barrier()
-    ms_total = max_over_ranks(proj.elapsed_ms(ev0, ev1))
+    ms_total = max_over_ranks(ms_local)
     launches = proj.launches - launches0
+    # the same launches strictly one after the other on one stream (what a single ncu-serialised launch costs)
+    serial_ms = None
+    if n_streams > 1:
+        for i in res_slots[1:]:
+            proj.set_stream(i, proj.get_stream(0))
+        ns, n_streams = n_streams, 1
+        timed_steps(1)
+        serial_ms = timed_steps(min(5, args.steps)) / (min(5, args.steps) * BATCH)
+        n_streams = ns
     ms_per_step = ms_total / args.steps
     value = world * args.steps * BATCH * PX_PER_IMAGE / (ms_total * 1e-3) / 1e6
     launch_ms = ms_total / (args.steps * BATCH)
@@ -301,22 +372,26 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             proj.sync(s)  # the slot's previous image (and its readback) is complete
             proj.process_image(s, pin_in[i % n_host].array, shifts, consts, W, H, pin_out[i % n_e2e_slots].array)
 
+    def time_e2e(n_steps):
+        for _ in range(2):
+            e2e_step()
+        proj.sync(-1)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            e2e_step()
+        proj.sync(-1)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return sec
+
     # the library transfers only the panorama rows these views can touch (p2p_view_row_range)
     row_first, row_last = proj.view_row_range(consts, W, H, WP, HP)
     h2d_per_image = (row_last - row_first + 1) * WP * 3 if proj.get_option(L.OPT_PARTIAL_UPLOAD) else H2D_PER_IMAGE
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        e2e_step()
-    proj.sync(-1)
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    proj.sync(-1)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    e2e_s = time_e2e(e2e_steps)
     e2e_value = world * e2e_steps * BATCH * PX_PER_IMAGE / e2e_s / 1e6
     clocks = sampler.stop() if sampler is not None else None
 
@@ -324,39 +399,71 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     check = proj.project_image(pin_in[(BATCH - 1) % n_host].array, YAWS, PITCHES, W, H, FOV)
     assert np.array_equal(check, pin_out[(BATCH - 1) % n_e2e_slots].array), "e2e readback differs from resident render"
 
+    # the same pipeline moving the WHOLE panorama (no knowledge of the view set used): secondary figure
+    e2e_full = None
+    if proj.get_option(L.OPT_PARTIAL_UPLOAD) and not args.no_extras:
+        proj.set_option(L.OPT_PARTIAL_UPLOAD, 0)
+        n_full = max(1, min(2, e2e_steps))
+        full_s = time_e2e(n_full)
+        proj.set_option(L.OPT_PARTIAL_UPLOAD, 1)
+        e2e_full = {"value": world * n_full * BATCH * PX_PER_IMAGE / full_s / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": BATCH * H2D_PER_IMAGE, "ms_per_step": full_s / n_full * 1e3, "steps": n_full}
+
+    # transfer ceiling: the bare page-locked copies of one e2e step (same buffers, same byte counts, two streams, no
+    # kernels), every rank at the same time
+    ceil_s = transfer_ceiling(torch, dev, pin_in, pin_out, h2d_per_image, D2H_PER_IMAGE, barrier, max_over_ranks)
+
+    # ---- parity of THIS rank's own data against the CPU oracle (outside every timed region) ----
+    parity = oracle_check(proj, host[0], rank * BATCH)
+    parity_ranks = int(round(ranks.sum(1.0 if parity["ok"] else 0.0)))
+
+    # ---- files flow at every N: JPEG file in, 12 JPEG files out, only files cross PCIe ----
+    e2e_files = None
+    if not args.no_extras:
+        e2e_files = files_flow(pkg, proj, synth.smooth(WP, HP, rank), shifts, consts, "jpg", world, barrier, max_over_ranks)
+
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = files_extras(pkg, proj, synth.smooth(WP, HP, 0), shifts, consts)
+        extras["configs"] = config_fractions(pkg, proj, synth, torch)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, _ms, done, info = cpu_reference_run(10_000, 1, budget_s=args.cpu_seconds)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
     elif rank == 0:
-        cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1,
+                        "kind": "reference" if REF_SCRIPT.exists() else "port",
                         "sample": "not run (N > 1 or --no-cpu-baseline); see the N = 1 line"}
 
     if rank == 0:
         peak, peak_src = read_peaks()
         achieved = B_ALG_PER_IMAGE / (launch_ms * 1e-3) / 1e9
+        mirror = proj.get_option(L.OPT_MIRROR)
+        kernel = {2: "p2p::project_rows_kernel<4, true, true>", 1: "p2p::project_mirror_kernel<4, true>"}.get(
+            mirror if proj.get_option(L.OPT_SAMPLER) == 1 and proj.get_option(L.OPT_IMAGES_PER_LAUNCH) == 1 else 0,
+            "p2p::project_kernel")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config({
+            "config": workload_config(),
+            "variant": {
                 "sampler": proj.get_option(L.OPT_SAMPLER), "warp_w": proj.get_option(L.OPT_WARP_W),
                 "yaws_per_thread": proj.get_option(L.OPT_YAWS_PER_THREAD),
                 "images_per_launch": proj.get_option(L.OPT_IMAGES_PER_LAUNCH),
-                "mirror_pairs": proj.get_option(L.OPT_MIRROR),
-                "distinct_seeds_per_gpu": n_distinct,
-            }),
+                "mirror_pairs": mirror, "seg_chunks": proj.get_option(L.OPT_SEG_CHUNKS),
+                "trig": "numpy_exact_svml" if proj.get_option(L.OPT_TRIG) == 0 else "minimax",
+                "distinct_seeds_per_gpu": n_distinct, "launching_streams": n_streams,
+            },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": read_traffic(), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": B_ALG_PER_IMAGE, "launch_ms": launch_ms,
-                "kernel": ("p2p::project_mirror_kernel<4>" if (proj.get_option(L.OPT_MIRROR) and proj.get_option(L.OPT_SAMPLER) == 1
-                                                              and proj.get_option(L.OPT_IMAGES_PER_LAUNCH) == 1)
-                           else "p2p::project_kernel") + " (one launch = one image = 12 views)",
+                "launch_ms_note": f"timed region / launches with the images alternating over {n_streams} launching stream(s)",
+                "serialized_launch_ms": serial_ms,
+                "serialized_frac": (B_ALG_PER_IMAGE / (serial_ms * 1e-3) / 1e9 / peak) if serial_ms else None,
+                "kernel": kernel + " (one launch = one image = 12 views)",
             },
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * h2d_per_image,
@@ -364,7 +471,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                     "ms_per_step": e2e_s / e2e_steps * 1e3, "pipeline_slots": n_e2e_slots,
                     "h2d_rows": [row_first, row_last],
                     "h2d_note": f"rows {row_first}..{row_last} of {HP}: the only panorama rows the 12 views read "
-                                f"({h2d_per_image} of {H2D_PER_IMAGE} bytes per image)"},
+                                f"({h2d_per_image} of {H2D_PER_IMAGE} bytes per image)",
+                    "transfer_ceiling_ms_per_step": ceil_s * 1e3,
+                    "frac_of_transfer_ceiling": ceil_s / (e2e_s / e2e_steps),
+                    "transfer_ceiling_note": "bare cudaMemcpyAsync of the same bytes from / to the same page-locked buffers, "
+                                             "upload || readback on two streams, no kernels, all ranks at once (max over ranks)",
+                    "full_upload": e2e_full},
+            "e2e_files": e2e_files,
+            "parity": {"checked_ranks": parity_ranks, "of_ranks": world, "rank0": parity},
             "gpu_launches": launches * world,
             "clocks": clocks,
         }
@@ -375,6 +489,125 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         b.free()
     proj.close()
     ranks.close()
+
+
+def transfer_ceiling(torch, dev, pin_in, pin_out, h2d_bytes, d2h_bytes, barrier, max_over_ranks, steps=2):
+    """Seconds per e2e step of the bare transfers: BATCH x (h2d_bytes up || d2h_bytes down) between the bench's own
+    page-locked buffers and scratch device memory on two streams.  No kernel, no library code: the PCIe / host-memory
+    ceiling of the step on this box with this many ranks active."""
+    d_in = [torch.empty(h2d_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_out = [torch.empty(d2h_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    h_in = [torch.from_numpy(b.array.reshape(-1)[:h2d_bytes]) for b in pin_in]     # views of the page-locked buffers
+    h_out = [torch.from_numpy(b.array.reshape(-1)[:d2h_bytes]) for b in pin_out]
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    import ctypes as C
+
+    rt = C.CDLL("libcudart.so.12")   # resolves to the runtime torch has already loaded
+    rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    rt.cudaMemcpyAsync.restype = C.c_int
+
+    def step():
+        for i in range(BATCH):
+            # cudaMemcpyAsync directly: torch's copy_ would stage a non-torch-pinned host tensor
+            rc1 = rt.cudaMemcpyAsync(d_in[i % 2].data_ptr(), h_in[i % len(h_in)].data_ptr(), h2d_bytes, 1, s_up.cuda_stream)
+            rc2 = rt.cudaMemcpyAsync(h_out[i % len(h_out)].data_ptr(), d_out[i % 2].data_ptr(), d2h_bytes, 2, s_dn.cuda_stream)
+            assert rc1 == 0 and rc2 == 0, (rc1, rc2)
+
+    step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    sec = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    return sec / steps
+
+
+def oracle_check(proj, pano, seed):
+    """One view (yaw 90, pitch 60) of this rank's own panorama against oracle.fixedpoint.project_view_single_pass.  The
+    oracle is the checker here, never the thing measured."""
+    from oracle import fixedpoint, svml_model
+
+    got = proj.project_image(pano, [90], [60], W, H, FOV)[0, 0]
+    want = fixedpoint.project_view_single_pass(pano, 90, 60, W, H, FOV)
+    strict = bool(svml_model.host_numpy_uses_svml())
+    frac = float((got == want).all(axis=-1).mean())
+    return {"ok": bool(frac == 1.0 if strict else frac >= 0.96), "exact_pixel_fraction": frac, "seed": int(seed),
+            "view": [90, 60], "mode": "bit-exact (host NumPy uses SVML arccos / arctan2, restated by the kernel)" if strict
+            else "tolerance (host NumPy does not take the SVML path: the reference itself differs in the last ulp here)"}
+
+
+def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=8, n_thr=4):
+    """Files to files on every rank: an 8192x4096 JPEG file in host memory -> the 12 views as files in page-locked host
+    memory; Huffman decode, IDCT, projection and encode all on the GPU, n_thr images in flight per rank.  Whole-job
+    Mpix/s = all ranks' images / the slowest rank's time."""
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+
+    data = cv2.imencode(".jpg", pano)[1].tobytes()
+
+    def one(_):
+        with proj.slots(1) as (s,):
+            proj.upload_jpeg(s, data)
+            if fmt == "jpg":
+                files = proj.project_jpeg(s, shifts, consts, W, H, copy=False)
+            else:
+                files = proj.process_image_png(s, None, shifts, consts, W, H, want_pixels=False, copy=False)[0]
+            return sum(len(f) for f in files)
+
+    with ThreadPoolExecutor(n_thr) as ex:
+        out_bytes = list(ex.map(one, range(n_thr)))[0]
+        barrier()
+        t0 = time.perf_counter()
+        list(ex.map(one, range(n_img)))
+        sec = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+    return {"value": world * n_img * PX_PER_IMAGE / sec / 1e6, "unit": UNIT, "format": f"jpg -> {fmt}",
+            "ms_per_image_per_gpu": sec / n_img * 1e3, "images_per_rank": n_img, "threads_per_rank": n_thr,
+            "h2d_bytes_per_image": len(data), "d2h_bytes_per_image": out_bytes,
+            "what": "8192x4096 JPEG file bytes (host) -> 12 x 1920x1080 files (host); decode, projection and encode on the "
+                    "GPU; every rank runs the same flow at once"}
+
+
+def config_fractions(pkg, proj, synth, torch):
+    """Device-resident time and HBM-roofline fraction of the other BASELINE configs (C1, C4, C5), each ONE launch of the
+    flat view list; the L2 is flushed before every repetition (C1 / C5 panoramas would otherwise stay L2-resident)."""
+    peak, _ = read_peaks()
+    cfgs = {   # name: Wp, Hp, W, H, fov, views, algorithmic bytes per output px (SURVEY 8d)
+        "C1": (2048, 1024, 640, 480, 90, [(0, 90)], 4.94),
+        "C4": (16384, 8192, 3840, 2160, 100, [(y, p) for y in YAWS for p in PITCHES], 5.529),
+        "C5": (8192, 4096, 2048, 2048, 90, [(0, 90), (90, 90), (180, 90), (270, 90), (0, 0), (0, 180)], 6.42),
+    }
+    out = {}
+    ev0, ev1 = proj.event(), proj.event()
+    for name, (wp, hp, w, h, fov, views, b_px) in cfgs.items():
+        with proj.slots(1) as (s,):
+            proj.upload(s, synth.noise(wp, hp, 0))
+            proj.sync(s)
+            d = torch.empty((len(views), h, w, 3), dtype=torch.uint8, device=f"cuda:{proj.device}")
+            sh = [pkg.yaw_table(wp, y)[2] for y, _ in views]
+            pc = [pkg.pitch_constants(w, fov, q) for _, q in views]
+            n0 = proj.launches
+            proj.project_list(s, sh, pc, w, h, out_device_ptr=d.data_ptr())
+            proj.sync(s)
+            per_image = proj.launches - n0
+            ts = []
+            for _ in range(10):
+                proj.flush_l2(s, 256 << 20)
+                proj.record(ev0, s)
+                proj.project_list(s, sh, pc, w, h, out_device_ptr=d.data_ptr())
+                proj.record(ev1, s)
+                proj.sync(s)
+                ts.append(proj.elapsed_ms(ev0, ev1))
+            ms = statistics.median(ts)
+            px = len(views) * w * h
+            gbs = b_px * px / (ms * 1e-3) / 1e9
+            out[name] = {"image_us": ms * 1e3, "launches_per_image": per_image, "gpix_s": px / ms / 1e6,
+                         "algorithmic_bytes_per_px": b_px, "achieved_gbs": gbs, "roofline_frac": gbs / peak}
+            del d
+    return out
 
 
 def files_extras(pkg, proj, pano, shifts, consts):
@@ -457,6 +690,7 @@ def main():
     ap.add_argument("--warp-w", type=int, default=None)
     ap.add_argument("--ny", type=int, default=None)
     ap.add_argument("--nb", type=int, default=None, help="resident panoramas per launch (1, 2, 4)")
+    ap.add_argument("--streams", type=int, default=2, help="launching streams the resident images alternate over")
     ap.add_argument("--distinct", type=int, default=8, help="distinct noise seeds per GPU (others are rolled copies)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap on end-to-end steps (each moves 5.6 GB over PCIe)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -244,6 +244,9 @@ int p2p_get_stream(p2p_ctx *ctx, int slot, void **cuda_stream);
 int p2p_event_create(p2p_ctx *ctx, void **event);
 int p2p_event_destroy(p2p_ctx *ctx, void *event);
 int p2p_event_record(p2p_ctx *ctx, void *event, int slot);
+/* make everything enqueued on `slot` from now on wait for `event` (fork / join of several slot streams around a timed
+ * region: record on one stream, wait on the others, and the reverse at the end) */
+int p2p_event_wait(p2p_ctx *ctx, void *event, int slot);
 int p2p_event_elapsed_ms(p2p_ctx *ctx, void *start, void *stop, float *ms); /* syncs on stop */
 /* overwrite `bytes` of scratch device memory on the slot's stream (L2 flush between reps) */
 int p2p_flush_l2(p2p_ctx *ctx, int slot, size_t bytes);

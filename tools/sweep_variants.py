@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--nbs", type=int, nargs="+", default=[1, 2, 4])
     ap.add_argument("--mirrors", type=int, nargs="+", default=[0, 1, 2])
     ap.add_argument("--seg-chunks", type=int, nargs="+", default=[4], help="row-segment kernel (mirror 2): chunks per warp")
+    ap.add_argument("--streams", type=int, default=1, help="launching streams the resident slots alternate over (1 = the "
+                    "bench's single stream; > 1: consecutive images overlap their tails, timed by wall clock around a device sync)")
     ap.add_argument("--tag", default="", help="free-form label copied into every line (e.g. the build variant)")
     ap.add_argument("--fov", type=int, default=None, help="override the FOV (locality experiments)")
     args = ap.parse_args()
@@ -40,7 +42,9 @@ def main():
     dev = torch.device("cuda", 0)
     proj = pkg.Projector(0, n_slots=args.batch)
     slots = list(range(args.batch))
-    proj.share_stream(slots, 0)
+    for i in slots:  # slot i launches on the stream of slot i % streams
+        if i >= args.streams:
+            proj.set_stream(i, proj.get_stream(i % args.streams))
     base = synth.noise(bench.WP, bench.HP, 0)
     d_stage = torch.from_numpy(base).to(dev)
     for i in slots:
@@ -71,19 +75,27 @@ def main():
                 proj.set_option(L.OPT_IMAGES_PER_LAUNCH, nb)
                 for _ in range(3):
                     step()
-                proj.sync(0)
-                proj.record(ev0, 0)
-                for _ in range(args.steps):
-                    step()
-                proj.record(ev1, 0)
-                proj.sync(0)
-                ms = proj.elapsed_ms(ev0, ev1) / (args.steps * args.batch)
+                proj.sync(-1)
+                if args.streams == 1:
+                    proj.record(ev0, 0)
+                    for _ in range(args.steps):
+                        step()
+                    proj.record(ev1, 0)
+                    proj.sync(0)
+                    ms = proj.elapsed_ms(ev0, ev1) / (args.steps * args.batch)
+                else:
+                    import time
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps * 4):
+                        step()
+                    proj.sync(-1)
+                    ms = (time.perf_counter() - t0) * 1e3 / (args.steps * 4 * args.batch)
                 torch.cuda.synchronize()
                 cur = d_out[0].clone()
                 same = True if ref is None else bool(torch.equal(cur, ref))
                 ref = cur if ref is None else ref  # every variant must produce the same bytes (bit-exact default mode)
                 print(json.dumps({"tag": args.tag, "sampler": sampler, "warp_w": ww, "ny": ny, "nb": nb, "mirror": mirror,
-                                  "seg_chunks": segc, "image_us": ms * 1e3,
+                                  "seg_chunks": segc, "streams": args.streams, "image_us": ms * 1e3,
                                   "gpix_s": bench.PX_PER_IMAGE / (ms * 1e-3) / 1e9,
                                   "roofline_frac": bench.B_ALG_PER_IMAGE / (ms * 1e-3) / 1e9 / bench.read_peaks()[0],
                                   "same_output": same}), flush=True)
