@@ -27,6 +27,7 @@ from .panorama_to_plane_pitch import (  # noqa: E402
     process_image_batch,
     process_single_image,
     process_yaw_and_pitchs,
+    scatter_upload,
     set_device,
     set_devices,
     yaw_mapping_cache,

@@ -1553,10 +1553,42 @@ int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *ya
     return P2P_OK;
 }
 
-// Replicate the panorama of src's slot into dst's slot (another device of the same box: one PCIe upload + NVLink peer
-// copies instead of one PCIe upload per GPU).  Asynchronous on the destination slot's stream, ordered after
-// everything enqueued on the source slot so far.
-int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
+// Packed rows [y0, y1] (inclusive, y1 <= Hp: row Hp is the clamp row) now hold data in slot `s` of size Wp x Hp: merge them
+// with the rows it held before (`was_valid`, old range) when both ranges touch - a panorama can be assembled from pieces
+// (p2p_upload_pano_rows, p2p_copy_pano_rows) - else the slot holds just the new piece.
+void merge_rows(Slot &s, bool was_valid, int old_Wp, int old_Hp, int old0, int old1, int y0, int y1) {
+    if (was_valid && old_Wp == s.Wp && old_Hp == s.Hp && y0 <= old1 + 1 && y1 >= old0 - 1) {
+        s.row0 = (old0 < y0) ? old0 : y0;
+        s.row1 = (old1 > y1) ? old1 : y1;
+    } else {
+        s.row0 = y0;
+        s.row1 = y1;
+    }
+    s.valid = true;
+}
+
+int p2p_upload_pano_rows(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int row_begin,
+                         int row_end) {
+    if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
+    if (row_begin < 0 || row_end > Hp || row_begin >= row_end) return fail(ctx, P2P_ERR_INVALID, "row range outside [0, Hp]");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->slots[slot];
+    const bool was_valid = s.valid;
+    const int oW = s.Wp, oH = s.Hp, o0 = s.row0, o1 = s.row1;
+    const size_t old_cap = s.rgba_cap;
+    const uint32_t *old_ptr = s.d_rgba;
+    // the last piece also writes the clamp row Hp (a copy of row Hp - 1)
+    const int y1 = (row_end == Hp) ? Hp : row_end - 1;
+    int rc = upload_rows(ctx, slot, bgr, Wp, Hp, row_stride, row_begin, y1);
+    if (rc) return rc;
+    merge_rows(s, was_valid && old_ptr == s.d_rgba && old_cap == s.rgba_cap, oW, oH, o0, o1, row_begin, y1);
+    return P2P_OK;
+}
+
+// Copy packed rows of src's slot into dst's slot (another device of the same box: cudaMemcpyPeerAsync, NVLink when peer
+// access is available).  row_begin < 0: every row the source holds.  Asynchronous on the destination slot's stream,
+// ordered after everything enqueued on the source slot so far.
+int p2p_copy_pano_rows(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot, int row_begin, int row_end) {
     if (!dst || !src) return P2P_ERR_INVALID;
     if (!slot_ok(dst, dst_slot) || !slot_ok(src, src_slot)) return fail(dst, P2P_ERR_INVALID, "bad slot");
     if (dst == src && dst_slot == src_slot) return fail(dst, P2P_ERR_INVALID, "source and destination are the same slot");
@@ -1566,6 +1598,16 @@ int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
     Slot &a = src->slots[src_slot];
     Slot &d = dst->slots[dst_slot];
     if (!a.valid) return fail(dst, P2P_ERR_STATE, "source slot holds no panorama");
+    int y0 = a.row0, y1 = a.row1;
+    if (row_begin >= 0) {
+        y0 = row_begin;
+        y1 = row_end - 1;   // half-open [row_begin, row_end) over the packed rows 0 .. Hp (Hp = the clamp row)
+        if (y0 > y1 || y0 < a.row0 || y1 > a.row1) return fail(dst, P2P_ERR_STATE, "source slot does not hold these rows");
+    }
+    const bool was_valid = d.valid;
+    const int oW = d.Wp, oH = d.Hp, o0 = d.row0, o1 = d.row1;
+    const size_t old_cap = d.rgba_cap;
+    const uint32_t *old_ptr = d.d_rgba;
     cudaEvent_t ev = nullptr;
     CK(cudaSetDevice(src->device));
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1583,7 +1625,7 @@ int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
     if (e == cudaSuccess && rc == P2P_OK) e = cudaStreamWaitEvent(d.stream, ev, 0);
     if (e == cudaSuccess && rc == P2P_OK) {
         const size_t row_bytes = (size_t)a.pitch_tex * 4;
-        const size_t off = (size_t)a.row0 * row_bytes, bytes = (size_t)(a.row1 - a.row0 + 1) * row_bytes;
+        const size_t off = (size_t)y0 * row_bytes, bytes = (size_t)(y1 - y0 + 1) * row_bytes;
         e = cudaMemcpyPeerAsync(reinterpret_cast<uint8_t *>(d.d_rgba) + off, dst->device,
                                 reinterpret_cast<const uint8_t *>(a.d_rgba) + off, src->device, bytes, d.stream);
     }
@@ -1591,13 +1633,19 @@ int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
     if (rc) return rc;
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return fail(dst, P2P_ERR_CUDA, "p2p_copy_pano", e);
+        return fail(dst, P2P_ERR_CUDA, "p2p_copy_pano_rows", e);
     }
-    d.valid = true;
-    d.row0 = a.row0;
-    d.row1 = a.row1;
+    merge_rows(d, was_valid && old_ptr == d.d_rgba && old_cap == d.rgba_cap, oW, oH, o0, o1, y0, y1);
     d.tex_current = false;  // the gather array of the destination is refreshed from the linear copy before its next launch
     return P2P_OK;
+}
+
+int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
+    if (dst && slot_ok(dst, dst_slot)) {   // a replica replaces whatever the destination held
+        std::lock_guard<std::mutex> lk(dst->mu);
+        dst->slots[dst_slot].valid = false;
+    }
+    return p2p_copy_pano_rows(dst, dst_slot, src, src_slot, -1, -1);
 }
 
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,

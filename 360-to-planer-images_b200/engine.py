@@ -233,6 +233,34 @@ class Projector:
         rc = self.lib.p2p_copy_pano(self.ctx, slot, src.ctx, src_slot)
         self._ck(rc)
 
+    def upload_rows(self, slot: int, pano: np.ndarray, row_begin: int, row_end: int):
+        """Upload + pack panorama rows [row_begin, row_end) only (a piece of an image split over GPUs)."""
+        pano = _as_u8_image(pano)
+        Hp, Wp, _ = pano.shape
+        self._ck(self.lib.p2p_upload_pano_rows(self.ctx, slot, pano.ctypes.data, Wp, Hp, pano.strides[0],
+                                               int(row_begin), int(row_end)))
+        return pano
+
+    def copy_pano_rows_from(self, slot: int, src: "Projector", src_slot: int, row_begin: int, row_end: int):
+        """Fetch packed rows [row_begin, row_end) (0 .. Hp + 1: the clamp row is row Hp) from another context's slot."""
+        self._ck(self.lib.p2p_copy_pano_rows(self.ctx, slot, src.ctx, src_slot, int(row_begin), int(row_end)))
+
+    def project_list_call(self, slot: int, shifts, consts, W: int, H: int, rows=None, out=None,
+                          out_device_ptr: int | None = None):
+        """``project_list`` with the arguments marshalled once: returns a zero-argument callable (hot loops)."""
+        shifts_a = np.ascontiguousarray(shifts, np.int32)
+        pc = self._consts_array(consts)
+        r0, r1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+        dst, on_dev = (C.c_void_p(out_device_ptr), 1) if out_device_ptr is not None else (out.ctypes.data, 0)
+        args = (self.ctx, slot, int(shifts_a.shape[0]), shifts_a.ctypes.data_as(C.POINTER(C.c_int32)), pc, W, H, r0, r1,
+                dst, on_dev)
+        fn = self.lib.p2p_project_view_list
+
+        def call(_keep=(shifts_a, pc, out)):
+            self._ck(fn(*args))
+
+        return call
+
     def batch_call(self, slots, shifts, consts, W: int, H: int, out_ptrs, on_device: bool = True):
         """Prebuilt ``p2p_project_batch`` call for resident panoramas: returns a zero-argument
         callable that enqueues one launch per slot (arguments are marshalled once)."""

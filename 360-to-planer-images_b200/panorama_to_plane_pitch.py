@@ -188,10 +188,30 @@ def _split_upload(projs, src, stack):
                 raise
             pano = _decode_source(p0, src, slot=s0)
     if pano is not None:
-        stack.callback(lambda keep=p0.upload(s0, pano): None)  # the host array outlives the asynchronous copy
-    for pr, sl in zip(projs[1:], slots[1:]):
+        # host pixels: every device uploads 1 / n of the rows over its own PCIe link and fetches the rest from its peers
+        stack.callback(lambda keep=scatter_upload(projs, slots, pano): None)  # the host array outlives the async copies
+        return slots
+    for pr, sl in zip(projs[1:], slots[1:]):     # decoded on the first device: replicate from there
         pr.copy_pano_from(sl, p0, s0)
     return slots
+
+
+def scatter_upload(projs, slots, pano):
+    """The panorama in every ``(projs[r], slots[r])``: device r uploads rows [Hp r / n, Hp (r + 1) / n) and copies the other
+    pieces from the devices that hold them (an all-gather made of NVLink peer copies, each ordered after its source's
+    upload on the device).  All asynchronous; returns the host array, which must stay alive until the slots are synced."""
+    pano = _engine._as_u8_image(pano, "pano_image")
+    Hp, n = pano.shape[0], len(projs)
+    b = [Hp * r // n for r in range(n + 1)]
+    for r in range(n):
+        if b[r] < b[r + 1]:
+            projs[r].upload_rows(slots[r], pano, b[r], b[r + 1])
+    for r in range(n):
+        for q in list(range(r + 1, n)) + list(range(r - 1, -1, -1)):   # outwards from the own piece: always contiguous
+            if b[q] < b[q + 1]:
+                # packed rows: the last piece carries the clamp row Hp as well
+                projs[r].copy_pano_rows_from(slots[r], projs[q], slots[q], b[q], b[q + 1] + (1 if b[q + 1] == Hp else 0))
+    return pano
 
 
 def _project_split(devices, src, consts, tables, yaw_angles, pitch_angles, W, H):

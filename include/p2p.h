@@ -157,6 +157,18 @@ int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *ya
  * slot unchanged until the destination slot has been synchronised. */
 int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot);
 
+/* A panorama assembled from pieces: when ONE image is split over n GPUs every device uploads 1 / n of the rows over its
+ * own PCIe link (p2p_upload_pano_rows) and fetches the other pieces from its peers over NVLink (p2p_copy_pano_rows) - an
+ * all-gather built from peer copies, so the PCIe time of the panorama shrinks with n instead of being paid by one GPU.
+ * p2p_upload_pano_rows copies + packs host rows [row_begin, row_end) (row_end == Hp also writes the clamp row);
+ * p2p_copy_pano_rows copies packed rows [row_begin, row_end) of the source slot (packed rows run 0 .. Hp, the clamp row
+ * included: row_end <= Hp + 1; row_begin < 0: everything the source holds).  A piece that touches the rows a slot already
+ * holds (same panorama size) extends them; otherwise the slot holds just the new piece.  Both are asynchronous on the
+ * destination slot's stream; the copy is ordered after the work enqueued on the source slot. */
+int p2p_upload_pano_rows(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int row_begin,
+                         int row_end);
+int p2p_copy_pano_rows(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot, int row_begin, int row_end);
+
 /* upload + project + readback of one image in one call (all asynchronous on the slot stream).
  * Because the views are known before the transfer, only the panorama rows they can touch are copied to the
  * device (P2P_OPT_PARTIAL_UPLOAD); the slot then holds a partial panorama: projecting other views from it

@@ -280,3 +280,55 @@ def test_last_error_is_per_thread(pkg, proj):
         assert seen == [""]
     finally:
         fresh.close()
+
+
+def test_panorama_assembled_from_pieces(pkg, proj):
+    """``p2p_upload_pano_rows`` / ``p2p_copy_pano_rows``: pieces that touch extend the rows a slot holds (the all-gather of
+    an image split over GPUs), a piece elsewhere replaces them; projecting needs the rows the views touch."""
+    Wp, Hp, W, H, fov = 1024, 512, 128, 96, 90
+    pano = synth.noise(Wp, Hp, 12)
+    consts = [pkg.pitch_constants(W, fov, 90)]
+    with proj.slots(3) as (a, b, c):
+        proj.upload(a, pano)
+        want = proj.project(a, [0], consts, W, H)
+        proj.sync(a)
+        # pieces in any contiguous order
+        proj.upload_rows(b, pano, 200, 300)
+        proj.upload_rows(b, pano, 300, Hp)
+        with pytest.raises(pkg.P2PError) as e:     # rows 0 .. 199 are still missing
+            proj.project(b, [0], consts, W, H)
+        assert e.value.code == -4
+        proj.upload_rows(b, pano, 0, 200)
+        got = proj.project(b, [0], consts, W, H)
+        proj.sync(b)
+        assert np.array_equal(got, want)
+        assert np.array_equal(proj.download_pano(b, Wp, Hp), pano)
+        # all-gather between two slots
+        proj.upload_rows(b, pano, 0, 256)           # not adjacent to nothing: replaces -> slot b holds rows 0 .. 255 only
+        proj.upload_rows(c, pano, 256, Hp)
+        proj.copy_pano_rows_from(b, proj, c, 256, Hp + 1)
+        proj.copy_pano_rows_from(c, proj, b, 0, 256)
+        for s in (b, c):
+            got = proj.project(s, [0], consts, W, H)
+            proj.sync(s)
+            assert np.array_equal(got, want)
+        proj.upload_rows(a, synth.noise(512, 256, 1), 0, 10)   # another size: slot a now holds rows 0 .. 9 of that image
+        with pytest.raises(pkg.P2PError) as e:                 # the source does not hold these rows
+            proj.copy_pano_rows_from(b, proj, a, 5, 50)
+        assert e.value.code == -4
+        with pytest.raises(pkg.P2PError):
+            proj.upload_rows(a, pano, 10, Hp + 1)
+    # the front-end helper over devices (a device may be listed twice)
+    for devs in _device_sets(pkg):
+        projs = [pkg.get_projector(d) for d in devs]
+        import contextlib
+
+        with contextlib.ExitStack() as st:
+            slots = [st.enter_context(p.slots(1))[0] for p in projs]
+            keep = pkg.scatter_upload(projs, slots, pano)
+            for p, s in zip(projs, slots):
+                got = p.project(s, [0], consts, W, H)
+                p.sync(s)
+                assert np.array_equal(got, want), devs
+                assert np.array_equal(p.download_pano(s, Wp, Hp), pano), devs
+            del keep

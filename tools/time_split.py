@@ -4,7 +4,9 @@
     python tools/time_split.py [--configs c2 c4 c5] [--devices 1 2 4 8] [--reps 10] > gpurun_out/r2_split.jsonl
 
 One process drives one context per device.  Per repetition (all calls asynchronous, page-locked host buffers):
-    upload the panorama to device 0 (PCIe) -> replicate it to the other devices (cudaMemcpyPeerAsync, NVLink)
+    the panorama reaches every device - mode "replicate": uploaded to device 0 over PCIe, then cudaMemcpyPeerAsync to the
+    others; mode "scatter": every device uploads 1 / n of the rows over its own PCIe link and fetches the other pieces
+    from its peers (an NVLink all-gather of peer copies) -
     -> every device renders its band of output rows of ALL views (p2p_project_view_list) -> bands land in one host array.
 Three timings per device count: ``e2e_ms`` the whole sequence, ``resident_ms`` panoramas already replicated (project +
 readback), ``device_ms`` outputs left in HBM (kernel only, wall clock around sync of all devices).  The N = 1 result is the
@@ -71,18 +73,22 @@ def main():
             bands = [shard.shard_rows(H, r, n) for r in range(n)]
             d_outs = [torch.empty((len(views), H, W, 3), dtype=torch.uint8, device=f"cuda:{r}") for r in range(n)]
 
-            def replicate():
-                ps[0].upload(0, pin_in.array)
-                for p in ps[1:]:
-                    p.copy_pano_from(0, ps[0], 0)
+            def replicate(mode="scatter"):
+                if mode == "scatter" and n > 1:
+                    pkg.scatter_upload(ps, [0] * n, pin_in.array)
+                else:
+                    ps[0].upload(0, pin_in.array)
+                    for p in ps[1:]:
+                        p.copy_pano_from(0, ps[0], 0)
+
+            host_calls = [p.project_list_call(0, shifts, consts, W, H, rows=bands[r], out=pin_out.array)
+                          for r, p in enumerate(ps) if bands[r][0] < bands[r][1]]
+            dev_calls = [p.project_list_call(0, shifts, consts, W, H, rows=bands[r], out_device_ptr=d_outs[r].data_ptr())
+                         for r, p in enumerate(ps) if bands[r][0] < bands[r][1]]
 
             def project(host=True):
-                for r, p in enumerate(ps):
-                    if bands[r][0] < bands[r][1]:
-                        if host:
-                            p.project_list(0, shifts, consts, W, H, rows=bands[r], out=pin_out.array)
-                        else:
-                            p.project_list(0, shifts, consts, W, H, rows=bands[r], out_device_ptr=d_outs[r].data_ptr())
+                for f in (host_calls if host else dev_calls):
+                    f()
 
             def sync():
                 for p in ps:
@@ -109,13 +115,14 @@ def main():
             e2e_ms = median_ms(e2e, args.reps)
             res_ms = median_ms(resident, args.reps)
             dev_ms = median_ms(device_only, args.reps)
-            rep_ms = median_ms(lambda: (replicate(), sync()), args.reps)
+            rep_ms = median_ms(lambda: (replicate("replicate"), sync()), args.reps)
+            sca_ms = median_ms(lambda: (replicate("scatter"), sync()), args.reps)
             px = len(views) * W * H
             print(json.dumps({
                 "config": name, "pano": [Wp, Hp], "out": [W, H], "views": len(views), "n_gpus": n,
                 "bands": bands, "identical": bool(np.array_equal(got, ref)),
                 "e2e_ms": e2e_ms[0], "e2e_ms_min": e2e_ms[1], "resident_ms": res_ms[0], "device_ms": dev_ms[0],
-                "device_ms_min": dev_ms[1], "upload_replicate_ms": rep_ms[0],
+                "device_ms_min": dev_ms[1], "upload_replicate_ms": rep_ms[0], "upload_scatter_allgather_ms": sca_ms[0],
                 "e2e_mpix_s": px / (e2e_ms[0] * 1e-3) / 1e6, "device_mpix_s": px / (dev_ms[0] * 1e-3) / 1e6,
             }), flush=True)
             del d_outs
