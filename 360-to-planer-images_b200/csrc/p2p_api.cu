@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler is attached
+
 #include <mutex>
 #include <new>
 #include <string>
@@ -18,6 +20,15 @@
 using namespace p2p;
 
 namespace {
+
+// NVTX range over one entry point of the C ABI (per image and stage: upload / decode, project, encode, replicate)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define P2P_NVTX(name) NvtxRange nvtx_range_(name)
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -120,10 +131,12 @@ struct p2p_ctx {
     int opt_gpu_huffman = 1;   // JPEG inputs without restart markers: Huffman decoding on the device
     long long gpu_huffman_used = 0, gpu_huffman_fallback = 0;
     uint32_t *d_crc_table = nullptr;    // CRC-32 table of the PNG encoder
-    p2pjpeg::Tables *d_jtab = nullptr;  // JPEG tables + header of (jW, jH, jQ)
+    p2pjpeg::Tables *d_jtab = nullptr;  // JPEG tables + header of (jW, jH, jQ): the entry of jtabs in use
     int jW = 0, jH = 0, jQ = 0;
+    struct JTab { int W, H, Q; p2pjpeg::Tables *d; };
+    std::vector<JTab> jtabs;            // one device copy per (size, quality) seen: a folder of mixed sizes never waits
     int *j_err_h = nullptr, *j_err_d = nullptr;  // mapped: set by the encoder kernels when a file does not fit
-    RowRange rows;
+    std::vector<RowRange> rows;   // memoised per geometry (the reference's pitch_mapping_cache key, ref :55-73)
     int *d_range = nullptr;
     long long launches = 0;
     uint4 *d_flush = nullptr;
@@ -237,10 +250,20 @@ bool slot_is_partial(const Slot &s) { return s.row0 > 0 || s.row1 < s.Hp; }
 // geometry on `st` (one small kernel + an 8-byte readback) and memoised in the context.
 int view_row_range(p2p_ctx *ctx, cudaStream_t st, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
                    int Wp, int Hp, int *lo, int *hi) {
-    RowRange &r = ctx->rows;
-    bool hit = r.valid && r.W == W && r.H == H && r.Wp == Wp && r.Hp == Hp && r.trig == ctx->opt_trig &&
-               (int)r.pc.size() == n_pitch;
-    for (int j = 0; hit && j < n_pitch; ++j) hit = memcmp(&r.pc[j], &pitch[j], sizeof(p2p_pitch_consts)) == 0;
+    RowRange *found = nullptr;
+    for (RowRange &c : ctx->rows) {
+        bool hit = c.valid && c.W == W && c.H == H && c.Wp == Wp && c.Hp == Hp && c.trig == ctx->opt_trig &&
+                   (int)c.pc.size() == n_pitch;
+        for (int j = 0; hit && j < n_pitch; ++j) hit = memcmp(&c.pc[j], &pitch[j], sizeof(p2p_pitch_consts)) == 0;
+        if (hit) found = &c;
+    }
+    const bool hit = found != nullptr;
+    if (!hit) {
+        if (ctx->rows.size() >= 64) ctx->rows.erase(ctx->rows.begin());  // oldest geometry out
+        ctx->rows.emplace_back();
+        found = &ctx->rows.back();
+    }
+    RowRange &r = *found;
     if (!hit) {
         if ((H + 7) / 8 > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
         if (!ctx->d_range) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_range), 2 * sizeof(int)));
@@ -647,18 +670,31 @@ int enqueue_jpeg(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int 
     if (W >= 65536 || H >= 65536) return fail(ctx, P2P_ERR_LIMIT, "JPEG dimensions must be < 65536");
     G = make_geometry(W, H);
     if ((size_t)G.n_blocks * 64ull * 27ull >= (1ull << 32)) return fail(ctx, P2P_ERR_LIMIT, "image too large for the JPEG encoder");
-    if (!ctx->d_jtab) CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_jtab), sizeof(Tables)));
     if (!ctx->j_err_h) {
         CK(cudaHostAlloc(reinterpret_cast<void **>(&ctx->j_err_h), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
         *ctx->j_err_h = 0;
         CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&ctx->j_err_d), ctx->j_err_h, 0));
     }
-    if (ctx->jW != W || ctx->jH != H || ctx->jQ != quality) {
-        // other streams may still read the old tables: rare (a new output size or quality), wait for everything
-        for (int i = 0; i < ctx->n_slots; ++i) CK(cudaStreamSynchronize(ctx->slots[i].stream));
-        Tables T;
-        build_tables(W, H, quality, T);
-        CK(cudaMemcpy(ctx->d_jtab, &T, sizeof(T), cudaMemcpyHostToDevice));
+    if (!ctx->d_jtab || ctx->jW != W || ctx->jH != H || ctx->jQ != quality) {
+        // tables + file header per (size, quality), each in its own device buffer: launches of other slots that still read
+        // another entry are not disturbed (no stream is synchronised)
+        Tables *found = nullptr;
+        for (const p2p_ctx::JTab &t : ctx->jtabs)
+            if (t.W == W && t.H == H && t.Q == quality) found = t.d;
+        if (!found) {
+            if (ctx->jtabs.size() >= 64) {  // a pathological stream of sizes: start over once everything has drained
+                for (int i = 0; i < ctx->n_slots; ++i) CK(cudaStreamSynchronize(ctx->slots[i].stream));
+                for (const p2p_ctx::JTab &t : ctx->jtabs) cudaFree(t.d);
+                ctx->jtabs.clear();
+                ctx->d_jtab = nullptr;
+            }
+            Tables T;
+            build_tables(W, H, quality, T);
+            CK(cudaMalloc(reinterpret_cast<void **>(&found), sizeof(Tables)));
+            CK(cudaMemcpy(found, &T, sizeof(T), cudaMemcpyHostToDevice));
+            ctx->jtabs.push_back(p2p_ctx::JTab{W, H, quality, found});
+        }
+        ctx->d_jtab = found;
         ctx->jW = W; ctx->jH = H; ctx->jQ = quality;
     }
     const size_t nb = (size_t)n * G.blk_stride, chunks = G.cap_bits_words / 4;
@@ -1203,7 +1239,7 @@ void p2p_destroy(p2p_ctx *ctx) {
     }
     cudaFree(ctx->d_flush);
     cudaFree(ctx->d_range);
-    cudaFree(ctx->d_jtab);
+    for (const p2p_ctx::JTab &t : ctx->jtabs) cudaFree(t.d);
     cudaFree(ctx->d_crc_table);
     if (ctx->j_err_h) cudaFreeHost(ctx->j_err_h);
     cudaGetLastError();
@@ -1376,12 +1412,14 @@ int p2p_host_unregister(void *ptr) {
 
 // ---- panorama upload -----------------------------------------------------------------------
 int p2p_upload_pano(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride) {
+    P2P_NVTX("p2p_upload_pano");
     if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
     std::lock_guard<std::mutex> lk(ctx->mu);
     return upload_rows(ctx, slot, bgr, Wp, Hp, row_stride, 0, Hp);
 }
 
 int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, int Hp, size_t row_stride) {
+    P2P_NVTX("p2p_upload_pano_device");
     if (!slot_ok(ctx, slot) || !d_bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_dims(ctx, Wp, Hp);
@@ -1395,6 +1433,7 @@ int p2p_upload_pano_device(p2p_ctx *ctx, int slot, const void *d_bgr, int Wp, in
 }
 
 int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix, const int32_t *fx) {
+    P2P_NVTX("p2p_rotate_pano");
     if (!slot_ok(ctx, src_slot) || !slot_ok(ctx, dst_slot) || src_slot == dst_slot || !ix || !fx)
         return fail(ctx, P2P_ERR_INVALID, "bad slots or null table");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1436,6 +1475,7 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
 // ---- hot path ------------------------------------------------------------------------------
 int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                       const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device) {
+    P2P_NVTX("p2p_project_views");
     if (!ctx) return P2P_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     return project_views_locked(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, out_on_device);
@@ -1444,6 +1484,7 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
 int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
                       int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
                       int out_on_device) {
+    P2P_NVTX("p2p_project_batch");
     if (!ctx || n_images <= 0 || !slots || !outs) return fail(ctx, P2P_ERR_INVALID, "bad batch arguments");
     int nb = 1;
     {
@@ -1494,6 +1535,7 @@ int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_ya
 // Flat view list, optional row band: view i = (yaw_shift[i], pitch[i]) -> out + i * W * H * 3, rows row_begin .. row_end - 1.
 int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *yaw_shift, const p2p_pitch_consts *pitch,
                           int W, int H, int row_begin, int row_end, uint8_t *out, int out_on_device) {
+    P2P_NVTX("p2p_project_view_list");
     if (!ctx) return P2P_ERR_INVALID;
     if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
     if (n_views <= 0 || !yaw_shift || !pitch || !out) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
@@ -1569,6 +1611,7 @@ void merge_rows(Slot &s, bool was_valid, int old_Wp, int old_Hp, int old0, int o
 
 int p2p_upload_pano_rows(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int row_begin,
                          int row_end) {
+    P2P_NVTX("p2p_upload_pano_rows");
     if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
     if (row_begin < 0 || row_end > Hp || row_begin >= row_end) return fail(ctx, P2P_ERR_INVALID, "row range outside [0, Hp]");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1589,6 +1632,7 @@ int p2p_upload_pano_rows(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int
 // access is available).  row_begin < 0: every row the source holds.  Asynchronous on the destination slot's stream,
 // ordered after everything enqueued on the source slot so far.
 int p2p_copy_pano_rows(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot, int row_begin, int row_end) {
+    P2P_NVTX("p2p_copy_pano_rows");
     if (!dst || !src) return P2P_ERR_INVALID;
     if (!slot_ok(dst, dst_slot) || !slot_ok(src, src_slot)) return fail(dst, P2P_ERR_INVALID, "bad slot");
     if (dst == src && dst_slot == src_slot) return fail(dst, P2P_ERR_INVALID, "source and destination are the same slot");
@@ -1651,6 +1695,7 @@ int p2p_copy_pano(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot) {
 int p2p_process_image(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride,
                       int n_yaw, const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch,
                       int W, int H, uint8_t *out_host) {
+    P2P_NVTX("p2p_process_image");
     if (!slot_ok(ctx, slot) || !bgr) return fail(ctx, P2P_ERR_INVALID, "bad slot or null panorama");
     if (n_pitch <= 0 || !pitch || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1691,6 +1736,7 @@ int p2p_view_row_range(p2p_ctx *ctx, int n_pitch, const p2p_pitch_consts *pitch,
 // ---- JPEG files of the views (the encode side of cv2.imwrite, ref :277) -------------------------------
 int p2p_encode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H, int quality,
                     uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    P2P_NVTX("p2p_encode_jpeg");
     if (!slot_ok(ctx, slot) || !bgr || n_images <= 0 || W <= 0 || H <= 0 || !out_host || !sizes)
         return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2pjpeg::Geometry G;
@@ -1719,6 +1765,7 @@ int p2p_encode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, i
 int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                            const p2p_pitch_consts *pitch, int W, int H, int quality, uint8_t *out_host,
                            size_t out_stride, size_t *sizes) {
+    P2P_NVTX("p2p_project_views_jpeg");
     return p2p_process_image_jpeg(ctx, slot, nullptr, 0, 0, 0, n_yaw, yaw_shift, n_pitch, pitch, W, H, quality, out_host,
                                   out_stride, sizes);
 }
@@ -1726,6 +1773,7 @@ int p2p_project_views_jpeg(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw
 int p2p_process_image_jpeg(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
                            const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
                            int quality, uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    P2P_NVTX("p2p_process_image_jpeg");
     if (!slot_ok(ctx, slot) || !out_host || !sizes) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     if (n_yaw <= 0 || n_pitch <= 0 || !pitch || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
     p2pjpeg::Geometry G;
@@ -1794,6 +1842,7 @@ int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t
 }
 
 int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp) {
+    P2P_NVTX("p2p_upload_pano_jpeg");
     if (!slot_ok(ctx, slot) || !file || !Wp || !Hp) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2pjdec::Parsed P;
     size_t dstride = 0;
@@ -1824,6 +1873,7 @@ int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len
 
 int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
                     size_t capacity_rows) {
+    P2P_NVTX("p2p_decode_jpeg");
     if (!slot_ok(ctx, slot) || !file || !bgr_host) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2pjdec::Parsed P;
     size_t dstride = 0;
@@ -1850,6 +1900,7 @@ int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uin
 // ---- PNG files of the views (cv2.imwrite(<name>.png, view), ref :277, the default output format) ----------------
 int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, int n_images, int W, int H,
                    uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    P2P_NVTX("p2p_encode_png");
     if (!slot_ok(ctx, slot) || !bgr || n_images <= 0 || W <= 0 || H <= 0 || !out_host || !sizes)
         return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2ppng::Geom G;
@@ -1878,6 +1929,7 @@ int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, in
 int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, int Hp, size_t row_stride, int n_yaw,
                           const int32_t *yaw_shift, int n_pitch, const p2p_pitch_consts *pitch, int W, int H,
                           uint8_t *out_host, size_t out_stride, size_t *sizes, uint8_t *pixels_host) {
+    P2P_NVTX("p2p_process_image_png");
     if (!slot_ok(ctx, slot) || !out_host || !sizes) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     if (n_yaw <= 0 || n_pitch <= 0 || !pitch || W <= 0 || H <= 0) return fail(ctx, P2P_ERR_INVALID, "null or empty view list / output");
     p2ppng::Geom G;

@@ -121,18 +121,20 @@ def _open_image(path):
     return cv2.imread(str(path))
 
 
-def _decode_source(proj, src, slot=None):
+def _decode_source(proj, src, slot=None, device_declined=False):
     """Host pixels of a source (fractional-yaw path, or a damaged file the device decoder gave up on).  ``slot``: the slot
-    the caller already holds (no second one is taken)."""
+    the caller already holds (no second one is taken).  ``device_declined``: the device decoder has already refused this
+    file (``upload_jpeg`` returned -6) - running the identical decode again could only fail again, go straight to cv2."""
     import cv2
 
     if not isinstance(src, _JpegSource):
         return src
-    try:
-        return proj.decode_jpeg(src.data, slot=slot)
-    except _engine.P2PError as e:
-        if e.code != -6:
-            raise
+    if not device_declined:
+        try:
+            return proj.decode_jpeg(src.data, slot=slot)
+        except _engine.P2PError as e:
+            if e.code != -6:
+                raise
     # the reference's own call: cv2.imread, not imdecode (for a truncated file libjpeg's file reader pads the scan and
     # returns an image where its memory reader gives up)
     img = cv2.imread(str(src.path))
@@ -169,6 +171,7 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
         except _engine.P2PError as e:
             if e.code != -6:
                 raise
+            src = _decode_source(proj, src, device_declined=True)
     return proj.project_image(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height, fov_deg,
                               consts=consts, tables=tables)
 
@@ -186,7 +189,7 @@ def _split_upload(projs, src, stack):
         except _engine.P2PError as e:
             if e.code != -6:
                 raise
-            pano = _decode_source(p0, src, slot=s0)
+            pano = _decode_source(p0, src, slot=s0, device_declined=True)
     if pano is not None:
         # host pixels: every device uploads 1 / n of the rows over its own PCIe link and fetches the rest from its peers
         stack.callback(lambda keep=scatter_upload(projs, slots, pano): None)  # the host array outlives the async copies
@@ -276,6 +279,9 @@ def _split_devices(devices, tables, yaw_angles, pitch_angles):
     return devs if all(t[2] is not None for t in tables) else None
 
 
+_ENCODER_FALLBACK_CODES = (-3, -5)   # P2P_ERR_NOMEM, P2P_ERR_LIMIT
+
+
 def _is_jpeg(output_format) -> bool:
     return str(output_format).lower() in ("jpg", "jpeg")
 
@@ -312,7 +318,7 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
                 except _engine.P2PError as e:
                     if e.code != -6:
                         raise
-                    pano = _decode_source(proj, src, slot=s)
+                    pano = _decode_source(proj, src, slot=s, device_declined=True)
             if pano is None:
                 flat = proj.project_jpeg(s, shifts, consts, output_width, output_height, copy=lease is None)
             else:
@@ -350,7 +356,7 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
                 except _engine.P2PError as e:
                     if e.code != -6:
                         raise
-                    pano = _decode_source(proj, src, slot=s)
+                    pano = _decode_source(proj, src, slot=s, device_declined=True)
             flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False,
                                              copy=lease is None)
             views = None
@@ -445,13 +451,21 @@ def process_single_image(input_image_path, output_dir, yaw_angles, pitch_angles,
     # the slot stays leased until the files are on disk: they are written straight from its page-locked buffer
     with contextlib.ExitStack() as lease, ThreadPoolExecutor(max_workers=max(1, int(num_workers))) as executor:
         try:
-            if jpeg:  # projected and encoded on the device: only the files come back
-                files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
-                                      output_height, fov_deg, lease=lease, devices=devices)
-            elif png:
-                files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
-                                            output_height, fov_deg, lease=lease, devices=devices)
-            else:
+            try:
+                if jpeg:  # projected and encoded on the device: only the files come back
+                    files = _project_jpeg(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
+                                          output_height, fov_deg, lease=lease, devices=devices)
+                elif png:
+                    files, views = _project_png(get_projector(), input_image, yaw_angles, pitch_angles, output_width,
+                                                output_height, fov_deg, lease=lease, devices=devices)
+            except _engine.P2PError as e:
+                if e.code not in _ENCODER_FALLBACK_CODES:
+                    raise
+                # the device encoders' scratch does not fit (huge views x many slots): the reference's own route,
+                # pixels back + cv2.imwrite, still produces the files
+                logging.warning(f"Device encoder unavailable for {input_image_path} ({e}); writing with cv2.imwrite")
+                jpeg = png = False
+            if not jpeg and not png:
                 views = _project(get_projector(), input_image, yaw_angles, pitch_angles, output_width, output_height,
                                  fov_deg, devices=devices)
         except Exception as e:
@@ -544,14 +558,21 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
                 logging.error(f"Failed to read image: {f}")
                 return
             try:
-                if jpeg_out:
-                    files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease, devices=[])
-                    futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
-                elif str(output_format).lower() == "png":
-                    files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease, devices=[])
-                    futs = _save_png(cv2, files_, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
-                                     writers)
-                else:
+                futs = None
+                try:
+                    if jpeg_out:
+                        files_ = _project_jpeg(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease, devices=[])
+                        futs = _save_files(files_, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format, writers)
+                    elif str(output_format).lower() == "png":
+                        files_, views = _project_png(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, lease=lease,
+                                                     devices=[])
+                        futs = _save_png(cv2, files_, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H,
+                                         output_format, writers)
+                except _engine.P2PError as e:
+                    if e.code not in _ENCODER_FALLBACK_CODES:
+                        raise
+                    logging.warning(f"Device encoder unavailable for {f} ({e}); writing with cv2.imwrite")
+                if futs is None:
                     views = _project(proj, src, yaw_angles, pitch_angles, W, H, fov_deg, devices=[])
                     futs = _save_views(cv2, views, f.stem, output_dir, yaw_angles, pitch_angles, W, H, output_format,
                                        writers)

@@ -304,7 +304,11 @@ def test_panorama_assembled_from_pieces(pkg, proj):
         assert np.array_equal(got, want)
         assert np.array_equal(proj.download_pano(b, Wp, Hp), pano)
         # all-gather between two slots
-        proj.upload_rows(b, pano, 0, 256)           # not adjacent to nothing: replaces -> slot b holds rows 0 .. 255 only
+        proj.upload_rows(b, synth.noise(512, 256, 1), 0, 10)   # another image: slot b forgets the rows it held
+        proj.upload_rows(b, pano, 0, 256)                      # -> rows 0 .. 255 of `pano` only
+        with pytest.raises(pkg.P2PError) as e:
+            proj.project(b, [0], consts, W, H)
+        assert e.value.code == -4
         proj.upload_rows(c, pano, 256, Hp)
         proj.copy_pano_rows_from(b, proj, c, 256, Hp + 1)
         proj.copy_pano_rows_from(c, proj, b, 0, 256)
