@@ -24,6 +24,8 @@ COORD_ULP_TOL = 8
 # G3 on noise: a coordinate within an ulp of a 1/32-px bin edge flips the bin (about 1 % of
 # pixels at 8K, SURVEY probe p4); everything else must be identical.
 NOISE_EXACT_MIN = 0.96
+# P2P_OPT_MIRROR: 2 = row-segment kernel (the default), 1 = round-1 pair kernel, 0 = every pixel evaluates its own coordinates
+MIRROR_DEFAULT = 2
 
 
 def load(golden_dir, name):
@@ -185,9 +187,9 @@ def test_g2_nan_pixel_set_equality(proj, golden_dir):
 def test_g3_bit_exact_against_every_golden_output(pkg, proj, golden_dir):
     """Default mode (NumPy-exact trig, mirror kernel): every stored output of the unmodified reference -
     C1 full size, the scaled README example on noise and on the smooth panorama, cube faces with pole
-    pitches, fractional yaws, the NaN-pixel case - is reproduced bit for bit, by both projection kernels."""
+    pitches, fractional yaws, the NaN-pixel case - is reproduced bit for bit, by all three projection kernels."""
     L = pkg._lib
-    for mirror in (1, 0):
+    for mirror in (2, 1, 0):
         proj.set_option(L.OPT_MIRROR, mirror)
         try:
             g = load(golden_dir, "c1.npz")
@@ -213,7 +215,7 @@ def test_g3_bit_exact_against_every_golden_output(pkg, proj, golden_dir):
             out = proj.project_image(synth.smooth(Wp, Hp, 0), [0], [int(p) for p in g["pitches"]], W, H, fov)
             assert np.array_equal(out, g["out"]), mirror
         finally:
-            proj.set_option(L.OPT_MIRROR, 1)
+            proj.set_option(L.OPT_MIRROR, MIRROR_DEFAULT)
 
 
 def test_g3_full_size_hashes_of_the_reference(proj, golden_dir):
@@ -334,7 +336,7 @@ def test_kernel_variants_identical(pkg, proj):
         proj.set_option(L.OPT_SAMPLER, 1)
         proj.set_option(L.OPT_WARP_W, 32)
         proj.set_option(L.OPT_YAWS_PER_THREAD, 4)
-        proj.set_option(L.OPT_MIRROR, 1)
+        proj.set_option(L.OPT_MIRROR, MIRROR_DEFAULT)
 
 
 def test_mirror_kernel_against_per_pixel_kernel_and_oracle(pkg, proj):
@@ -356,20 +358,23 @@ def test_mirror_kernel_against_per_pixel_kernel_and_oracle(pkg, proj):
             proj.set_option(L.OPT_MIRROR, 0)
             ref_n = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
         finally:
-            proj.set_option(L.OPT_MIRROR, 1)
-        got_n = proj.project_image(noise, yaws, pitches, W, H, fov)
-        # NumPy-exact trig: the pair shares SVML's sign-independent atan2 core, both halves are identical
-        assert np.array_equal(got_n, ref_n), "mirror kernel differs from the per-pixel kernel"
-        try:  # minimax trig: the derived half may flip a 1/32-px bin where the azimuths differ in the last ulp
-            proj.set_option(L.OPT_TRIG, 1)
-            got_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
-            proj.set_option(L.OPT_MIRROR, 0)
-            ref_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
-        finally:
-            proj.set_option(L.OPT_MIRROR, 1)
-            proj.set_option(L.OPT_TRIG, 0)
-        assert np.array_equal(got_m[..., W // 2:, :], ref_m[..., W // 2:, :]), "direct half differs"
-        assert exact_fraction(got_m[..., :W // 2, :], ref_m[..., :W // 2, :]) >= 0.97
+            proj.set_option(L.OPT_MIRROR, MIRROR_DEFAULT)
+        for mirror in (1, 2):   # the round-1 pair kernel and the row-segment kernel (default)
+            try:
+                proj.set_option(L.OPT_MIRROR, mirror)
+                got_n = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+                # NumPy-exact trig: the pair shares SVML's sign-independent atan2 core, both halves are identical
+                assert np.array_equal(got_n, ref_n), f"pair kernel {mirror} differs from the per-pixel kernel"
+                # minimax trig: the derived half may flip a 1/32-px bin where the azimuths differ in the last ulp
+                proj.set_option(L.OPT_TRIG, 1)
+                got_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+                proj.set_option(L.OPT_MIRROR, 0)
+                ref_m = proj.project_image(noise, yaws, pitches, W, H, fov).copy()
+            finally:
+                proj.set_option(L.OPT_MIRROR, MIRROR_DEFAULT)
+                proj.set_option(L.OPT_TRIG, 0)
+            assert np.array_equal(got_m[..., W // 2:, :], ref_m[..., W // 2:, :]), "direct half differs"
+            assert exact_fraction(got_m[..., :W // 2, :], ref_m[..., :W // 2, :]) >= 0.97
         got_s = proj.project_image(smooth, yaws, pitches, W, H, fov)
         for i, y in enumerate(yaws):
             for j, p in enumerate(pitches):
@@ -472,7 +477,7 @@ def test_multi_image_launch_matches_single(pkg, proj):
         finally:
             proj.set_option(L.OPT_SAMPLER, 1)
             proj.set_option(L.OPT_IMAGES_PER_LAUNCH, 1)
-            proj.set_option(L.OPT_MIRROR, 1)
+            proj.set_option(L.OPT_MIRROR, MIRROR_DEFAULT)
 
 
 def test_many_yaws_and_pitches_chunking(proj):

@@ -336,3 +336,24 @@ def test_panorama_assembled_from_pieces(pkg, proj):
                 assert np.array_equal(got, want), devs
                 assert np.array_equal(p.download_pano(s, Wp, Hp), pano), devs
             del keep
+
+
+@pytest.mark.parametrize("W,H", [(8, 5), (64, 9), (72, 16), (264, 20), (520, 11), (1928, 8)])
+def test_row_segment_lengths_identical(pkg, W, H):
+    """The row-segment kernel writes 32-bit words everywhere except at the two ends of a warp's segment (byte stores by
+    lanes 0 / 31): every segment length - one chunk per warp up to the whole row - must give the per-pixel kernel's bytes."""
+    L = pkg._lib
+    Wp, Hp, fov = 2048, 1024, 110
+    pano = synth.noise(Wp, Hp, 13)
+    yaws, pitches = [0, 90, 180, 270, 45], [35, 90, 160]   # five yaws: a group of four and a group of one per pitch
+    p = pkg.Projector(0, n_slots=2)
+    try:
+        p.set_option(L.OPT_MIRROR, 0)
+        want = p.project_image(pano, yaws, pitches, W, H, fov).copy()
+        p.set_option(L.OPT_MIRROR, 2)
+        for seg in (1, 2, 3, 4, 5, 7, 64):
+            p.set_option(L.OPT_SEG_CHUNKS, seg)
+            got = p.project_image(pano, yaws, pitches, W, H, fov)
+            assert np.array_equal(got, want), seg
+    finally:
+        p.close()
