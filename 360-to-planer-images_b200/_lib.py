@@ -83,6 +83,7 @@ OPT_SAMPLER, OPT_WARP_W, OPT_YAWS_PER_THREAD, OPT_COUNT_LAUNCHES, OPT_IMAGES_PER
 OPT_PARTIAL_UPLOAD = 8
 OPT_GPU_HUFFMAN, OPT_GPU_HUFFMAN_COUNT = 9, 10
 OPT_SEG_CHUNKS = 11
+OPT_SEAM_WRAP = 12
 
 _lib = None
 

@@ -127,6 +127,7 @@ struct p2p_ctx {
     int opt_seg_chunks = 4;    // chunks of 32 pixel pairs a warp of the row-segment kernel walks
     int opt_trig = 0;          // 0: NumPy-exact (SVML) acos / atan2, 1: own minimax fits
     int opt_interp = 0;
+    int opt_seam_wrap = 0;     // exact-bilinear mode only: interpolate across the 0 / 360 degree seam instead of clamping
     int opt_partial = 1;       // p2p_process_image transfers only the panorama rows its views can touch
     int opt_gpu_huffman = 1;   // JPEG inputs without restart markers: Huffman decoding on the device
     long long gpu_huffman_used = 0, gpu_huffman_fallback = 0;
@@ -530,6 +531,9 @@ int launch_project(p2p_ctx *ctx, Slot *const *sl, int nb, int n_yaw, const int32
     P.Wp_f = (float)s.Wp;
     P.Hp_f = (float)s.Hp;
     P.Umax = (float)(s.Wp - 1);
+    // exact-bilinear mode with the seam-wrap option: U is limited to [0, Wp) instead of [0, Wp - 1], so a pixel whose azimuth
+    // falls between the last and the first column interpolates between them (column Wp of the packed layout is column 0)
+    if (ctx->opt_interp == 1 && ctx->opt_seam_wrap) P.Umax = nextafterf((float)s.Wp, 0.0f);
     P.Vmax = (float)(s.Hp - 1);
     P.inv_Wp = (float)(1.0 / (double)s.Wp);
     P.inv_Hp = (float)(1.0 / (double)s.Hp);
@@ -1284,6 +1288,10 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "interp must be 0 (cv2 fixed point) or 1 (exact bilinear)");
             ctx->opt_interp = value;
             return P2P_OK;
+        case P2P_OPT_SEAM_WRAP:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "seam_wrap must be 0 or 1");
+            ctx->opt_seam_wrap = value;
+            return P2P_OK;
         case P2P_OPT_TRIG:
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "trig must be 0 (NumPy-exact) or 1 (minimax)");
             ctx->opt_trig = value;
@@ -1314,6 +1322,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_MIRROR: *value = ctx->opt_mirror; return P2P_OK;
         case P2P_OPT_SEG_CHUNKS: *value = ctx->opt_seg_chunks; return P2P_OK;
         case P2P_OPT_INTERP: *value = ctx->opt_interp; return P2P_OK;
+        case P2P_OPT_SEAM_WRAP: *value = ctx->opt_seam_wrap; return P2P_OK;
         case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
         case P2P_OPT_PARTIAL_UPLOAD: *value = ctx->opt_partial; return P2P_OK;
         case P2P_OPT_GPU_HUFFMAN: *value = ctx->opt_gpu_huffman; return P2P_OK;
@@ -2148,7 +2157,7 @@ int p2p_sample_with_maps(p2p_ctx *ctx, int slot, int yaw_shift, const float *U_h
     if (e == cudaSuccess) {
         dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
         sample_maps_kernel<<<grid, block, 0, s.stream>>>(s.d_rgba, s.pitch_tex, s.Wp, s.Hp, yaw_shift, d, d + n, W, H, d_o,
-                                                        ctx->opt_interp);
+                                                        ctx->opt_interp, ctx->opt_interp == 1 && ctx->opt_seam_wrap);
         ctx->launches++;
         e = cudaGetLastError();
     }

@@ -75,6 +75,10 @@ typedef enum p2p_option {
                                      subsequences, restart intervals as independent scans); the library's host decoder
                                      takes over when that does not converge; 0: always the host decoder */
     ,P2P_OPT_GPU_HUFFMAN_COUNT = 10 /* read-only: JPEG inputs whose Huffman stage ran on the device so far */
+    ,P2P_OPT_SEAM_WRAP = 12        /* exact-bilinear mode only (P2P_OPT_INTERP = 1).  0 (default): U is clipped to Wp - 1 like the
+                                     reference does (ref :172) - no interpolation across the 0 / 360 degree seam; 1: U runs over
+                                     [0, Wp) and a pixel between the last and the first panorama column blends the two (true wrap,
+                                     scipy's mode='grid-wrap'; the north-star's "edge / wrap mode") */
     ,P2P_OPT_SEG_CHUNKS = 11       /* row-segment kernel: chunks of 32 pixel pairs per warp (default 4, 1..64) */
     ,P2P_OPT_PARTIAL_UPLOAD = 8    /* 1 (default): p2p_process_image copies only the panorama rows its views can
                                      touch (p2p_view_row_range) over PCIe; 0: always the whole panorama */

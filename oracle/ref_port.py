@@ -72,8 +72,10 @@ def pitch_scalars(W: int, fov_deg, pitch_deg):
     return f, np.float32(np.cos(p)), np.float32(np.sin(p))
 
 
-def pitch_mapping(W: int, H: int, fov_deg, pitch_deg, pano_width: int, pano_height: int):
-    """(U, V) pitch map, ref ``precompute_pitch_mapping`` :114-175 via ``get_pitch_mapping`` :55-73."""
+def pitch_mapping(W: int, H: int, fov_deg, pitch_deg, pano_width: int, pano_height: int, seam_wrap: bool = False):
+    """(U, V) pitch map, ref ``precompute_pitch_mapping`` :114-175 via ``get_pitch_mapping`` :55-73.
+    ``seam_wrap`` (NOT the reference: the oracle of the exact-bilinear mode's wrap option) limits U to [0, Wp) instead of
+    the reference's [0, Wp - 1]."""
     fov_rad = np.radians(fov_deg)
     p = np.radians(pitch_deg)
     focal = (0.5 * W) / np.tan(fov_rad / 2)
@@ -95,7 +97,8 @@ def pitch_mapping(W: int, H: int, fov_deg, pitch_deg, pano_width: int, pano_heig
     phi = (np.arctan2(yr, xr) % (2 * np.pi)).astype(np.float32)
     U = (phi * pano_width) / (2 * np.pi)
     V = (theta * pano_height) / np.pi
-    U = np.clip(U, 0, pano_width - 1).astype(np.float32)
+    u_max = np.nextafter(np.float32(pano_width), np.float32(0)) if seam_wrap else pano_width - 1
+    U = np.clip(U, 0, u_max).astype(np.float32)
     V = np.clip(V, 0, pano_height - 1).astype(np.float32)
     return U, V
 

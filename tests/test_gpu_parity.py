@@ -423,6 +423,31 @@ def test_exact_bilinear_mode_against_scipy(pkg):
                         assert exact_fraction(out[i, j], want) >= 0.97
         with pytest.raises(pkg.P2PError):   # fractional yaws are only defined for the cv2 mode
             p.project_image(pano, [30], [90], W, H, fov)
+        # seam-wrap option: U runs over [0, Wp), pixels between the last and the first column blend the two
+        # (scipy mode='grid-wrap'); without it they are clamped to the last column like the reference's clip does
+        p.set_option(L.OPT_SEAM_WRAP, 1)
+        Wp2, Hp2 = 257, 129
+        pano2 = synth.noise(Wp2, Hp2, 3)
+        U2 = rng.uniform(0, Wp2, (64, 96)).astype(np.float32)
+        U2 = np.minimum(U2, np.nextafter(np.float32(Wp2), np.float32(0)))
+        U2[0, :] = np.linspace(Wp2 - 1, Wp2, 96, endpoint=False, dtype=np.float32)   # inside the seam interval
+        V2 = rng.uniform(0, Hp2 - 1, (64, 96)).astype(np.float32)
+        with p.slots(1) as (s,):
+            p.upload(s, pano2)
+            for shift in (0, 7, Wp2 - 1):
+                assert np.array_equal(p.sample_with_maps(s, shift, U2, V2),
+                                      eb.sample_view_exact(pano2, U2, V2, shift, seam_wrap=True)), shift
+        pano = synth.make("smooth", Wp, Hp, 0)
+        clamp_views = {}
+        for seam in (1, 0):
+            p.set_option(L.OPT_SEAM_WRAP, seam)
+            out = p.project_image(pano, [0, 90], [60, 90], W, H, fov)
+            for i, yw in enumerate([0, 90]):
+                for j, pt in enumerate([60, 90]):
+                    want = eb.project_view_exact(pano, yw, pt, W, H, fov, seam_wrap=bool(seam))
+                    assert np.abs(out[i, j].astype(np.int16) - want.astype(np.int16)).max() <= 1, (seam, yw, pt)
+            clamp_views[seam] = out.copy()
+        assert not np.array_equal(clamp_views[0], clamp_views[1])   # the seam column really is interpolated differently
         # and the default mode is untouched: it differs from the exact mode (5-bit fractions) on noise
         exact_view = p.project_image(pano, [0], [90], W, H, fov)[0, 0].copy()
         p.set_option(L.OPT_INTERP, 0)
