@@ -13,7 +13,7 @@ from . import _lib
 
 _lib.load()  # fail loudly: no CPU fallback
 
-from .engine import PinnedBuffer, Projector, pitch_constants, yaw_table  # noqa: E402
+from .engine import PinnedBuffer, Projector, host_assumptions, pitch_constants, warn_if_host_differs, yaw_table  # noqa: E402
 from .panorama_to_plane_pitch import (  # noqa: E402
     check_pitch,
     cli,

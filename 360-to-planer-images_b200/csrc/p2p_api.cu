@@ -12,6 +12,7 @@
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -1607,7 +1608,9 @@ int p2p_project_view_list(p2p_ctx *ctx, int slot, int n_views, const int32_t *ya
 // Packed rows [y0, y1] (inclusive, y1 <= Hp: row Hp is the clamp row) now hold data in slot `s` of size Wp x Hp: merge them
 // with the rows it held before (`was_valid`, old range) when both ranges touch - a panorama can be assembled from pieces
 // (p2p_upload_pano_rows, p2p_copy_pano_rows) - else the slot holds just the new piece.
-void merge_rows(Slot &s, bool was_valid, int old_Wp, int old_Hp, int old0, int old1, int y0, int y1) {
+static std::atomic<bool> peer_tried[64][64];   // peer access of (destination device, source device) has been requested
+
+static void merge_rows(Slot &s, bool was_valid, int old_Wp, int old_Hp, int old0, int old1, int y0, int y1) {
     if (was_valid && old_Wp == s.Wp && old_Hp == s.Hp && y0 <= old1 + 1 && y1 >= old0 - 1) {
         s.row0 = (old0 < y0) ? old0 : y0;
         s.row1 = (old1 > y1) ? old1 : y1;
@@ -1666,7 +1669,8 @@ int p2p_copy_pano_rows(p2p_ctx *dst, int dst_slot, p2p_ctx *src, int src_slot, i
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     cudaError_t e = cudaEventRecord(ev, a.stream);
     if (e == cudaSuccess) e = cudaSetDevice(dst->device);
-    if (e == cudaSuccess && dst->device != src->device) {
+    if (e == cudaSuccess && dst->device != src->device && dst->device < 64 && src->device < 64 &&
+        !peer_tried[dst->device][src->device].exchange(true)) {   // once per device pair and process
         int can = 0;
         if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
             cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);  // direct NVLink path; staged through the host otherwise

@@ -53,6 +53,65 @@ def yaw_table(pano_width: int, yaw_deg):
     return np.ascontiguousarray(ix, np.int32), np.ascontiguousarray(fx, np.int32), shift
 
 
+# Inputs on which NumPy's AVX-512 (Intel SVML) f32 arccos / arctan2 differ from the correctly rounded result, with the
+# bits SVML returns: a host whose NumPy reproduces all of them evaluates the reference's coordinates exactly like the kernel
+# does (P2P_OPT_TRIG = 0).  (bits of the inputs, bits of the result)
+_SVML_ACOS = [(0x3f4b5f9b, 0x3f27196e), (0x3f0d26ad, 0x3f7c9e37), (0xbf0cb1a5, 0x4009c542), (0x3f3f4266, 0x3f3a230f),
+              (0x3f18197c, 0x3f6f420f), (0xbd8356a4, 0x3fd146b7)]
+_SVML_ATAN2 = [(0xbf08228e, 0x3ef486e0, 0xbf56caa4), (0x3da43f1d, 0x3f4f9ef9, 0x3dc9dcc2), (0x3e2f4aa4, 0x3f2aa213, 0x3e80b676),
+               (0xbeae3612, 0x3e94d102, 0xbf5d2563), (0x3f5bde94, 0xbeb18192, 0x3ffa2b9f), (0x3ef1b780, 0xbec103ff, 0x400fa816)]
+PINNED_VERSIONS = {"numpy": "2.3", "cv2": "4.13"}   # what the bit / byte identity claims were checked against
+
+
+def host_assumptions() -> dict:
+    """What the bit-exact claims rest on, checked on THIS host (no GPU needed):
+
+    * ``numpy_svml``: NumPy evaluates f32 ``arccos`` / ``arctan2`` with the SVML routines the kernel restates (AVX-512
+      hosts).  Elsewhere the reference itself changes in the last ulp and the device output is within <= 1 LSB of it
+      instead of identical - ``P2P_OPT_TRIG`` then makes no difference to parity.
+    * ``numpy_nep50``: NumPy >= 2 scalar promotion (``phi + np.radians(int)`` is float64, ref :98); NumPy 1.x keeps float32
+      there and produces another yaw table.
+    * ``versions`` / ``pinned``: the byte-identical PNG / JPEG files and the JPEG decoder are pinned to OpenCV 4.13's bundled
+      zlib / libpng / libjpeg-turbo settings; another OpenCV may write different (equally valid) bytes.
+    """
+    u32 = np.uint32
+    az = np.array([a for a, _ in _SVML_ACOS], u32).view(np.float32)
+    ar = np.array([r for _, r in _SVML_ACOS], u32)
+    ty = np.array([y for y, _, _ in _SVML_ATAN2], u32).view(np.float32)
+    tx = np.array([x for _, x, _ in _SVML_ATAN2], u32).view(np.float32)
+    tr = np.array([r for _, _, r in _SVML_ATAN2], u32)
+    svml = bool(np.array_equal(np.arccos(az).view(u32), ar) and np.array_equal(np.arctan2(ty, tx).view(u32), tr))
+    nep50 = (np.float32(1) + np.radians(1)).dtype == np.float64
+    versions = {"numpy": np.__version__}
+    try:
+        import cv2
+
+        versions["cv2"] = cv2.__version__
+    except Exception:  # noqa: BLE001
+        versions["cv2"] = None
+    matches = {k: (versions.get(k) or "").startswith(v) for k, v in PINNED_VERSIONS.items()}
+    return {"numpy_svml": svml, "numpy_nep50": bool(nep50), "versions": versions, "pinned": dict(PINNED_VERSIONS),
+            "versions_match_pinned": matches}
+
+
+def warn_if_host_differs(log=None) -> dict:
+    """Log one warning per assumption this host does not meet (called once by the front end); returns the report."""
+    import logging
+
+    log = log or logging.getLogger(__name__)
+    rep = host_assumptions()
+    if not rep["numpy_svml"]:
+        log.warning("NumPy on this host does not use the AVX-512 SVML arccos / arctan2: outputs are within 1 LSB of the "
+                    "reference run here instead of bit-identical (see DESIGN.md section 2)")
+    if not rep["numpy_nep50"]:
+        log.warning("NumPy < 2 scalar promotion: the reference's yaw table differs on this host")
+    for k, ok in rep["versions_match_pinned"].items():
+        if not ok:
+            log.warning(f"{k} {rep['versions'].get(k)} differs from the version the byte-identity claims were checked "
+                        f"against ({PINNED_VERSIONS[k]}.x)")
+    return rep
+
+
 def jpeg_probe(data: bytes):
     """(W, H) if the device JPEG decoder handles this file, else None (read it with cv2.imread).  Headers only, no GPU."""
     w, h = C.c_int(), C.c_int()

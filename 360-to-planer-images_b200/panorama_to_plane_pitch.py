@@ -69,9 +69,16 @@ def set_devices(devices):
         set_device(devs[0])
 
 
+_host_checked = False
+
+
 def get_projector(device: int | None = None) -> _engine.Projector:
+    global _host_checked
     d = _default_device if device is None else int(device)
     with _projectors_lock:
+        if not _host_checked:   # once per process: say so if this host does not meet the bit-exactness assumptions
+            _host_checked = True
+            _engine.warn_if_host_differs(logging.getLogger())
         if d not in _projectors:
             _projectors[d] = _engine.Projector(d, n_slots=16)  # device buffers are allocated per slot on first use
         return _projectors[d]
@@ -209,11 +216,25 @@ def scatter_upload(projs, slots, pano):
     for r in range(n):
         if b[r] < b[r + 1]:
             projs[r].upload_rows(slots[r], pano, b[r], b[r + 1])
+    packed_end = lambda hi: hi + (1 if hi == Hp else 0)   # packed rows: the last piece carries the clamp row Hp as well
+    if n > 1 and (n & (n - 1)) == 0 and all(b[r] < b[r + 1] for r in range(n)):
+        # recursive doubling: log2(n) exchanges per device with the partner r ^ 2^k, which holds the adjacent block of
+        # 2^k pieces - n log2(n) peer copies (24 for 8 GPUs) instead of n (n - 1), the same bytes per device
+        have = [(b[r], b[r + 1]) for r in range(n)]
+        step = 1
+        while step < n:
+            nxt = list(have)
+            for r in range(n):
+                lo, hi = have[r ^ step]
+                projs[r].copy_pano_rows_from(slots[r], projs[r ^ step], slots[r ^ step], lo, packed_end(hi))
+                nxt[r] = (min(have[r][0], lo), max(have[r][1], hi))
+            have = nxt
+            step *= 2
+        return pano
     for r in range(n):
         for q in list(range(r + 1, n)) + list(range(r - 1, -1, -1)):   # outwards from the own piece: always contiguous
             if b[q] < b[q + 1]:
-                # packed rows: the last piece carries the clamp row Hp as well
-                projs[r].copy_pano_rows_from(slots[r], projs[q], slots[q], b[q], b[q + 1] + (1 if b[q + 1] == Hp else 0))
+                projs[r].copy_pano_rows_from(slots[r], projs[q], slots[q], b[q], packed_end(b[q + 1]))
     return pano
 
 

@@ -223,3 +223,14 @@ def test_slot_lease_keeps_the_slot_until_the_files_are_written(pkg):
     except RuntimeError:
         pass
     assert sorted(pool.free) == [0, 1, 2], "an exception must not leak the slot"
+
+
+def test_host_assumptions_report(pkg):
+    """The product's own host check: agrees with the oracle's SVML model on this host and reports versions."""
+    from oracle import svml_model
+
+    rep = pkg.host_assumptions()
+    assert rep["numpy_svml"] == svml_model.host_numpy_uses_svml()
+    assert rep["numpy_nep50"] is True            # NumPy >= 2 in this image
+    assert set(rep["versions"]) == {"numpy", "cv2"} and set(rep["versions_match_pinned"]) == {"numpy", "cv2"}
+    assert pkg.warn_if_host_differs() == rep
