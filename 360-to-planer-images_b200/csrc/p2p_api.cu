@@ -8,6 +8,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler is attached
@@ -96,6 +97,8 @@ struct Slot {
     p2pjdec::DevHuff *jd_tables = nullptr;    // [3]
     int32_t *jd_dc = nullptr;                 // [2][3][dc_stride]: DC differences, exclusive sums
     size_t jd_dc_cap = 0;
+    uint32_t *jd_tiles = nullptr;             // tile sums / offsets of the three-phase DC scan
+    size_t jd_tiles_cap = 0;
     unsigned long long *jd_tot_d = nullptr;   // scan totals (device) [4]
     struct JdFlags { int changed[8]; int bad; int out_of_range; unsigned long long total; } *jd_flags_h = nullptr, *jd_flags_d = nullptr;  // mapped
     uint8_t *jd_sub = nullptr;                // subsequence layout + first subsequence of every restart interval
@@ -857,7 +860,15 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     }
     G.dc_stride = (max_dc + 3) & ~3u;
     const size_t nsub4 = ((size_t)G.n_sub + 3) & ~(size_t)3;
-    DevHuff T[3];
+    // device tables: the three per-component tables, then the unified look-up of the synchronisation rounds
+    struct DevTables {
+        DevHuff T[3];
+        SyncLut L;
+    };
+    std::vector<unsigned char> tables_mem(sizeof(DevTables));
+    DevTables &DT = *reinterpret_cast<DevTables *>(tables_mem.data());
+    DevHuff *T = DT.T;
+    for (int c = 0; c < 3; ++c) build_sync_lut(P.dc[P.td[c]], P.ac[P.ta[c]], DT.L.e[c][0], DT.L.e[c][1], DT.L.w[c][0], DT.L.w[c][1]);
     for (int c = 0; c < 3; ++c) {
         const HuffTable &d = P.dc[P.td[c]], &a = P.ac[P.ta[c]];
         memcpy(T[c].dc_look, d.look, sizeof(d.look));
@@ -874,32 +885,41 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     const unsigned sgrid = (G.n_sub + 127) / 128;
     SubSeq *d_sub = nullptr;
     uint32_t *d_ivl_first = nullptr;
+    const SyncLut *d_lut = nullptr;
+    bool fast_rounds = true;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
+        fast_rounds = ctx->opt_gpu_huffman != 2;   // 2 = the plain rounds (tables in global memory), the tests' yardstick
         CK(cudaSetDevice(ctx->device));
         const size_t sub_bytes = ((size_t)G.n_sub * sizeof(SubSeq) + 15) & ~(size_t)15;
         int rc = ensure_grow(ctx, &s.jd_stream, &s.jd_stream_cap, n_words * 4);
         if (!rc) rc = ensure_grow(ctx, &s.jd_states, &s.jd_states_cap, 2 * (size_t)G.n_sub * sizeof(unsigned long long));
         if (!rc) rc = ensure_grow(ctx, &s.jd_nblk, &s.jd_nblk_cap, 2 * nsub4 * sizeof(uint32_t));
         if (!rc) rc = ensure(ctx, &s.jd_dc, &s.jd_dc_cap, 2 * 3 * (size_t)G.dc_stride * sizeof(int32_t));
+        if (!rc) rc = ensure(ctx, &s.jd_tiles, &s.jd_tiles_cap, 2 * 3 * ((((size_t)G.dc_stride + 4095) / 4096 + 3) & ~(size_t)3) * sizeof(uint32_t));
         if (!rc) rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
         if (!rc) rc = ensure_grow(ctx, &s.jd_sub, &s.jd_sub_cap, sub_bytes + ((size_t)n_ivl + 1) * sizeof(uint32_t));
         if (rc) return rc;
         d_sub = reinterpret_cast<SubSeq *>(s.jd_sub);
         d_ivl_first = reinterpret_cast<uint32_t *>(s.jd_sub + sub_bytes);
-        if (!s.jd_tables) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tables), 3 * sizeof(DevHuff)));
+        if (!s.jd_tables) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tables), sizeof(DevTables)));
         if (!s.jd_tot_d) CK(cudaMalloc(reinterpret_cast<void **>(&s.jd_tot_d), 4 * sizeof(unsigned long long)));
         int frc = ensure_jd_flags(ctx, s);
         if (frc) return frc;
         CK(cudaMemcpyAsync(s.jd_stream, w, n_words * 4, cudaMemcpyHostToDevice, st));
         // the tables below live in pageable memory: cudaMemcpyAsync stages them before it returns
-        CK(cudaMemcpyAsync(s.jd_tables, T, sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.jd_tables, &DT, sizeof(DevTables), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_sub, subs.data(), (size_t)G.n_sub * sizeof(SubSeq), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_ivl_first, ivl_first.data(), ((size_t)n_ivl + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(s.jd_coef_d, 0, I.n_coef * sizeof(int16_t), st));
         s.jd_flags_h->bad = 0;
-        huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
-                                              s.jd_nblk, 1, &s.jd_flags_d->changed[0]);
+        d_lut = reinterpret_cast<const SyncLut *>(reinterpret_cast<const unsigned char *>(s.jd_tables) + offsetof(DevTables, L));
+        if (fast_rounds)
+            huff_sync_fast_kernel<<<sgrid, kSyncThreads, 0, st>>>(s.jd_stream, s.jd_tables, d_lut, G, d_sub, s.jd_states,
+                                                                 s.jd_states + G.n_sub, s.jd_nblk, 1, &s.jd_flags_d->changed[0]);
+        else
+            huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states, s.jd_states + G.n_sub,
+                                                  s.jd_nblk, 1, &s.jd_flags_d->changed[0]);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -913,8 +933,13 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
             // decides convergence is the one of the LAST round of the batch
             for (int r = 0; r < kRoundsPerCheck; ++r) {
                 s.jd_flags_h->changed[r] = 0;   // nothing of this slot is running: the stream was drained above
-                huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states,
-                                                      s.jd_states + G.n_sub, s.jd_nblk, 0, &s.jd_flags_d->changed[r]);
+                if (fast_rounds)
+                    huff_sync_fast_kernel<<<sgrid, kSyncThreads, 0, st>>>(s.jd_stream, s.jd_tables, d_lut, G, d_sub, s.jd_states,
+                                                                         s.jd_states + G.n_sub, s.jd_nblk, 0,
+                                                                         &s.jd_flags_d->changed[r]);
+                else
+                    huff_sync_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, s.jd_states,
+                                                          s.jd_states + G.n_sub, s.jd_nblk, 0, &s.jd_flags_d->changed[r]);
             }
             ctx->launches += kRoundsPerCheck;
             CK(cudaGetLastError());
@@ -941,12 +966,26 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
     CK(cudaSetDevice(ctx->device));
     int32_t *dcdiff = s.jd_dc;
     uint32_t *dcsum = reinterpret_cast<uint32_t *>(s.jd_dc + 3 * (size_t)G.dc_stride);
-    huff_write_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, d_ivl_first, s.jd_states, s.jd_nblk + nsub4,
-                                           s.jd_coef_d, dcdiff, &s.jd_flags_d->out_of_range);
+    if (fast_rounds)
+        huff_write_fast_kernel<<<sgrid, kSyncThreads, 0, st>>>(s.jd_stream, s.jd_tables, d_lut, G, d_sub, d_ivl_first, s.jd_states,
+                                                              s.jd_nblk + nsub4, s.jd_coef_d, dcdiff, &s.jd_flags_d->out_of_range);
+    else
+        huff_write_kernel<<<sgrid, 128, 0, st>>>(s.jd_stream, s.jd_tables, G, d_sub, d_ivl_first, s.jd_states, s.jd_nblk + nsub4,
+                                               s.jd_coef_d, dcdiff, &s.jd_flags_d->out_of_range);
     // per component: exclusive sums of the DC differences in scan order (mod 2^32 arithmetic = two's complement sums)
     CK(cudaMemcpyAsync(s.jd_nblk, G.dc_count, 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));  // reuse as n_per_image
-    p2pjpeg::jpeg_scan_kernel<<<3, 1024, 0, st>>>(reinterpret_cast<const uint32_t *>(dcdiff), dcsum, s.jd_nblk, 0u,
-                                                  (size_t)G.dc_stride, s.jd_tot_d);
+    {   // three-phase scan over the whole GPU (the luma plane of an 8K file has 524,288 differences)
+        const uint32_t n_tiles = (G.dc_stride + 4095u) / 4096u;
+        const size_t tiles_stride = ((size_t)n_tiles + 3) & ~(size_t)3;
+        uint32_t *tile_sums = s.jd_tiles, *tile_offs = s.jd_tiles + 3 * tiles_stride;
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(dcdiff);
+        p2pjpeg::scan_tile_sums_kernel<<<dim3(n_tiles, 3), 1024, 0, st>>>(in, s.jd_nblk, 0u, (size_t)G.dc_stride, tile_sums,
+                                                                         tiles_stride);
+        p2pjpeg::jpeg_scan_kernel<<<3, 1024, 0, st>>>(tile_sums, tile_offs, nullptr, n_tiles, tiles_stride, s.jd_tot_d);
+        p2pjpeg::scan_tiles_apply_kernel<<<dim3(n_tiles, 3), 1024, 0, st>>>(in, dcsum, s.jd_nblk, 0u, (size_t)G.dc_stride,
+                                                                           tile_offs, tiles_stride);
+        ctx->launches += 2;
+    }
     huff_dc_kernel<<<dim3((G.dc_stride + 255) / 256, 3), 256, 0, st>>>(dcdiff, dcsum, G, s.jd_coef_d);
     ctx->launches += 3;
     CK(cudaGetLastError());
@@ -1236,6 +1275,7 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.jd_nblk);
         cudaFree(s.jd_tables);
         cudaFree(s.jd_dc);
+        cudaFree(s.jd_tiles);
         cudaFree(s.jd_tot_d);
         cudaFree(s.jd_sub);
         if (s.jd_flags_h) cudaFreeHost(s.jd_flags_h);
@@ -1302,7 +1342,7 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             ctx->opt_partial = value;
             return P2P_OK;
         case P2P_OPT_GPU_HUFFMAN:
-            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "gpu_huffman must be 0 or 1");
+            if (value < 0 || value > 2) return fail(ctx, P2P_ERR_INVALID, "gpu_huffman must be 0, 1 or 2");
             ctx->opt_gpu_huffman = value;
             return P2P_OK;
 

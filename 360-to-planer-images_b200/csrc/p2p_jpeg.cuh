@@ -336,6 +336,85 @@ jpeg_scan_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, co
     if (threadIdx.x == 0) total[img] = s_carry;
 }
 
+// The same scan for long arrays in three launches that use the whole GPU instead of one CTA per image:
+//   scan_tile_sums_kernel   sum of every 4096-item tile            (grid: tiles x images)
+//   jpeg_scan_kernel        exclusive scan of the tile sums        (one CTA per image, a few hundred items)
+//   scan_tiles_apply_kernel exclusive scan inside every tile + the tile's offset
+// (the DC predictions of an 8192 x 4096 JPEG file are 524,288 differences per luma plane: 153 us in one CTA, ~15 us here)
+__global__ void __launch_bounds__(1024)
+scan_tile_sums_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ n_per_image, uint32_t n_fixed, size_t stride,
+                      uint32_t *__restrict__ tile_sums, size_t tiles_stride) {
+    __shared__ uint32_t s_warp[32];
+    const int img = blockIdx.y;
+    const uint32_t n = n_per_image ? n_per_image[img] : n_fixed;
+    const uint32_t *src = in + (size_t)img * stride;
+    const uint32_t i0 = blockIdx.x * 4096u + threadIdx.x * 4u;
+    uint32_t sum = 0;
+    if (i0 + 3u < n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(src + i0);
+        sum = v.x + v.y + v.z + v.w;
+    } else {
+        if (i0 < n) sum += src[i0];
+        if (i0 + 1u < n) sum += src[i0 + 1u];
+        if (i0 + 2u < n) sum += src[i0 + 2u];
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t t = __reduce_add_sync(0xffffffffu, s_warp[threadIdx.x]);
+        if (threadIdx.x == 0) tile_sums[(size_t)img * tiles_stride + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_tiles_apply_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, const uint32_t *__restrict__ n_per_image,
+                        uint32_t n_fixed, size_t stride, const uint32_t *__restrict__ tile_offs, size_t tiles_stride) {
+    __shared__ uint32_t s_warp[32];
+    const int img = blockIdx.y;
+    const uint32_t n = n_per_image ? n_per_image[img] : n_fixed;
+    const uint32_t *src = in + (size_t)img * stride;
+    uint32_t *dst = out + (size_t)img * stride;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i0 = blockIdx.x * 4096u + threadIdx.x * 4u;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 + 3u < n) {
+        v = *reinterpret_cast<const uint4 *>(src + i0);
+    } else {
+        if (i0 < n) v.x = src[i0];
+        if (i0 + 1u < n) v.y = src[i0 + 1u];
+        if (i0 + 2u < n) v.z = src[i0 + 2u];
+    }
+    const uint32_t sum = v.x + v.y + v.z + v.w;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t excl = tile_offs[(size_t)img * tiles_stride + blockIdx.x] + (inc - sum) + (warp ? s_warp[warp - 1] : 0u);
+    const uint4 o4 = make_uint4(excl, excl + v.x, excl + v.x + v.y, excl + v.x + v.y + v.z);
+    if (i0 + 3u < n) {
+        *reinterpret_cast<uint4 *>(dst + i0) = o4;
+    } else {
+        if (i0 < n) dst[i0] = o4.x;
+        if (i0 + 1u < n) dst[i0 + 1u] = o4.y;
+        if (i0 + 2u < n) dst[i0 + 2u] = o4.z;
+    }
+}
+
 struct BitSink {
     uint32_t *words;
     unsigned long long acc;   // low `n` bits are pending (the first word starts with the offset's zero bits)

@@ -460,6 +460,57 @@ struct DevHuff {                 // one per component: its DC and AC table
     uint8_t ac_vals[256];
 };
 
+// Synchronisation rounds only need to know, per code word, how many bits it consumes (code + value bits) and how far it
+// moves the zigzag index: one 16-bit entry per 10-bit window, [component][0 = DC, 1 = AC]: consumed | advance << 5
+// (advance: 1 for a DC symbol, run + 1 for a coefficient, 16 for ZRL, 64 = end of block); 0 = the code is longer than 10
+// bits (or no code): the general path.  12 KB, staged in shared memory by every CTA: DC and AC symbols, ZRL and EOB then
+// take ONE code path - the lanes of a warp sit in different decoder states, and with separate paths per state an iteration
+// used to cost the sum of all of them.
+struct SyncLut {
+    uint16_t e[3][2][1 << kFastBits];
+    // the same windows for the write pass, which also needs the code length and the size of the value on their own:
+    // length | size << 5 | advance << 9
+    uint32_t w[3][2][1 << kFastBits];
+};
+
+inline void build_sync_lut(const HuffTable &dc, const HuffTable &ac, uint16_t *dc_out, uint16_t *ac_out, uint32_t *dc_w,
+                           uint32_t *ac_w) {
+    auto symbol = [](const HuffTable &t, int win10, int mask, int &len) -> int {
+        const uint16_t e = t.look[win10 >> (kFastBits - 9)];
+        if (e) {
+            len = e >> 8;
+            return e & 0xFF;
+        }
+        if (win10 <= t.maxcode[10]) {   // jdhuff.c: the first length whose largest code is not below the prefix
+            len = 10;
+            return t.vals[(win10 + t.valoff[10]) & mask];
+        }
+        return -1;
+    };
+    for (int i = 0; i < (1 << kFastBits); ++i) {
+        int len = 0;
+        int s = symbol(dc, i, 15, len);
+        if (s >= 0) {
+            s = (s > 15) ? 15 : s;
+            dc_out[i] = (uint16_t)((len + s) | (1 << 5));
+            dc_w[i] = (uint32_t)len | ((uint32_t)s << 5) | (1u << 9);
+        } else {
+            dc_out[i] = 0;
+            dc_w[i] = 0;
+        }
+        const int rs = symbol(ac, i, 255, len);
+        if (rs >= 0) {
+            const int r = rs >> 4, sz = rs & 15;
+            const int adv = sz ? r + 1 : (r == 15 ? 16 : 64);
+            ac_out[i] = (uint16_t)((len + sz) | (adv << 5));
+            ac_w[i] = (uint32_t)len | ((uint32_t)sz << 5) | ((uint32_t)adv << 9);
+        } else {
+            ac_out[i] = 0;
+            ac_w[i] = 0;
+        }
+    }
+}
+
 struct HuffGeom {
     uint32_t n_bits;             // bits of the destuffed scan
     uint32_t n_sub;              // subsequences
@@ -648,6 +699,99 @@ huff_sync_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, 
     endst[i] = pack_state(st);
 }
 
+// The same rounds with the stream and the unified look-up staged in shared memory (the default; the kernel above is the
+// plain form, kept as the yardstick of the tests).  A CTA owns 128 consecutive subsequences = one contiguous piece of the
+// stream (<= 4096 + 3 words, skewed by one word per 32 so that lanes at the same offset of their subsequences hit different
+// banks); CTAs in which no subsequence has to move leave before staging anything.
+constexpr int kSyncThreads = 128;
+constexpr int kSyncWords = kSyncThreads * (kSubBits / 32) + 4;
+
+__global__ void __launch_bounds__(kSyncThreads)
+huff_sync_fast_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const SyncLut *__restrict__ lut,
+                      const HuffGeom G, const SubSeq *__restrict__ sub, unsigned long long *__restrict__ start,
+                      unsigned long long *__restrict__ endst, uint32_t *__restrict__ nblk, int first_round,
+                      int *__restrict__ changed) {
+    __shared__ uint16_t s_lut[3 * 2 * (1 << kFastBits)];
+    __shared__ uint32_t s_w[kSyncWords + kSyncWords / 32 + 2];
+    const uint32_t i0 = blockIdx.x * kSyncThreads, i = i0 + threadIdx.x;
+    bool active = false;
+    SubSeq q;
+    q.begin = q.end = q.ivl = q.first = 0;
+    HState st;
+    st.pos = 0;
+    st.b = st.z = 0;
+    unsigned long long from = 0;
+    if (i < G.n_sub) {
+        q = sub[i];
+        if (first_round) {
+            st.pos = q.begin;
+            from = pack_state(st);
+            active = true;
+        } else if (!q.first) {           // the first subsequence of an interval starts in the true state: never moves
+            from = endst[i - 1];
+            if (from != start[i]) {
+                st = unpack_state(from);
+                active = true;
+            }
+        }
+    }
+    if (!__syncthreads_or(active)) return;
+    // stage the look-up (12 KB) and this CTA's piece of the stream
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lut);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(s_lut);
+        for (int k = threadIdx.x; k < 3 * 2 * (1 << kFastBits) / 2; k += kSyncThreads) dst[k] = __ldg(src + k);
+    }
+    const uint32_t i_last = (i0 + kSyncThreads <= G.n_sub ? i0 + kSyncThreads : G.n_sub) - 1;
+    const uint32_t wlo = sub[i0].begin >> 5;
+    const uint32_t whi = (sub[i_last].end >> 5) + 3;          // a code word may run 27 bits past the end: two more words
+    const uint32_t nw = (whi - wlo < (uint32_t)kSyncWords) ? whi - wlo : (uint32_t)kSyncWords;
+    for (uint32_t k = threadIdx.x; k < nw; k += kSyncThreads) s_w[k + (k >> 5)] = __ldg(w + wlo + k);
+    __syncthreads();
+    if (!active) return;
+    uint32_t done = 0;
+    int comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
+    while (st.pos < q.end) {
+        const uint32_t j = (st.pos >> 5) - wlo;
+        uint32_t win;
+        if (j + 1 < nw) {
+            win = __funnelshift_l(s_w[j + 1 + ((j + 1) >> 5)], s_w[j + (j >> 5)], st.pos & 31);
+        } else {
+            win = window32(w, st.pos);   // (cannot happen for a piece within kSyncWords; kept as a guard)
+        }
+        const uint32_t e = s_lut[((comp << 1) + (st.z != 0)) * (1 << kFastBits) + (win >> (32 - kFastBits))];
+        if (e) {
+            st.pos += e & 31u;
+            st.z += (int)(e >> 5);
+        } else {   // a code longer than 10 bits (or none): the general path, one symbol
+            const DevHuff &H = T[comp];
+            int len;
+            if (st.z == 0) {
+                int s = slow_symbol(win, H.dc_maxcode, H.dc_valoff, H.dc_vals, 15, len);
+                s = (s < 0) ? 0 : (s > 15) ? 15 : s;
+                st.pos += (uint32_t)(len + s);
+                st.z = 1;
+            } else {
+                int rs = slow_symbol(win, H.ac_maxcode, H.ac_valoff, H.ac_vals, 255, len);
+                rs = (rs < 0) ? 0 : rs;
+                const int r = rs >> 4, s = rs & 15;
+                st.z += s ? r + 1 : (r == 15 ? 16 : 64);
+                st.pos += (uint32_t)(len + s);
+            }
+        }
+        if (st.z >= 64) {   // block complete
+            st.z = 0;
+            st.b = (st.b + 1 == G.nb) ? 0 : st.b + 1;
+            comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
+            ++done;
+        }
+    }
+    start[i] = from;
+    nblk[i] = done;
+    endst[i] = pack_state(st);
+    if (!first_round) *changed = 1;
+}
+
 // blkoff = exclusive prefix sum of nblk over ALL subsequences; ivl_first[k] = first subsequence of interval k
 // (ivl_first[n_ivl] = n_sub).  An interval must hold at least its quota of blocks (the padding bits at its end may
 // decode as a few more).
@@ -680,6 +824,107 @@ huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T,
     huff_decode_range<true>(w, T, G, st, q.end, blk, limit, coef, dcdiff, damaged);
     // the last block of an interval must end inside it: libjpeg feeds zero bits past a marker, this reader would
     // continue into the next interval
+    if (i + 1 == ivl_first[q.ivl + 1] && st.pos > q.end) damaged = true;
+    if (damaged) *damaged_flag = 1;
+}
+
+// The write pass with the stream and the (length, size, advance) look-up staged in shared memory like the fast rounds.
+// Same trajectory, same stores, same "damaged" conditions as huff_decode_range<true>.
+__global__ void __launch_bounds__(kSyncThreads)
+huff_write_fast_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const SyncLut *__restrict__ lut,
+                       const HuffGeom G, const SubSeq *__restrict__ sub, const uint32_t *__restrict__ ivl_first,
+                       const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
+                       int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag) {
+    __shared__ uint32_t s_lut[3 * 2 * (1 << kFastBits)];
+    __shared__ uint32_t s_w[kSyncWords + kSyncWords / 32 + 2];
+    const uint32_t i0 = blockIdx.x * kSyncThreads, i = i0 + threadIdx.x;
+    for (int k = threadIdx.x; k < 3 * 2 * (1 << kFastBits); k += kSyncThreads) s_lut[k] = __ldg(&lut->w[0][0][0] + k);
+    const uint32_t i_last = (i0 + kSyncThreads <= G.n_sub ? i0 + kSyncThreads : G.n_sub) - 1;
+    const uint32_t wlo = sub[i0].begin >> 5;
+    const uint32_t whi = (sub[i_last].end >> 5) + 3;
+    const uint32_t nw = (whi - wlo < (uint32_t)kSyncWords) ? whi - wlo : (uint32_t)kSyncWords;
+    for (uint32_t k = threadIdx.x; k < nw; k += kSyncThreads) s_w[k + (k >> 5)] = __ldg(w + wlo + k);
+    __syncthreads();
+    if (i >= G.n_sub) return;
+    const SubSeq q = sub[i];
+    HState st = unpack_state(start[i]);
+    const uint32_t first_blk = q.ivl * G.ivl_blocks;
+    uint32_t blk = first_blk + (blkoff[i] - blkoff[ivl_first[q.ivl]]);
+    const uint32_t blk_limit = (first_blk + G.ivl_blocks <= G.total_blocks) ? first_blk + G.ivl_blocks : G.total_blocks;
+    bool damaged = false;
+    int16_t *cur = nullptr;
+    int comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
+    uint32_t dc_idx = 0;
+    auto locate = [&]() {   // address of the block being written, index of its DC difference
+        const uint32_t mcu = blk / (uint32_t)G.nb;
+        const int k = (int)(blk - mcu * (uint32_t)G.nb);
+        const uint32_t my = mcu / (uint32_t)G.mcux, mx = mcu - my * (uint32_t)G.mcux;
+        const int c = (k < G.n_luma) ? 0 : k - G.n_luma + 1;
+        const uint32_t by = c ? my : my * G.vmax + k / G.hmax, bx = c ? mx : mx * G.hmax + k % G.hmax;
+        cur = coef + G.coef_off[c] + ((size_t)by * G.bw[c] + bx) * 64;
+        dc_idx = c ? mcu : mcu * (uint32_t)G.n_luma + (uint32_t)k;
+    };
+    if (blk < blk_limit) locate();
+    while (st.pos < q.end) {
+        if (blk >= blk_limit) break;   // the interval's quota is done: the rest are padding bits
+        const uint32_t j = (st.pos >> 5) - wlo;
+        const uint32_t win = (j + 1 < nw) ? __funnelshift_l(s_w[j + 1 + ((j + 1) >> 5)], s_w[j + (j >> 5)], st.pos & 31)
+                                          : window32(w, st.pos);
+        const uint32_t e = s_lut[((comp << 1) + (st.z != 0)) * (1 << kFastBits) + (win >> (32 - kFastBits))];
+        if (e) {
+            const int len = (int)(e & 31u), sz = (int)((e >> 5) & 15u), adv = (int)(e >> 9);
+            const int val = sz ? extend_bits((win << len) >> (32 - sz), sz) : 0;
+            if (st.z == 0) {
+                if (sz > 11) damaged = true;
+                dcdiff[(size_t)comp * G.dc_stride + dc_idx] = val;
+                st.z = 1;
+            } else {
+                const int zc = st.z + adv - 1;          // zigzag position of this coefficient
+                if (sz) {
+                    if (zc > 63) damaged = true;
+                    else cur[kNatDev[zc]] = (int16_t)val;
+                }
+                st.z += adv;
+            }
+            st.pos += (uint32_t)(len + sz);
+        } else {   // a code longer than 10 bits (or none): the general path, one symbol
+            const DevHuff &H = T[comp];
+            int len;
+            if (st.z == 0) {
+                int s = slow_symbol(win, H.dc_maxcode, H.dc_valoff, H.dc_vals, 15, len);
+                if (s < 0 || s > 11) damaged = true;
+                s = (s < 0) ? 0 : (s > 15) ? 15 : s;
+                dcdiff[(size_t)comp * G.dc_stride + dc_idx] = s ? extend_bits((win << len) >> (32 - s), s) : 0;
+                st.pos += (uint32_t)(len + s);
+                st.z = 1;
+            } else {
+                int rs = slow_symbol(win, H.ac_maxcode, H.ac_valoff, H.ac_vals, 255, len);
+                if (rs < 0) {
+                    damaged = true;
+                    rs = 0;
+                }
+                const int r = rs >> 4, s = rs & 15;
+                if (s == 0) {
+                    st.z = (r == 15) ? st.z + 16 : 64;
+                    st.pos += (uint32_t)len;
+                } else {
+                    st.z += r;
+                    if (st.z > 63) damaged = true;
+                    if (st.z < 64) cur[kNatDev[st.z]] = (int16_t)extend_bits((win << len) >> (32 - s), s);
+                    st.z += 1;
+                    st.pos += (uint32_t)(len + s);
+                }
+            }
+        }
+        if (st.z >= 64) {   // block complete
+            st.z = 0;
+            st.b = (st.b + 1 == G.nb) ? 0 : st.b + 1;
+            comp = (st.b < G.n_luma) ? 0 : st.b - G.n_luma + 1;
+            ++blk;
+            if (blk < blk_limit) locate();
+        }
+    }
+    // the last block of an interval must end inside it (see huff_write_kernel)
     if (i + 1 == ivl_first[q.ivl + 1] && st.pos > q.end) damaged = true;
     if (damaged) *damaged_flag = 1;
 }

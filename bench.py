@@ -296,9 +296,10 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     # most, so the L2 still holds one image's cross-view working set most of the time.  The timed region is bracketed by
     # ONE event pair on stream 0: the other streams wait for the start event, stream 0 waits for their end events.
     n_streams = max(1, min(args.streams, BATCH))
+    own_streams = [proj.get_stream(i) for i in res_slots]   # given back after the resident region
     for i in res_slots:
         if i >= n_streams:
-            proj.set_stream(i, proj.get_stream(i % n_streams))
+            proj.set_stream(i, own_streams[i % n_streams])
     n_distinct = min(BATCH, args.distinct)
     host = [synth.noise(WP, HP, rank * BATCH + i) for i in range(n_distinct)]
     d_stage = torch.empty((HP, WP, 3), dtype=torch.uint8, device=dev)
@@ -354,6 +355,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         timed_steps(1)
         serial_ms = timed_steps(min(5, args.steps)) / (min(5, args.steps) * BATCH)
         n_streams = ns
+    for i in res_slots:   # every slot back on its own stream: the later legs (files flow) borrow these slots concurrently
+        proj.set_stream(i, own_streams[i])
     ms_per_step = ms_total / args.steps
     value = world * args.steps * BATCH * PX_PER_IMAGE / (ms_total * 1e-3) / 1e6
     launch_ms = ms_total / (args.steps * BATCH)
@@ -539,7 +542,7 @@ def oracle_check(proj, pano, seed):
             else "tolerance (host NumPy does not take the SVML path: the reference itself differs in the last ulp here)"}
 
 
-def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=8, n_thr=4):
+def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=32, n_thr=8):
     """Files to files on every rank: an 8192x4096 JPEG file in host memory -> the 12 views as files in page-locked host
     memory; Huffman decode, IDCT, projection and encode all on the GPU, n_thr images in flight per rank.  Whole-job
     Mpix/s = all ranks' images / the slowest rank's time."""

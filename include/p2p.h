@@ -73,7 +73,9 @@ typedef enum p2p_option {
                                      reference bit for bit there; 1: table-free minimax fits (<= 1.2 ulp) */
     ,P2P_OPT_GPU_HUFFMAN = 9       /* 1 (default): JPEG inputs are Huffman-decoded on the device (self-synchronising
                                      subsequences, restart intervals as independent scans); the library's host decoder
-                                     takes over when that does not converge; 0: always the host decoder */
+                                     takes over when that does not converge; 0: always the host decoder; 2: the device
+                                     stage with its plain synchronisation rounds (tables in global memory - the yardstick
+                                     the shared-memory rounds of mode 1 are tested against) */
     ,P2P_OPT_GPU_HUFFMAN_COUNT = 10 /* read-only: JPEG inputs whose Huffman stage ran on the device so far */
     ,P2P_OPT_SEAM_WRAP = 12        /* exact-bilinear mode only (P2P_OPT_INTERP = 1).  0 (default): U is clipped to Wp - 1 like the
                                      reference does (ref :172) - no interpolation across the 0 / 360 degree seam; 1: U runs over

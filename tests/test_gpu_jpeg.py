@@ -270,10 +270,15 @@ def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
         proj.set_option(L.OPT_GPU_HUFFMAN, 0)
         try:
             host = proj.decode_jpeg(data)
+            assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1
+            # mode 2: the device stage with its plain rounds / write pass (tables in global memory), the yardstick of the
+            # shared-memory kernels that mode 1 runs
+            proj.set_option(L.OPT_GPU_HUFFMAN, 2)
+            plain = proj.decode_jpeg(data)
+            assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 2
         finally:
             proj.set_option(L.OPT_GPU_HUFFMAN, 1)
-        assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1
-        assert np.array_equal(host, ref)
+        assert np.array_equal(host, ref) and np.array_equal(plain, ref)
     # white noise needs ~80 synchronisation rounds; restart intervals are independent scans with known start states
     noise = synth.noise(1024, 512, 1)
     for params in ([cv2.IMWRITE_JPEG_QUALITY, 95], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 4],
@@ -283,5 +288,11 @@ def test_device_huffman_stage_is_used_and_equals_host_stage(pkg, proj):
         img = noise if len(params) == 2 else textured
         data = cv2.imencode(".jpg", img, params)[1].tobytes()
         n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
-        assert np.array_equal(proj.decode_jpeg(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)), params
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(proj.decode_jpeg(data), ref), params
         assert proj.get_option(L.OPT_GPU_HUFFMAN_COUNT) == n0 + 1, params
+        proj.set_option(L.OPT_GPU_HUFFMAN, 2)
+        try:
+            assert np.array_equal(proj.decode_jpeg(data), ref), params
+        finally:
+            proj.set_option(L.OPT_GPU_HUFFMAN, 1)
