@@ -13,8 +13,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 ROOT = PKG_DIR.parent
 SOURCES = [PKG_DIR / "csrc" / "p2p_api.cu"]
-HEADERS = [PKG_DIR / "csrc" / "p2p_kernels.cuh", PKG_DIR / "csrc" / "svml14_tables.inc", PKG_DIR / "csrc" / "p2p_jpeg.cuh",
-           PKG_DIR / "csrc" / "p2p_jpeg_host.cuh", PKG_DIR / "csrc" / "p2p_jpegdec.cuh", PKG_DIR / "csrc" / "p2p_png.cuh", ROOT / "include" / "p2p.h"]
+HEADERS = sorted(p for p in (PKG_DIR / "csrc").iterdir() if p.suffix in (".cuh", ".inl", ".inc")) + [ROOT / "include" / "p2p.h"]
 OUT = PKG_DIR / "libp2p_b200.so"
 
 NVCC_FLAGS = [
