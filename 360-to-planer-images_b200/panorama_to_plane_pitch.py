@@ -566,6 +566,12 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
         # the host Huffman stage of a JPEG input runs on the worker thread: as many images in flight as there are workers
         n_in = max(1, min(int(inflight) if inflight else num_workers, proj.n_slots - 1))
         jpeg_out = _is_jpeg(output_format)
+        if jpeg_out or str(output_format).lower() == "png":
+            # every image in flight pins a file buffer of n_views x (W x H x 4 + 4096) bytes on its slot (plus the
+            # encoders' device scratch): keep the total under a budget instead of running out of memory mid-folder
+            per_slot = len(yaw_angles) * len(pitch_angles) * (W * H * 4 + 4096)
+            budget = float(os.environ.get("P2P_PINNED_BUDGET_GB", "8")) * 2 ** 30
+            n_in = max(1, min(n_in, int(budget // max(1, per_slot))))
 
         def one(f, writers):
             # the slot stays leased until this image's files are on disk (written straight from its page-locked buffer)

@@ -357,3 +357,52 @@ def test_row_segment_lengths_identical(pkg, W, H):
             assert np.array_equal(got, want), seg
     finally:
         p.close()
+
+
+def test_integration_md_multi_gpu_snippet_runs(pkg):
+    """The view-list / split snippet printed in INTEGRATION.md, executed verbatim (two contexts on device 0 play two GPUs;
+    with >= 2 devices the second context lives on device 1)."""
+    import ctypes as C
+    import re
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    blocks = re.findall(r"```python\n(.*?)```", (root / "INTEGRATION.md").read_text(), flags=re.S)
+    stub = next(b for b in blocks if "def process_yaw_and_pitchs" in b and "C.CDLL" in b)
+    snippet = next(b for b in blocks if "p2p_project_view_list.argtypes" in b)
+    ns = {}
+    exec(compile(stub.replace('C.CDLL("libp2p_b200.so")', f'C.CDLL(r"{pkg._lib.LIB_PATH}")'), "INTEGRATION.md", "exec"), ns)
+    lib = ns["_lib"]
+    n_dev = lib.p2p_device_count()
+    ctxs = []
+    for r in range(2):
+        c = C.c_void_p()
+        assert lib.p2p_create(min(r, n_dev - 1), 2, C.byref(c)) == 0
+        ctxs.append(c)
+    Wp, Hp, W, H, fov = 1024, 512, 128, 96, 90
+    pano = synth.noise(Wp, Hp, 14)
+    views = FACES
+    shifts_l, consts_l = _flat(pkg, Wp, W, fov, views)
+    shifts = (C.c_int32 * len(views))(*shifts_l)
+    consts = (ns["PitchConsts"] * len(views))()
+    for i, (f, c, s) in enumerate(consts_l):
+        consts[i].f, consts[i].c, consts[i].s = f, c, s
+    out = np.zeros((len(views), H, W, 3), np.uint8)
+
+    def ck(rc):
+        assert rc == 0, lib.p2p_last_error(ctxs[0]).decode()
+
+    lib.p2p_destroy.argtypes = [C.c_void_p]
+    ns.update(ctxs=ctxs, n=2, pano=pano, Wp=Wp, Hp=Hp, n_views=len(views), shifts=shifts, consts=consts, W=W, H=H, out=out,
+              ck=ck)
+    try:
+        exec(compile(snippet, "INTEGRATION.md", "exec"), ns)
+        proj = pkg.get_projector()
+        with proj.slots(1) as (s,):
+            proj.upload(s, pano)
+            want = proj.project_list(s, shifts_l, consts_l, W, H)
+            proj.sync(s)
+        assert np.array_equal(out, want)
+    finally:
+        for c in ctxs:
+            lib.p2p_destroy(c)
