@@ -193,7 +193,7 @@ int launch_rows(p2p_ctx *ctx, Slot &s, int n_views, const int32_t *yaw_shift, co
     int rc = ensure_texture(ctx, s);
     if (rc) return rc;
     const int band = row_end - row_begin;
-    if ((band + 7) / 8 > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+    if ((band + kRowsWarps - 1) / kRowsWarps > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
     RowsParams P;
     memset(&P, 0, sizeof(P));
     P.tex = s.tex;
@@ -219,8 +219,8 @@ int launch_rows(p2p_ctx *ctx, Slot &s, int n_views, const int32_t *yaw_shift, co
     auto flush = [&]() -> int {
         if (ng == 0) return P2P_OK;
         for (int g = 0; g < ng; ++g) full = full && (P.grp[g].ny == ny_max);
-        dim3 grid((P.n_chunks + P.seg_chunks - 1) / P.seg_chunks, (band + 7) / 8, ng);
-        pick_rows(ctx->opt_trig == 0, full, ny_max)<<<grid, 256, 0, s.stream>>>(P);
+        dim3 grid((P.n_chunks + P.seg_chunks - 1) / P.seg_chunks, (band + kRowsWarps - 1) / kRowsWarps, ng);
+        pick_rows(ctx->opt_trig == 0, full, ny_max)<<<grid, 32 * kRowsWarps, 0, s.stream>>>(P);
         ctx->launches++;
         CK(cudaGetLastError());
         ng = 0;
