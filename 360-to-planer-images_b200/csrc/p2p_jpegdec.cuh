@@ -671,6 +671,12 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
     return done;
 }
 
+// the destuffed scan arrives in file byte order; the decoders read 32-bit windows MSB-first
+__global__ void __launch_bounds__(256) bswap_words_kernel(uint32_t *__restrict__ w, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = __byte_perm(w[i], 0u, 0x0123);
+}
+
 // round 0: every subsequence from its guessed state; later rounds: only where the predecessor's end state moved
 __global__ void __launch_bounds__(128)
 huff_sync_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,

@@ -550,6 +550,9 @@ def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ra
     from concurrent.futures import ThreadPoolExecutor
 
     data = cv2.imencode(".jpg", pano)[1].tobytes()
+    # images in flight per rank: the host half of the decoder (removing the FF 00 stuffing) runs on the calling thread, so
+    # the ranks of one box share its cores
+    n_thr = max(2, min(n_thr, (os.cpu_count() or 8) // max(1, world)))
 
     def one(_):
         with proj.slots(1) as (s,):
