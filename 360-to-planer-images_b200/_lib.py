@@ -84,6 +84,7 @@ OPT_PARTIAL_UPLOAD = 8
 OPT_GPU_HUFFMAN, OPT_GPU_HUFFMAN_COUNT = 9, 10
 OPT_SEG_CHUNKS = 11
 OPT_SEAM_WRAP = 12
+OPT_HOST_WAIT = 13
 
 _lib = None
 

@@ -78,6 +78,7 @@ void p2p_destroy(p2p_ctx *ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < ctx->n_slots; ++i) {
         Slot &s = ctx->slots[i];
+        if (s.wait_ev) cudaEventDestroy(s.wait_ev);
         if (s.tex) cudaDestroyTextureObject(s.tex);
         if (s.surf) cudaDestroySurfaceObject(s.surf);
         if (s.arr) cudaFreeArray(s.arr);
@@ -103,6 +104,9 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.pg_Z);
         cudaFree(s.pg_sums);
         cudaFree(s.jd_stream);
+        cudaFree(s.jd_raw);
+        cudaFree(s.jd_dcnt);
+        cudaFree(s.jd_gate_d);
         cudaFree(s.jd_states);
         cudaFree(s.jd_nblk);
         cudaFree(s.jd_tables);
@@ -173,8 +177,12 @@ int p2p_set_option(p2p_ctx *ctx, int key, int value) {
             if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "partial_upload must be 0 or 1");
             ctx->opt_partial = value;
             return P2P_OK;
+        case P2P_OPT_HOST_WAIT:
+            if (value != 0 && value != 1) return fail(ctx, P2P_ERR_INVALID, "host_wait must be 0 or 1");
+            ctx->opt_host_wait.store(value);
+            return P2P_OK;
         case P2P_OPT_GPU_HUFFMAN:
-            if (value < 0 || value > 2) return fail(ctx, P2P_ERR_INVALID, "gpu_huffman must be 0, 1 or 2");
+            if (value < 0 || value > 3) return fail(ctx, P2P_ERR_INVALID, "gpu_huffman must be 0 ... 3");
             ctx->opt_gpu_huffman = value;
             return P2P_OK;
 
@@ -199,6 +207,7 @@ int p2p_get_option(p2p_ctx *ctx, int key, int *value) {
         case P2P_OPT_TRIG: *value = ctx->opt_trig; return P2P_OK;
         case P2P_OPT_PARTIAL_UPLOAD: *value = ctx->opt_partial; return P2P_OK;
         case P2P_OPT_GPU_HUFFMAN: *value = ctx->opt_gpu_huffman; return P2P_OK;
+        case P2P_OPT_HOST_WAIT: *value = ctx->opt_host_wait.load(); return P2P_OK;
         case P2P_OPT_GPU_HUFFMAN_COUNT: *value = (int)ctx->gpu_huffman_used; return P2P_OK;
 
         default: return fail(ctx, P2P_ERR_INVALID, "unknown option");
@@ -318,7 +327,7 @@ int p2p_set_stream(p2p_ctx *ctx, int slot, void *cuda_stream) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slots[slot];
-    CK(cudaStreamSynchronize(s.stream));
+    CK(wait_slot(ctx, s));
     // the slot's own stream is kept (another slot may have borrowed it through p2p_get_stream)
     // and released by p2p_destroy
     if (s.own_stream) s.owned = s.stream;
@@ -471,7 +480,7 @@ int p2p_sample_with_maps(p2p_ctx *ctx, int slot, int yaw_shift, const float *U_h
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_o, n * 3, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess) e = wait_slot(ctx, s);
     cudaFree(d);
     cudaFree(d_o);
     if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_sample_with_maps", e);
@@ -495,7 +504,7 @@ int p2p_download_pano(p2p_ctx *ctx, int slot, uint8_t *bgr_host, size_t row_stri
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess)
         e = cudaMemcpy2DAsync(bgr_host, row_stride, d, dstride, dstride, s.Hp, cudaMemcpyDeviceToHost, s.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess) e = wait_slot(ctx, s);
     cudaFree(d);
     if (e != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "p2p_download_pano", e);
     return P2P_OK;

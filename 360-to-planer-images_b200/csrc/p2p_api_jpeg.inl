@@ -76,7 +76,7 @@ int enqueue_jpeg(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int 
 
 // wait for the slot's encoder and copy the files out (called WITHOUT the context lock: only stream calls)
 int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8_t *out_host, size_t out_stride, size_t *sizes) {
-    cudaError_t e = cudaStreamSynchronize(s.stream);
+    cudaError_t e = wait_slot(ctx, s);
     if (e != cudaSuccess) return P2P_ERR_CUDA;
     int rc = P2P_OK;
     for (int i = 0; i < n; ++i) {
@@ -91,7 +91,7 @@ int collect_jpeg(p2p_ctx *ctx, Slot &s, int n, const p2pjpeg::Geometry &G, uint8
                             cudaMemcpyDeviceToHost, s.stream);
         if (e != cudaSuccess) return P2P_ERR_CUDA;
     }
-    e = cudaStreamSynchronize(s.stream);
+    e = wait_slot(ctx, s);
     if (e != cudaSuccess) return P2P_ERR_CUDA;
     (void)ctx;
     return rc;

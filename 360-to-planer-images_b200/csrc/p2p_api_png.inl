@@ -87,8 +87,8 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
 }
 
 // wait and copy the PNG files out; sizes[i] = 0 marks an image the device encoder does not handle
-int collect_png(Slot &s, int n, size_t cap_per_image, uint8_t *out_host, size_t out_stride, size_t *sizes) {
-    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return P2P_ERR_CUDA;
+int collect_png(p2p_ctx *ctx, Slot &s, int n, size_t cap_per_image, uint8_t *out_host, size_t out_stride, size_t *sizes) {
+    if (wait_slot(ctx, s) != cudaSuccess) return P2P_ERR_CUDA;
     int rc = P2P_OK;
     for (int i = 0; i < n; ++i) {
         const unsigned long long sz = s.j_sizes_h[i];
@@ -103,7 +103,7 @@ int collect_png(Slot &s, int n, size_t cap_per_image, uint8_t *out_host, size_t 
                             cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
             return P2P_ERR_CUDA;
     }
-    if (cudaStreamSynchronize(s.stream) != cudaSuccess) return P2P_ERR_CUDA;
+    if (wait_slot(ctx, s) != cudaSuccess) return P2P_ERR_CUDA;
     return rc;
 }
 
@@ -134,7 +134,7 @@ int p2p_encode_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int on_device, in
         if (rc) return rc;
     }
     cudaSetDevice(ctx->device);
-    int rc = collect_png(s, n_images, G.out_cap, out_host, out_stride, sizes);
+    int rc = collect_png(ctx, s, n_images, G.out_cap, out_host, out_stride, sizes);
     if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a PNG file does not fit its output buffer (out_stride)");
     if (rc) return fail(ctx, rc, "PNG encoder: CUDA error");
     return P2P_OK;
@@ -182,7 +182,7 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
         if (pixels_host) CK(cudaMemcpyAsync(pixels_host, s.d_out, (size_t)n * W * H * 3, cudaMemcpyDeviceToHost, s.stream));
     }
     cudaSetDevice(ctx->device);
-    int rc = collect_png(s, n, G.out_cap, out_host, out_stride, sizes);
+    int rc = collect_png(ctx, s, n, G.out_cap, out_host, out_stride, sizes);
     if (rc == P2P_ERR_LIMIT) return fail(ctx, rc, "a PNG file does not fit its output buffer (out_stride)");
     if (rc) return fail(ctx, rc, "PNG encoder: CUDA error");
     return P2P_OK;

@@ -671,6 +671,85 @@ __device__ __forceinline__ uint32_t huff_decode_range(const uint32_t *__restrict
     return done;
 }
 
+// ---- destuffing on the device (files without restart markers) ----------------------------------------------------
+// The entropy-coded segment as it sits in the file: every data byte 0xFF is followed by a stuffed 0x00 (removed here);
+// 0xFF followed by anything else is a marker or a fill byte, which a scan without restart intervals must not contain
+// before its end: `irregular` is raised and the host pass (which knows libjpeg's rules for those) takes over.
+// Chunks of 4096 bytes: one CTA, 16 bytes per thread.
+constexpr int kDestuffChunk = 4096;
+
+__device__ __forceinline__ uint32_t destuff_flags16(const uint8_t *__restrict__ raw, uint32_t n, uint32_t i0, int *irregular) {
+    // bit j of the result: byte i0 + j is a stuffed zero (to be removed)
+    uint32_t rem = 0;
+    if (i0 >= n) return 0;
+    uint8_t prev = i0 ? raw[i0 - 1] : 0;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t i = i0 + j;
+        if (i < n) {
+            const uint8_t b = raw[i];
+            if (prev == 0xFF) {
+                if (b == 0x00) rem |= 1u << j;
+                else bad = true;
+            }
+            prev = (prev == 0xFF && b == 0x00) ? 0x01 : b;   // the stuffed zero itself is not data
+            if (i + 1 == n && b == 0xFF) bad = true;          // a lone 0xFF at the end: fill byte before the marker
+        }
+    }
+    if (bad) *irregular = 1;
+    return rem;
+}
+
+__global__ void __launch_bounds__(256)
+destuff_count_kernel(const uint8_t *__restrict__ raw, uint32_t n, uint32_t *__restrict__ counts, int *__restrict__ irregular) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t i0 = blockIdx.x * (uint32_t)kDestuffChunk + threadIdx.x * 16u;
+    uint32_t c = __popc(destuff_flags16(raw, n, i0, irregular));
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s_warp[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// kept byte i of the raw segment -> byte (i - removed before i) of the destuffed stream, stored MSB-first inside 32-bit words
+__global__ void __launch_bounds__(256)
+destuff_scatter_kernel(const uint8_t *__restrict__ raw, uint32_t n, const uint32_t *__restrict__ chunk_off,
+                       uint8_t *__restrict__ out) {
+    __shared__ uint32_t s_warp[8];
+    int unused = 0;
+    const uint32_t i0 = blockIdx.x * (uint32_t)kDestuffChunk + threadIdx.x * 16u;
+    const uint32_t rem = destuff_flags16(raw, n, i0, &unused);
+    const uint32_t c = __popc(rem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = chunk_off[blockIdx.x] + (inc - c);
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t i = i0 + j;
+        if (i < n) {
+            if (rem & (1u << j)) {
+                ++before;
+            } else {
+                const uint32_t k = i - before;
+                out[(k & ~3u) | (3u - (k & 3u))] = raw[i];
+            }
+        }
+    }
+}
+
 // the destuffed scan arrives in file byte order; the decoders read 32-bit windows MSB-first
 __global__ void __launch_bounds__(256) bswap_words_kernel(uint32_t *__restrict__ w, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,13 +892,27 @@ huff_check_kernel(const uint32_t *__restrict__ blkoff, const uint32_t *__restric
     if (got < quota || got > quota + 8u) *bad = 1;
 }
 
+// Optimistic enqueue: the host queues a fixed number of rounds, the block-count check, the write pass and everything
+// after it without waiting for any of them; this one-thread kernel decides on the device whether the write pass may run
+// (the last queued round moved nothing = fixed point reached, and every interval holds its quota of blocks) and leaves
+// the same verdict where the host finds it after its single wait: 1 = go, 0 = not converged yet (the host queues more
+// rounds), -1 = block counts off (the host decoder takes the file).
+__global__ void huff_gate_kernel(const int *__restrict__ changed_last, const int *__restrict__ bad, int *__restrict__ gate_dev,
+                                 int *__restrict__ gate_host) {
+    const int v = *changed_last ? 0 : (*bad ? -1 : 1);
+    *gate_dev = (v == 1);
+    *gate_host = v;
+}
+
 __global__ void __launch_bounds__(128)
 huff_write_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const HuffGeom G,
                   const SubSeq *__restrict__ sub, const uint32_t *__restrict__ ivl_first,
                   const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
-                  int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag) {
+                  int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag,
+                  const int *__restrict__ gate) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= G.n_sub) return;
+    if (gate && !*gate) return;   // optimistic enqueue: the rounds before did not converge / the block counts are off
     const SubSeq q = sub[i];
     HState st = unpack_state(start[i]);
     // scan-order index of the block in progress: interval base + blocks completed earlier in this interval
@@ -840,9 +933,11 @@ __global__ void __launch_bounds__(kSyncThreads)
 huff_write_fast_kernel(const uint32_t *__restrict__ w, const DevHuff *__restrict__ T, const SyncLut *__restrict__ lut,
                        const HuffGeom G, const SubSeq *__restrict__ sub, const uint32_t *__restrict__ ivl_first,
                        const unsigned long long *__restrict__ start, const uint32_t *__restrict__ blkoff,
-                       int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag) {
+                       int16_t *__restrict__ coef, int32_t *__restrict__ dcdiff, int *__restrict__ damaged_flag,
+                       const int *__restrict__ gate) {
     __shared__ uint32_t s_lut[3 * 2 * (1 << kFastBits)];
     __shared__ uint32_t s_w[kSyncWords + kSyncWords / 32 + 2];
+    if (gate && !*gate) return;   // optimistic enqueue (see huff_gate_kernel): uniform over the grid
     const uint32_t i0 = blockIdx.x * kSyncThreads, i = i0 + threadIdx.x;
     for (int k = threadIdx.x; k < 3 * 2 * (1 << kFastBits); k += kSyncThreads) s_lut[k] = __ldg(&lut->w[0][0][0] + k);
     const uint32_t i_last = (i0 + kSyncThreads <= G.n_sub ? i0 + kSyncThreads : G.n_sub) - 1;

@@ -72,15 +72,23 @@ typedef enum p2p_option {
                                      hosts (Intel SVML, ref :162-164) - coordinates and pixels then match the
                                      reference bit for bit there; 1: table-free minimax fits (<= 1.2 ulp) */
     ,P2P_OPT_GPU_HUFFMAN = 9       /* 1 (default): JPEG inputs are Huffman-decoded on the device (self-synchronising
-                                     subsequences, restart intervals as independent scans); the library's host decoder
-                                     takes over when that does not converge; 0: always the host decoder; 2: the device
-                                     stage with its plain synchronisation rounds (tables in global memory - the yardstick
-                                     the shared-memory rounds of mode 1 are tested against) */
+                                     subsequences, restart intervals as independent scans), the FF 00 stuffing of files
+                                     without restart markers is removed on the device too, and the whole stage is queued
+                                     without waiting for it (a fixed number of rounds, then a device-side verdict gates the
+                                     write pass; a file that needs more rounds continues with host-checked rounds); the
+                                     library's host decoder takes over when that does not converge; 0: always the host
+                                     decoder; 3: the device stage with destuffing on the calling thread and a host check
+                                     after every few rounds; 2: like 3 with the plain synchronisation rounds (tables in
+                                     global memory - the yardstick the shared-memory rounds are tested against) */
     ,P2P_OPT_GPU_HUFFMAN_COUNT = 10 /* read-only: JPEG inputs whose Huffman stage ran on the device so far */
     ,P2P_OPT_SEAM_WRAP = 12        /* exact-bilinear mode only (P2P_OPT_INTERP = 1).  0 (default): U is clipped to Wp - 1 like the
                                      reference does (ref :172) - no interpolation across the 0 / 360 degree seam; 1: U runs over
                                      [0, Wp) and a pixel between the last and the first panorama column blends the two (true wrap,
                                      scipy's mode='grid-wrap'; the north-star's "edge / wrap mode") */
+    ,P2P_OPT_HOST_WAIT = 13        /* how a host thread waits for its slot's stream.  0 (default): cudaStreamSynchronize (CUDA's
+                                     default spins: lowest latency, one busy core per waiting thread - the reference's
+                                     ThreadPoolExecutor workers, ref :252-265, block in cv2 instead); 1: the thread sleeps on a
+                                     blocking-sync event, for more images in flight than cores (several ranks on one box) */
     ,P2P_OPT_SEG_CHUNKS = 11       /* row-segment kernel: chunks of 32 pixel pairs per warp (default 4, 1..64) */
     ,P2P_OPT_PARTIAL_UPLOAD = 8    /* 1 (default): p2p_process_image copies only the panorama rows its views can
                                      touch (p2p_view_row_range) over PCIe; 0: always the whole panorama */
