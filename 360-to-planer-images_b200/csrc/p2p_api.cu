@@ -97,7 +97,6 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.jd_coef_d);
         cudaFree(s.jd_planes);
         cudaFree(s.pg_F);
-        cudaFree(s.pg_S);
         cudaFree(s.pg_tlen);
         cudaFree(s.pg_blk);
         cudaFree(s.pg_info);

@@ -37,10 +37,9 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
         CK(cudaMemcpy(ctx->d_crc_table, table, sizeof(table), cudaMemcpyHostToDevice));
     }
     const size_t npos = (size_t)n * G.Npad, nblk = (size_t)n * G.max_blk;
-    const size_t chunk_words = (size_t)n * ((G.N + kScanChunk - 1) / kScanChunk);
-    const size_t blk_words = nblk * 2 + (((size_t)n + 3) & ~(size_t)3) + nblk * (kLCodes + 2) + 2 * chunk_words;
+    const size_t tile_words = npos / kTile;   // per-tile arrays: last change, inherited run start, tokens, first token index
+    const size_t blk_words = nblk * 2 + (((size_t)n + 3) & ~(size_t)3) + nblk * (kLCodes + 2) + 4 * tile_words;
     int rc = ensure(ctx, &s.pg_F, &s.pg_F_cap, npos);
-    if (!rc) rc = ensure(ctx, &s.pg_S, &s.pg_S_cap, npos * sizeof(uint32_t));
     if (!rc) rc = ensure(ctx, &s.pg_tlen, &s.pg_tlen_cap, npos * sizeof(uint16_t));
     if (!rc) rc = ensure(ctx, &s.pg_blk, &s.pg_blk_cap, blk_words * sizeof(uint32_t));
     if (!rc) rc = ensure(ctx, &s.pg_info, &s.pg_info_cap, nblk * sizeof(BlockInfo));
@@ -58,30 +57,28 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
     }
     uint32_t *blockpos = s.pg_blk, *blkoff = s.pg_blk + nblk, *ntok = s.pg_blk + 2 * nblk;
     uint32_t *lfreq = ntok + (((size_t)n + 3) & ~(size_t)3);
-    uint32_t *chunk_agg = lfreq + nblk * (kLCodes + 2), *chunk_carry = chunk_agg + chunk_words;
+    uint32_t *tile_last = lfreq + nblk * (kLCodes + 2), *tile_carry = tile_last + tile_words;
+    uint32_t *tile_cnt = tile_carry + tile_words, *tile_first = tile_cnt + tile_words;
     unsigned long long *sums = s.pg_sums, *zbits = s.pg_sums + 2 * (size_t)n;
     cudaStream_t st = s.stream;
     if (H > 65535) return fail(ctx, P2P_ERR_LIMIT, "image too tall for one grid");
     CK(cudaMemsetAsync(s.pg_Z, 0, (size_t)n * G.z_cap, st));
     CK(cudaMemsetAsync(s.pg_sums, 0, 3 * (size_t)n * sizeof(unsigned long long), st));
     png_filter_kernel<<<dim3((W + 255) / 256, H, n), 256, 0, st>>>(d_bgr, s.pg_F, G);
-    const unsigned n_chunks = (G.N + kScanChunk - 1) / kScanChunk;
-    const dim3 sgrid(n_chunks, n);
-    png_scan_kernel<0, false><<<sgrid, 1024, 0, st>>>(s.pg_F, s.pg_S, nullptr, nullptr, chunk_agg, nullptr, G);
-    png_chunk_carry_kernel<0><<<(n + 31) / 32, 32, 0, st>>>(chunk_agg, chunk_carry, nullptr, G);
-    png_scan_kernel<0, true><<<sgrid, 1024, 0, st>>>(s.pg_F, s.pg_S, nullptr, nullptr, nullptr, chunk_carry, G);
-    png_scan_kernel<1, false><<<sgrid, 1024, 0, st>>>(s.pg_F, s.pg_S, nullptr, nullptr, chunk_agg, nullptr, G);
-    png_chunk_carry_kernel<1><<<(n + 31) / 32, 32, 0, st>>>(chunk_agg, chunk_carry, ntok, G);
-    png_scan_kernel<1, true><<<sgrid, 1024, 0, st>>>(s.pg_F, s.pg_S, s.pg_tlen, blockpos, nullptr, chunk_carry, G);
+    const dim3 tgrid(G.Npad / kTile, n);
+    png_tile_kernel<<<tgrid, 256, 0, st>>>(s.pg_F, tile_last, sums, G);
+    png_tile_scan_kernel<0><<<n, 1024, 0, st>>>(tile_last, tile_carry, nullptr, G);
+    png_token_kernel<<<tgrid, 256, 0, st>>>(s.pg_F, tile_carry, s.pg_tlen, tile_cnt, G);
+    png_tile_scan_kernel<1><<<n, 1024, 0, st>>>(tile_cnt, tile_first, ntok, G);
+    png_blockpos_kernel<<<dim3((G.max_blk + 3) / 4, n), 128, 0, st>>>(s.pg_tlen, tile_first, ntok, blockpos, G);
     png_hist_kernel<<<dim3(G.max_blk, n), 256, 0, st>>>(s.pg_F, s.pg_tlen, blockpos, ntok, lfreq, G);
-    png_tree_kernel<<<dim3((G.max_blk + 31) / 32, n), 32, 0, st>>>(lfreq, ntok, blockpos, s.pg_info, G);
-    png_layout_kernel<<<(n + 31) / 32, 32, 0, st>>>(s.pg_info, ntok, blkoff, zbits, G);
+    png_tree_kernel<<<dim3((G.max_blk + kTreeWarps - 1) / kTreeWarps, n), kTreeWarps * 32, 0, st>>>(lfreq, ntok, blockpos, s.pg_info, G);
+    png_layout_kernel<<<n, 32, 0, st>>>(s.pg_info, ntok, blkoff, zbits, G);
     png_emit_kernel<<<dim3(G.max_blk, n), 256, 0, st>>>(s.pg_F, s.pg_tlen, blockpos, ntok, s.pg_info, blkoff, zbits, s.pg_Z, G);
-    png_adler_kernel<<<dim3(64, n), 256, 0, st>>>(s.pg_F, sums, G);
-    png_pack_kernel<<<dim3(128, n), 256, 0, st>>>(s.pg_Z, zbits, sums, s.j_out, G);
     const unsigned max_chunks = (unsigned)(G.z_cap / kIdat + 1);
-    png_finish_kernel<<<dim3((max_chunks + 7) / 8, n), 256, 0, st>>>(s.j_out, zbits, ctx->d_crc_table, s.j_sizes_d, G);
-    ctx->launches += 14;
+    png_finish_kernel<<<dim3((max_chunks + kFinWarps - 1) / kFinWarps, n), kFinWarps * 32, 0, st>>>(s.pg_Z, zbits, sums, s.j_out,
+                                                                                                ctx->d_crc_table, s.j_sizes_d, G);
+    ctx->launches += 11;
     CK(cudaGetLastError());
     return P2P_OK;
 }

@@ -69,8 +69,6 @@ struct Slot {
     // PNG encoder scratch (p2p_encode_png)
     uint8_t *pg_F = nullptr;
     size_t pg_F_cap = 0;
-    uint32_t *pg_S = nullptr;
-    size_t pg_S_cap = 0;
     uint16_t *pg_tlen = nullptr;
     size_t pg_tlen_cap = 0;
     uint32_t *pg_blk = nullptr;      // blockpos | blkoff | ntok | lfreq
