@@ -48,6 +48,7 @@ SIGNATURES = {
     "p2p_upload_pano_device": (_i, [_vp, _i, _vp, _i, _i, _sz]),
     "p2p_rotate_pano": (_i, [_vp, _i, _i, _i32p, _i32p]),
     "p2p_project_views": (_i, [_vp, _i, _i, _i32p, _i, _pcp, _i, _i, _u8p, _i]),
+    "p2p_project_views_table": (_i, [_vp, _i, _i, C.POINTER(_i32p), C.POINTER(_i32p), _i, _pcp, _i, _i, _u8p, _i]),
     "p2p_project_batch": (_i, [_vp, _i, _i32p, _i, _i32p, _i, _pcp, _i, _i, C.POINTER(_vp), _i]),
     "p2p_project_view_list": (_i, [_vp, _i, _i, _i32p, _pcp, _i, _i, _i, _i, _u8p, _i]),
     "p2p_copy_pano": (_i, [_vp, _i, _vp, _i]),

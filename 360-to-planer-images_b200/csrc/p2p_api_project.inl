@@ -523,6 +523,102 @@ int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shif
     return project_views_locked(ctx, slot, n_yaw, yaw_shift, n_pitch, pitch, W, H, out, out_on_device);
 }
 
+// Fractional yaws without the materialised yaw pass (project_frac_kernel): yaw k is its Wp-entry column table.
+int p2p_project_views_table(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *const *ix, const int32_t *const *fx, int n_pitch,
+                            const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device) {
+    P2P_NVTX("p2p_project_views_table");
+    if (!ctx) return P2P_ERR_INVALID;
+    if (!slot_ok(ctx, slot)) return fail(ctx, P2P_ERR_INVALID, "bad slot");
+    if (n_yaw <= 0 || n_pitch <= 0 || !ix || !fx || !pitch || !out || W <= 0 || H <= 0)
+        return fail(ctx, P2P_ERR_INVALID, "bad argument");
+    if (W >= 32767 || H >= 32767) return fail(ctx, P2P_ERR_LIMIT, "output dimension >= 32767");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->slots[slot];
+    if (!s.valid) return fail(ctx, P2P_ERR_STATE, "slot holds no panorama");
+    if (slot_is_partial(s)) return fail(ctx, P2P_ERR_STATE, "slot holds a partial panorama (p2p_process_image)");
+    if (ctx->opt_interp != 0)
+        return fail(ctx, P2P_ERR_INVALID, "fractional yaws are only defined for the cv2 fixed-point interpolation mode");
+    const int Wp = s.Wp;
+    if (Wp > 65535) return fail(ctx, P2P_ERR_LIMIT, "panorama too wide for the packed yaw table");
+    // tab[k][c] = ix | fx << 16, entry Wp repeats entry 0
+    std::vector<uint32_t> tabs((size_t)n_yaw * (Wp + 1));
+    for (int k = 0; k < n_yaw; ++k) {
+        if (!ix[k] || !fx[k]) return fail(ctx, P2P_ERR_INVALID, "null yaw table");
+        uint32_t *t = tabs.data() + (size_t)k * (Wp + 1);
+        for (int c = 0; c < Wp; ++c) {
+            if (ix[k][c] < 0 || ix[k][c] >= Wp || fx[k][c] < 0 || fx[k][c] > 31)
+                return fail(ctx, P2P_ERR_INVALID, "yaw table entry out of range");
+            t[c] = (uint32_t)ix[k][c] | ((uint32_t)fx[k][c] << 16);
+        }
+        t[Wp] = t[0];
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_texture(ctx, s);
+    if (rc) return rc;
+    rc = ensure(ctx, &s.d_tab, &s.tab_cap, tabs.size() * sizeof(uint32_t));
+    if (rc) return rc;
+    const size_t bytes = (size_t)n_yaw * n_pitch * W * H * 3;
+    uint8_t *d_out = out;
+    if (!out_on_device) {
+        rc = ensure(ctx, &s.d_out, &s.out_cap, bytes);
+        if (rc) return rc;
+        d_out = s.d_out;
+    }
+    // (pageable source: the copy is staged before the call returns, and ordered behind earlier launches that read d_tab)
+    CK(cudaMemcpyAsync(s.d_tab, tabs.data(), tabs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    ProjParams P;
+    memset(&P, 0, sizeof(P));
+    P.tex[0] = s.tex;
+    P.out[0] = d_out;
+    P.view_stride = (unsigned long long)W * H * 3;
+    P.yaw_stride = P.view_stride * (unsigned long long)n_pitch;
+    P.pitch_tex = s.pitch_tex;
+    P.Wp = s.Wp; P.Hp = s.Hp; P.W = W; P.H = H;
+    P.halfW = (float)(W / 2.0);
+    P.halfH = (float)(H / 2.0);
+    P.Wp_f = (float)s.Wp;
+    P.Hp_f = (float)s.Hp;
+    P.Umax = (float)(s.Wp - 1);
+    P.Vmax = (float)(s.Hp - 1);
+    P.inv_Wp = (float)(1.0 / (double)s.Wp);
+    P.inv_Hp = (float)(1.0 / (double)s.Hp);
+    P.numpy_trig = (ctx->opt_trig == 0);
+    const bool quad = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0);
+    for (int y0 = 0; y0 < n_yaw; y0 += 4) {
+        const int ny_l = (n_yaw - y0 < 4) ? n_yaw - y0 : 4;
+        FracTabs T;
+        for (int k = 0; k < 4; ++k)
+            T.tab[k] = reinterpret_cast<const uint32_t *>(s.d_tab) + (size_t)(y0 + (k < ny_l ? k : 0)) * (Wp + 1);
+        P.yaw_off = y0;
+        for (int p0 = 0; p0 < n_pitch; p0 += kMaxPitchPerLaunch) {
+            const int np_l = (n_pitch - p0 < kMaxPitchPerLaunch) ? n_pitch - p0 : kMaxPitchPerLaunch;
+            P.n_pitch = np_l;
+            P.pitch_off = p0;
+            for (int j = 0; j < np_l; ++j) {
+                P.pc[j].f = pitch[p0 + j].f;
+                P.pc[j].c = pitch[p0 + j].c;
+                P.pc[j].s = pitch[p0 + j].s;
+            }
+            dim3 grid((W + 31) / 32, (H + 7) / 8, np_l);
+            if (grid.y > 65535) return fail(ctx, P2P_ERR_LIMIT, "output too large for one grid");
+            switch (ny_l * 2 + (quad ? 1 : 0)) {
+                case 2: project_frac_kernel<1, false><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 3: project_frac_kernel<1, true><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 4: project_frac_kernel<2, false><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 5: project_frac_kernel<2, true><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 6: project_frac_kernel<3, false><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 7: project_frac_kernel<3, true><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                case 8: project_frac_kernel<4, false><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+                default: project_frac_kernel<4, true><<<grid, kThreads, 0, s.stream>>>(P, T); break;
+            }
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    if (!out_on_device) CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, s.stream));
+    return P2P_OK;
+}
+
 int p2p_project_batch(p2p_ctx *ctx, int n_images, const int32_t *slots, int n_yaw, const int32_t *yaw_shift,
                       int n_pitch, const p2p_pitch_consts *pitch, int W, int H, uint8_t *const *outs,
                       int out_on_device) {

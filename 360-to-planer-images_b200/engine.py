@@ -263,6 +263,51 @@ class Projector:
                                             n_pitch, pc, W, H, dst, on_dev))
         return out
 
+    def project_tables(self, slot: int, tables, consts, W: int, H: int, out=None, out_device_ptr: int | None = None):
+        """Enqueue n_yaw x n_pitch views for yaws that are NOT integer column rolls, in one pass: ``tables[k] = (ix, fx)``
+        is yaw k's column table from :func:`yaw_table`.  Both remap passes of the reference (ref :191-199, :212-218) are
+        evaluated per output pixel; bit-identical to :meth:`rotate` + :meth:`project`.  ``out`` as in :meth:`project`."""
+        n_yaw, n_pitch = len(tables), len(consts)
+        pc = self._consts_array(consts)
+        ixs = [np.ascontiguousarray(t[0], np.int32) for t in tables]
+        fxs = [np.ascontiguousarray(t[1], np.int32) for t in tables]
+        P = C.POINTER(C.c_int32)
+        ixp = (P * n_yaw)(*[a.ctypes.data_as(P) for a in ixs])
+        fxp = (P * n_yaw)(*[a.ctypes.data_as(P) for a in fxs])
+        if out_device_ptr is not None:
+            dst, on_dev = C.c_void_p(out_device_ptr), 1
+        else:
+            if out is None:
+                out = np.empty((n_yaw, n_pitch, H, W, 3), np.uint8)
+            if out.dtype != np.uint8 or not out.flags.c_contiguous or out.size != n_yaw * n_pitch * H * W * 3:
+                raise ValueError("out must be C-contiguous uint8 [n_yaw, n_pitch, H, W, 3]")
+            dst, on_dev = out.ctypes.data, 0
+        self._ck(self.lib.p2p_project_views_table(self.ctx, slot, n_yaw, ixp, fxp, n_pitch, pc, W, H, dst, on_dev))
+        return out
+
+    def project_any(self, slot: int, tables, consts, W: int, H: int, out: np.ndarray | None = None) -> np.ndarray:
+        """All yaw x pitch views of the (whole) panorama resident in ``slot`` into the host array ``out``
+        [n_yaw, n_pitch, H, W, 3]: integer-roll yaws through :meth:`project`, the others through :meth:`project_tables`,
+        from the same slot.  ``tables[k]`` = :func:`yaw_table` of yaw k.  Synchronous."""
+        if out is None:
+            out = np.empty((len(tables), len(consts), H, W, 3), np.uint8)
+        roll = [k for k, t in enumerate(tables) if t[2] is not None]
+        frac = [k for k, t in enumerate(tables) if t[2] is None]
+        tmp = ftmp = None
+        if roll:
+            tmp = self.project(slot, [tables[k][2] for k in roll], consts, W, H, out=out if not frac else None)
+        if frac:   # one pass from the same slot (round 1 materialised a rotated panorama per fractional yaw)
+            if roll:
+                self.sync(slot)   # both launches stage their host output through the slot's device buffer
+            ftmp = self.project_tables(slot, [tables[k] for k in frac], consts, W, H, out=out if not roll else None)
+        self.sync(slot)
+        if roll and frac:
+            for i, k in enumerate(roll):
+                out[k] = tmp[i]
+            for i, k in enumerate(frac):
+                out[k] = ftmp[i]
+        return out
+
     def project_list(self, slot: int, shifts, consts, W: int, H: int, rows=None, out=None,
                      out_device_ptr: int | None = None):
         """Enqueue a flat list of views - view i = (shifts[i], consts[i]) - in one launch; ``rows = (begin, end)`` renders
@@ -605,8 +650,8 @@ class Projector:
         """All yaw x pitch views of one panorama: u8 [n_yaw, n_pitch, H, W, 3].
 
         Replaces the reference's per-image fan-out (ref :252-265): every yaw that is an integer
-        column roll goes into one batched launch; a fractional yaw first materialises the rotated
-        panorama (the reference's yaw remap, ref :191-199) and is projected from that.
+        column roll goes into one batched launch; the fractional yaws go into a second one that evaluates the
+        reference's yaw remap (ref :191-199) per output pixel instead of materialising a rotated panorama.
         ``consts`` / ``tables`` let a caller pass memoised host scalars (the mirror module's caches).
         """
         pano = _as_u8_image(pano)
@@ -624,23 +669,7 @@ class Projector:
             raise ValueError(f"out must be C-contiguous uint8 {shape}")
         if not yaw_angles or not pitch_angles:
             return out
-        roll = [k for k, t in enumerate(tables) if t[2] is not None]
-        frac = [k for k, t in enumerate(tables) if t[2] is None]
-        with self.slots(2 if frac else 1) as got:
-            src = got[0]
+        with self.slots(1) as (src,):
             self.upload(src, pano)
-            tmp = None
-            if roll:
-                dst = out if len(roll) == len(tables) else None
-                tmp = self.project(src, [tables[k][2] for k in roll], consts, W, H, out=dst)
-            for k in frac:
-                self.sync(src)  # the rotate kernel reads the packed source on another stream
-                self.rotate(src, got[1], tables[k][0], tables[k][1])
-                one = self.project(got[1], [0], consts, W, H)
-                self.sync(got[1])
-                out[k] = one[0]
-            self.sync(src)
-            if roll and tmp is not out:
-                for i, k in enumerate(roll):
-                    out[k] = tmp[i]
+            self.project_any(src, tables, consts, W, H, out)
         return out

@@ -168,13 +168,11 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
     devs = _split_devices(devices, tables, yaw_angles, pitch_angles)
     if devs:
         return _project_split(devs, src, consts, tables, yaw_angles, pitch_angles, output_width, output_height)
-    if isinstance(src, _JpegSource) and yaw_angles and pitch_angles and all(t[2] is not None for t in tables):
-        try:  # decode on the device straight into a slot, project from there
+    if isinstance(src, _JpegSource) and yaw_angles and pitch_angles:
+        try:  # decode on the device straight into a slot, project from there (fractional yaws too: one pass, same slot)
             with proj.slots(1) as (s,):
                 proj.upload_jpeg(s, src.data)
-                out = proj.project(s, [t[2] for t in tables], consts, output_width, output_height)
-                proj.sync(s)
-            return out
+                return proj.project_any(s, tables, consts, output_width, output_height)
         except _engine.P2PError as e:
             if e.code != -6:
                 raise

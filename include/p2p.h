@@ -146,6 +146,14 @@ int p2p_rotate_pano(p2p_ctx *ctx, int src_slot, int dst_slot, const int32_t *ix,
 int p2p_project_views(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *yaw_shift, int n_pitch,
                       const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device);
 
+/* p2p_project_views for yaws that are NOT integer column rolls, in one pass: yaw k is given by its Wp-entry column table
+ * (ix[k][c], fx[k][c]) from p2p_yaw_table.  Both cv2.remap passes of the reference - the yaw pass over the whole panorama
+ * (precompute_yaw_mapping, ref :79-108, :191-199) and the pitch pass (ref :212-218) - are evaluated per output pixel from the
+ * 2 x 3 source texels under its footprint; the result is bit-identical to p2p_rotate_pano + p2p_project_views with shift 0,
+ * without materialising a rotated panorama per yaw.  The slot must hold a whole panorama.  `out` as in p2p_project_views. */
+int p2p_project_views_table(p2p_ctx *ctx, int slot, int n_yaw, const int32_t *const *ix, const int32_t *const *fx, int n_pitch,
+                            const p2p_pitch_consts *pitch, int W, int H, uint8_t *out, int out_on_device);
+
 /* The same views for a batch of panoramas that are already resident (one launch per image,
  * each on its slot's stream): slots[i] -> outs[i].  One host call per batch keeps the launch
  * queue full when a launch is only tens of microseconds (BASELINE configs[2]). */

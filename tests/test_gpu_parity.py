@@ -306,6 +306,48 @@ def test_fractional_yaw_rotate_bit_exact_and_end_to_end(proj, golden_dir):
             assert exact_fraction(out[i, j], g["out"][i, j]) >= NOISE_EXACT_MIN
 
 
+def test_fractional_yaw_one_pass_equals_the_two_passes(pkg, proj):
+    """The one-pass form of the fractional-yaw path (p2p_project_views_table: both remap passes per output pixel) against
+    its yardstick, the materialised yaw pass + projection with shift 0: bit-identical, on panoramas whose width makes
+    ordinary yaws fractional (Wp % 360 != 0), at the clipped last columns (ix = Wp - 1: the constant-border tap), at the
+    poles, with more yaws than one launch takes, output widths that are not multiples of 4, device-resident outputs."""
+    import torch
+
+    for (Wp, Hp, W, H, fov, yaws, pitches) in [
+        (1000, 500, 200, 120, 100, [0.5, 37, 90, 181, 359.9], [30, 90, 150]),
+        (2040, 1020, 163, 90, 120, [45, 10.25, 100], [1, 90, 179]),
+        (777, 388, 64, 64, 90, [359, 1, 123, 200, 271, 33, 77], [0, 60, 180]),
+    ]:
+        pano = synth.noise(Wp, Hp, Wp)
+        consts = [pkg.pitch_constants(W, fov, p) for p in pitches]
+        tables = [pkg.yaw_table(Wp, y) for y in yaws]
+        frac = [t for t in tables if t[2] is None]
+        assert len(frac) >= 2, "the case is meant to hold fractional yaws"
+        with proj.slots(2) as (a, b):
+            proj.upload(a, pano)
+            proj.sync(a)
+            want = np.empty((len(frac), len(pitches), H, W, 3), np.uint8)
+            for k, t in enumerate(frac):
+                proj.rotate(a, b, t[0], t[1])
+                one = proj.project(b, [0], consts, W, H)
+                proj.sync(b)
+                want[k] = one[0]
+            got = proj.project_tables(a, frac, consts, W, H)
+            proj.sync(a)
+            assert np.array_equal(got, want), (Wp, W)
+            d = torch.empty(want.shape, dtype=torch.uint8, device=f"cuda:{proj.device}")
+            proj.project_tables(a, frac, consts, W, H, out_device_ptr=d.data_ptr())
+            proj.sync(a)
+            assert np.array_equal(d.cpu().numpy(), want), (Wp, W, "device output")
+        # and through the front door, mixed with integer rolls
+        out = proj.project_image(pano, yaws, pitches, W, H, fov)
+        k = 0
+        for i, t in enumerate(tables):
+            if t[2] is None:
+                assert np.array_equal(out[i], want[k]), (Wp, yaws[i])
+                k += 1
+
+
 # ------------------------------------------------------------------------------------------
 # kernel variants must agree bit for bit with each other
 # ------------------------------------------------------------------------------------------
