@@ -436,7 +436,7 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
         s.jd_run.pending = false;
     }
     bool coef_on_device = false;
-    if (use_gpu) {
+    if (use_gpu && !P.progressive) {   // (a progressive file's scans are decoded on the calling thread)
         const int rc = device_huffman(ctx, s, file, len, P, use_gpu);
         if (rc == P2P_OK) coef_on_device = true;
         else if (rc != 1) return rc;

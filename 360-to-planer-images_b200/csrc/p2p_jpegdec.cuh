@@ -196,8 +196,28 @@ struct Parsed {
     HuffTable dc[4], ac[4];
     int td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     int dri = 0;
-    size_t ecs = 0;   // offset of the entropy-coded data
+    size_t ecs = 0;   // offset of the entropy-coded data (progressive: of the first SOS marker)
+    bool progressive = false;   // SOF2: several scans, decoded on the host (decode_progressive)
+    int cid[3] = {0, 0, 0};     // component ids of the frame header
 };
+
+// one DHT segment into the table sets (jdmarker.c get_dht + jdhuff.c jpeg_make_d_derived_tbl's checks); 0 = ok
+inline int parse_dht(const uint8_t *seg, size_t sl, HuffTable *dc, HuffTable *ac) {
+    size_t j = 0;
+    while (j < sl) {
+        if (j + 17 > sl) return 1;
+        const int tc = seg[j] >> 4, th = seg[j] & 15;
+        int nv = 0;
+        for (int k = 0; k < 16; ++k) nv += seg[j + 1 + k];
+        if (tc > 1 || th > 3 || nv > 256 || j + 17 + nv > sl) return 1;
+        if (!tc)   // jdhuff.c jpeg_make_d_derived_tbl: DC symbols are categories 0..15
+            for (int k = 0; k < nv; ++k)
+                if (seg[j + 17 + k] > 15) return 1;
+        if (!build_huff(seg + j + 1, seg + j + 17, nv, tc ? ac[th] : dc[th])) return 1;
+        j += 17 + (size_t)nv;
+    }
+    return 0;
+}
 
 inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
     if (len < 4 || d[0] != 0xFF || d[1] != 0xD8) return 1;
@@ -216,7 +236,7 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
         i += 2;
         // only the segments a baseline JFIF / EXIF file is made of; libjpeg rejects or special-cases the rest
         const bool known = (m >= 0xE0 && m <= 0xEF) || m == 0xFE || m == 0xDB || m == 0xC4 || m == 0xC0 || m == 0xC1 ||
-                           m == 0xDD || m == 0xDA;
+                           m == 0xC2 || m == 0xDD || m == 0xDA;
         if (!known) return 1;
         const size_t L = ((size_t)d[i] << 8) | d[i + 1];
         if (L < 2 || i + L > len) return 1;
@@ -236,20 +256,9 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 have_qt[t] = true;
             }
         } else if (m == 0xC4) {
-            size_t j = 0;
-            while (j < sl) {
-                if (j + 17 > sl) return 1;
-                const int tc = seg[j] >> 4, th = seg[j] & 15;
-                int nv = 0;
-                for (int k = 0; k < 16; ++k) nv += seg[j + 1 + k];
-                if (tc > 1 || th > 3 || nv > 256 || j + 17 + nv > sl) return 1;
-                if (!tc)   // jdhuff.c jpeg_make_d_derived_tbl: DC symbols are categories 0..15
-                    for (int k = 0; k < nv; ++k)
-                        if (seg[j + 17 + k] > 15) return 1;
-                if (!build_huff(seg + j + 1, seg + j + 17, nv, tc ? P.ac[th] : P.dc[th])) return 1;
-                j += 17 + (size_t)nv;
-            }
-        } else if (m == 0xC0 || m == 0xC1) {
+            if (parse_dht(seg, sl, P.dc, P.ac)) return 1;
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+            P.progressive = (m == 0xC2);
             if (have_frame || sl < 6 || seg[0] != 8 || (seg[5] != 3 && seg[5] != 1) || sl != 6 + 3 * (size_t)seg[5]) return 1;
             I.ncomp = seg[5];
             I.H = (seg[1] << 8) | seg[2];
@@ -264,9 +273,10 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 if (tq[k] > 3 || hs[k] < 1 || hs[k] > 4 || vs[k] < 1 || vs[k] > 4) return 1;
             }
             if (I.ncomp == 3 && (cid[0] == cid[1] || cid[0] == cid[2] || cid[1] == cid[2])) return 1;
+            for (int k = 0; k < 3; ++k) P.cid[k] = cid[k];
             have_frame = true;
-        } else if (m >= 0xC2 && m <= 0xCF) {
-            return 1;  // progressive, lossless, arithmetic, hierarchical
+        } else if (m >= 0xC3 && m <= 0xCF) {
+            return 1;  // lossless, arithmetic, hierarchical
         } else if (m == 0xDD) {
             if (sl != 2) return 1;
             P.dri = (seg[0] << 8) | seg[1];
@@ -282,14 +292,21 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
             }
         } else if (m == 0xDA) {
             const int nc = I.ncomp;
-            if (!have_frame || sl != 1 + 2 * (size_t)nc + 3 || seg[0] != nc) return 1;
-            for (int k = 0; k < nc; ++k) {
-                if (seg[1 + 2 * k] != cid[k]) return 1;
-                P.td[k] = seg[2 + 2 * k] >> 4;
-                P.ta[k] = seg[2 + 2 * k] & 15;
-                if (P.td[k] > 3 || P.ta[k] > 3 || !P.dc[P.td[k]].present || !P.ac[P.ta[k]].present) return 1;
+            if (!have_frame) return 1;
+            if (P.progressive) {
+                // the scans (their headers, the tables between them) are walked by decode_progressive, from this marker on
+                if (sl < 6) return 1;
+            } else {
+                if (sl != 1 + 2 * (size_t)nc + 3 || seg[0] != nc) return 1;
+                for (int k = 0; k < nc; ++k) {
+                    if (seg[1 + 2 * k] != cid[k]) return 1;
+                    P.td[k] = seg[2 + 2 * k] >> 4;
+                    P.ta[k] = seg[2 + 2 * k] & 15;
+                    if (P.td[k] > 3 || P.ta[k] > 3 || !P.dc[P.td[k]].present || !P.ac[P.ta[k]].present) return 1;
+                }
+                if (seg[1 + 2 * nc] != 0 || seg[2 + 2 * nc] != 63 || seg[3 + 2 * nc] != 0) return 1;
             }
-            if (seg[1 + 2 * nc] != 0 || seg[2 + 2 * nc] != 63 || seg[3 + 2 * nc] != 0) return 1;
+            const size_t scan_data = P.progressive ? i - L - 2 : i;   // progressive: the SOS marker itself
             if (nc == 1) {
                 // a single-component scan is not interleaved: one block per MCU, ceil(W / 8) x ceil(H / 8) blocks whatever
                 // sampling factors the frame header declares; the chroma planes are zero coefficients on the same grid
@@ -310,7 +327,7 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
                 I.n_coef = off;
                 I.cw = I.W;
                 I.ch = I.H;
-                P.ecs = i;
+                P.ecs = scan_data;
                 return 0;
             }
             // colour space as libjpeg guesses it (jdapimin.c default_decompress_parms): JFIF -> YCbCr; else the Adobe
@@ -340,15 +357,248 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
             I.n_coef = off;
             I.cw = (I.W + I.hmax - 1) / I.hmax;
             I.ch = (I.H + I.vmax - 1) / I.vmax;
-            P.ecs = i;
+            P.ecs = scan_data;
             return 0;
         }
     }
     return 1;
 }
 
+// Progressive files (SOF2; jdphuff.c): the coefficients arrive in several scans - DC first / DC refinement over one or all
+// components, AC bands of ONE component as first pass (with end-of-band runs) or refinement pass (correction bits for the
+// coefficients that are already non-zero) - with Huffman tables redefined between them.  Decoded here on the calling
+// thread into the same coefficient planes as a baseline scan; inverse DCT, upsampling and colour conversion are the
+// device kernels.  The rule for anything libjpeg only warns about stays "declined": scans out of the standard progression
+// (a refinement whose Ah is not the previous Al, AC before DC), codes that do not exist, a magnitude other than 1 in a
+// refinement pass, restart markers out of sequence, bytes between a scan and the next marker.  A file whose scans do not
+// bring every coefficient to full precision is declined too: libjpeg then smooths the blocks from their neighbours'
+// DC values (jdcoefct.c decompress_smooth_data), which is not restated.  0 = ok, 1 = declined.
+inline int decode_progressive(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef) {
+    const Info &I = P.info;
+    memset(coef, 0, I.n_coef * sizeof(int16_t));
+    std::vector<HuffTable> dc(P.dc, P.dc + 4), ac(P.ac, P.ac + 4);
+    int dri = P.dri;
+    int cbits[3][64];   // jdphuff.c coef_bits: -1 = not seen yet, else the Al of the last scan that covered the coefficient
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < 64; ++k) cbits[c][k] = -1;
+    size_t i = P.ecs;
+    bool eoi = false;
+    while (i + 2 <= len) {
+        if (d[i] != 0xFF) return 1;
+        while (i + 1 < len && d[i + 1] == 0xFF) ++i;
+        if (i + 2 > len) return 1;
+        const int m = d[i + 1];
+        i += 2;
+        if (m == 0xD9) {
+            eoi = true;
+            break;
+        }
+        if (i + 2 > len) return 1;
+        const size_t L = ((size_t)d[i] << 8) | d[i + 1];
+        if (L < 2 || i + L > len) return 1;
+        const uint8_t *seg = d + i + 2;
+        const size_t sl = L - 2;
+        i += L;
+        if (m == 0xC4) {
+            if (parse_dht(seg, sl, dc.data(), ac.data())) return 1;
+            continue;
+        }
+        if (m == 0xDD) {
+            if (sl != 2) return 1;
+            dri = (seg[0] << 8) | seg[1];
+            continue;
+        }
+        if ((m >= 0xE0 && m <= 0xEF) || m == 0xFE) continue;
+        if (m != 0xDA) return 1;
+        // ---- scan header (jdmarker.c get_sos, jdphuff.c start_pass_phuff_decoder)
+        const int ns = sl ? seg[0] : 0;
+        if (ns < 1 || ns > I.ncomp || sl != 1 + 2 * (size_t)ns + 3) return 1;
+        int comp[3], td[3], ta[3];
+        for (int k = 0; k < ns; ++k) {
+            int c = -1;
+            for (int q = 0; q < I.ncomp; ++q)
+                if (P.cid[q] == seg[1 + 2 * k]) c = q;
+            if (c < 0 || (k && c <= comp[k - 1])) return 1;
+            comp[k] = c;
+            td[k] = seg[2 + 2 * k] >> 4;
+            ta[k] = seg[2 + 2 * k] & 15;
+            if (td[k] > 3 || ta[k] > 3) return 1;
+        }
+        const int Ss = seg[1 + 2 * ns], Se = seg[2 + 2 * ns], Ah = seg[3 + 2 * ns] >> 4, Al = seg[3 + 2 * ns] & 15;
+        const bool dc_scan = (Ss == 0);
+        if (dc_scan ? (Se != 0) : (ns != 1 || Se < Ss || Se > 63)) return 1;
+        if (Al > 13 || (Ah != 0 && Al != Ah - 1)) return 1;
+        for (int k = 0; k < ns; ++k) {
+            int *cb = cbits[comp[k]];
+            if (!dc_scan && cb[0] < 0) return 1;                       // AC before DC
+            for (int z = Ss; z <= Se; ++z) {
+                if (Ah != (cb[z] < 0 ? 0 : cb[z])) return 1;           // not the standard progression
+                cb[z] = Al;
+            }
+            if (Ah == 0 || !dc_scan) {                                 // (a DC refinement reads raw bits only)
+                const HuffTable &t = dc_scan ? dc[td[k]] : ac[ta[k]];
+                if (!t.present) return 1;
+            }
+        }
+        // ---- the scan's entropy-coded data
+        BitReader br;
+        br.p = d + i;
+        br.end = d + len;
+        int pred[3] = {0, 0, 0};
+        unsigned eobrun = 0;
+        int togo = dri, next_rst = 0;
+        const bool interleaved = ns > 1;
+        const int c0 = comp[0];
+        // a single-component scan walks the component's own blocks: ceil(width / 8) x ceil(height / 8)
+        const int cw = (c0 == 0 || I.ncomp == 1) ? I.W : I.cw, chh = (c0 == 0 || I.ncomp == 1) ? I.H : I.ch;
+        const int nx = interleaved ? I.mcux : (cw + 7) / 8, ny = interleaved ? I.mcuy : (chh + 7) / 8;
+        const int p1 = 1 << Al, m1 = -(1 << Al);
+        auto get_bit = [&]() -> int {
+            if (br.n < 1) br.fill();
+            const int b = (int)br.peek(1);
+            br.skip(1);
+            return b;
+        };
+        for (int my = 0; my < ny; ++my) {
+            for (int mx = 0; mx < nx; ++mx) {
+                if (dri) {
+                    if (togo == 0) {
+                        if (br.overran()) return 1;
+                        br.acc = 0;
+                        br.n = 0;
+                        br.marker = false;
+                        br.zero_bits = 0;
+                        if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] != 0xD0 + next_rst) return 1;
+                        next_rst = (next_rst + 1) & 7;
+                        br.p += 2;
+                        pred[0] = pred[1] = pred[2] = 0;
+                        eobrun = 0;
+                        togo = dri;
+                    }
+                    --togo;
+                }
+                if (dc_scan) {
+                    for (int k = 0; k < ns; ++k) {
+                        const int c = comp[k];
+                        const int nb = interleaved ? (c ? 1 : I.hmax * I.vmax) : 1;
+                        for (int b = 0; b < nb; ++b) {
+                            const int by = interleaved ? (c ? my : my * I.vmax + b / I.hmax) : my;
+                            const int bx = interleaved ? (c ? mx : mx * I.hmax + b % I.hmax) : mx;
+                            int16_t *blk = coef + I.coef_off[c] + ((size_t)by * I.bw[c] + bx) * 64;
+                            if (Ah == 0) {
+                                if (br.n < 32) br.fill();
+                                const int sz = decode_sym(br, dc[td[k]]);
+                                if (sz < 0 || sz > 11) return 1;
+                                if (sz) pred[c] += receive_extend(br, sz);
+                                blk[0] = (int16_t)(pred[c] * p1);
+                            } else if (get_bit()) {
+                                blk[0] = (int16_t)(blk[0] | p1);
+                            }
+                        }
+                    }
+                    continue;
+                }
+                int16_t *blk = coef + I.coef_off[c0] + ((size_t)my * I.bw[c0] + mx) * 64;
+                const HuffTable &act = ac[ta[0]];
+                if (Ah == 0) {   // decode_mcu_AC_first
+                    if (eobrun > 0) {
+                        --eobrun;
+                        continue;
+                    }
+                    for (int k = Ss; k <= Se; ++k) {
+                        if (br.n < 32) br.fill();
+                        const int rs = decode_sym(br, act);
+                        if (rs < 0) return 1;
+                        const int r = rs >> 4, sz = rs & 15;
+                        if (sz) {
+                            k += r;
+                            if (k > Se) return 1;
+                            blk[kNat[k]] = (int16_t)(receive_extend(br, sz) * p1);
+                        } else if (r == 15) {
+                            k += 15;
+                        } else {
+                            eobrun = 1u << r;
+                            if (r) {
+                                eobrun += br.peek(r);
+                                br.skip(r);
+                            }
+                            --eobrun;
+                            break;
+                        }
+                    }
+                    continue;
+                }
+                // decode_mcu_AC_refine
+                int k = Ss;
+                if (eobrun == 0) {
+                    for (; k <= Se; ++k) {
+                        if (br.n < 32) br.fill();
+                        const int rs = decode_sym(br, act);
+                        if (rs < 0) return 1;
+                        int r = rs >> 4, sz = rs & 15, val = 0;
+                        if (sz) {
+                            if (sz != 1) return 1;
+                            val = get_bit() ? p1 : m1;
+                        } else if (r != 15) {
+                            eobrun = 1u << r;
+                            if (r) {
+                                eobrun += br.peek(r);
+                                br.skip(r);
+                            }
+                            break;
+                        }
+                        // over the coefficients that are already non-zero (a correction bit each) and r zero ones
+                        do {
+                            int16_t *cf = blk + kNat[k];
+                            if (*cf != 0) {
+                                if (get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                            } else if (--r < 0) {
+                                break;
+                            }
+                            ++k;
+                        } while (k <= Se);
+                        if (val) {
+                            if (k > Se) return 1;
+                            blk[kNat[k]] = (int16_t)val;
+                        }
+                    }
+                }
+                if (eobrun > 0) {   // the rest of the band: correction bits only
+                    for (; k <= Se; ++k) {
+                        int16_t *cf = blk + kNat[k];
+                        if (*cf != 0 && get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                    }
+                    --eobrun;
+                }
+            }
+        }
+        if (br.overran()) return 1;
+        i = (size_t)(br.p - d);   // the reader stops in front of the marker that ends the scan
+    }
+    if (!eoi) return 1;
+    for (int c = 0; c < I.ncomp; ++c)
+        for (int k = 0; k < 64; ++k)
+            if (cbits[c][k] != 0) return 1;   // not at full precision: libjpeg would smooth (see above)
+    // damaged data shows as blocks no 8-bit encoder produces (see kMaxBlockNorm): libjpeg's SIMD IDCT wraps on them
+    for (int c = 0; c < I.ncomp; ++c) {
+        float qf[64];
+        for (int k = 0; k < 64; ++k) qf[k] = (float)I.quant[c][k];
+        const int16_t *blk = coef + I.coef_off[c];
+        for (size_t b = 0, nb = (size_t)I.bw[c] * I.bh[c]; b < nb; ++b, blk += 64) {
+            float e = 0.f;
+            for (int k = 0; k < 64; ++k) {
+                const float v = (float)blk[k] * qf[k];
+                e += v * v;
+            }
+            if (e > kMaxBlockNorm * kMaxBlockNorm) return 1;
+        }
+    }
+    return 0;
+}
+
 // Huffman-decode the scan into `coef` (int16, natural order, component planes [by][bx][64]).  0 = ok, 1 = damaged.
 inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef) {
+    if (P.progressive) return decode_progressive(d, len, P, coef);
     const Info &I = P.info;
     BitReader br;
     br.p = d + P.ecs;

@@ -34,6 +34,7 @@ def parse(data: bytes):
     qt, huff = {}, {}
     frame, scan, dri = None, None, 0
     jfif, adobe = False, None
+    progressive = False
     while i < len(data):
         if data[i] != 0xFF:
             raise Unsupported("marker expected")
@@ -71,14 +72,15 @@ def parse(data: bytes):
                 vals = list(seg[j + 17:j + 17 + n])
                 huff[tc_th] = (bits, vals)
                 j += 17 + n
-        elif m in (0xC0, 0xC1):
+        elif m in (0xC0, 0xC1, 0xC2):
+            progressive = (m == 0xC2)
             if seg[0] != 8:
                 raise Unsupported("sample precision")
             H, W, nc = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4], seg[5]
             comps = [(seg[6 + 3 * k], seg[7 + 3 * k] >> 4, seg[7 + 3 * k] & 15, seg[8 + 3 * k]) for k in range(nc)]
             frame = dict(W=W, H=H, comps=comps)
-        elif 0xC2 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
-            raise Unsupported("not a baseline / extended sequential Huffman JPEG")
+        elif 0xC3 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            raise Unsupported("not a baseline / extended sequential / progressive Huffman JPEG")
         elif m == 0xDD:
             dri = (seg[0] << 8) | seg[1]
         elif m == 0xE0 and len(seg) >= 14 and seg[:5] == b"JFIF\x00":
@@ -88,14 +90,16 @@ def parse(data: bytes):
         elif m == 0xDA:
             ns = seg[0]
             scan = [(seg[1 + 2 * k], seg[2 + 2 * k] >> 4, seg[2 + 2 * k] & 15) for k in range(ns)]
-            if frame is None or ns != len(frame["comps"]):
+            if frame is None or (ns != len(frame["comps"]) and not progressive):
                 raise Unsupported("non-interleaved scans")
             # jdapimin.c default_decompress_parms, 3 components: JFIF -> YCbCr; else Adobe transform 0 -> RGB, other ->
             # YCbCr; else component ids 'R','G','B' -> RGB, anything else YCbCr
             ids = bytes(c[0] for c in frame["comps"])
             if len(ids) == 3 and not jfif and (adobe == 0 if adobe is not None else ids == b"RGB"):
                 raise Unsupported("RGB-coded file")
-            return dict(frame=frame, qt=qt, huff=huff, scan=scan, dri=dri, ecs=data[i:])
+            # (a progressive file: only the frame and the quantisation tables are of use here - the pixel pipeline behind the
+            # coefficients, reconstruct(), is the same; its scans are not restated in this model)
+            return dict(frame=frame, qt=qt, huff=huff, scan=scan, dri=dri, ecs=data[i:], progressive=progressive)
     raise Unsupported("no scan")
 
 
@@ -164,6 +168,8 @@ def extend(v, s):
 
 def entropy_decode(p):
     """Coefficient planes per component: [blocks_y, blocks_x, 64] natural order, on the MCU-padded block grid."""
+    if p.get("progressive"):
+        raise Unsupported("progressive scans are not restated in this model (see parse)")
     f = p["frame"]
     comps = f["comps"]
     if len(comps) == 1:          # a single-component scan is not interleaved: one block per MCU whatever the sampling factors

@@ -144,9 +144,33 @@ def test_upload_jpeg_equals_imread_path(pkg, proj, tmp_path):
         want = proj.project(s, shifts, consts, W, H)
         proj.sync(s)
     assert np.array_equal(got, want)
-    with pytest.raises(pkg.P2PError) as ei:
-        proj.decode_jpeg(cv2.imencode(".jpg", pano[:64, :64], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes())
+    with pytest.raises(pkg.P2PError) as ei:   # outside the decoder's subset: the caller falls back to cv2.imread
+        proj.decode_jpeg(cv2.imencode(".png", pano[:64, :64])[1].tobytes())
     assert ei.value.code == -6
+
+
+@pytest.mark.parametrize("sname", ["420", "422", "444"])
+def test_progressive_files_decode_like_cv2(pkg, proj, tmp_path, sname):
+    """Progressive JPEG files (SOF2): the scans are decoded by the library on the calling thread, IDCT / upsampling /
+    colour run on the device; same pixels as cv2.imdecode, through decode_jpeg, upload_jpeg and the front door."""
+    rng = np.random.default_rng(5)
+    for (w, h, q, rst) in [(1, 1, 90, 0), (17, 33, 95, 0), (240, 136, 75, 7), (1000, 333, 50, 0), (2048, 1024, 92, 0)]:
+        img = synth.smooth(w, h, 3) if w >= 8 and w != 240 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        data = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_PROGRESSIVE, 1,
+                                          cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING[sname]])[1].tobytes()
+        assert b"\xff\xc2" in data[:800]
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(proj.decode_jpeg(data), ref), (w, h, q, rst)
+    Wp, Hp, W, H, fov = 2048, 1024, 240, 136, 120
+    with proj.slots(1) as (s,):
+        assert proj.upload_jpeg(s, data) == (Wp, Hp)
+        assert np.array_equal(proj.download_pano(s, Wp, Hp), ref)
+    path = tmp_path / "progressive.jpg"
+    path.write_bytes(data)
+    view = pkg.panorama_to_plane(path, fov, (W, H), 90, 60)
+    assert np.array_equal(view, pkg.process_yaw_and_pitchs(cv2.imread(str(path)), 90, [60], W, H, fov)[0])
+    g = cv2.imencode(".jpg", img[..., 1], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()   # grayscale, progressive
+    assert np.array_equal(proj.decode_jpeg(g), cv2.imdecode(np.frombuffer(g, np.uint8), cv2.IMREAD_COLOR))
 
 
 def test_front_end_jpeg_input_equals_imread_path(pkg, tmp_path):

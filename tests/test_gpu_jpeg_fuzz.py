@@ -73,7 +73,7 @@ def test_damaged_files_are_declined_or_decode_like_cv2(pkg, proj, capfd):
         proj.set_option(L.OPT_GPU_HUFFMAN, device_stage)
         declined = same = 0
         try:
-            for label, data in damaged_files(77, 300, max_wh=(400, 300), gray_every=5):
+            for label, data in damaged_files(77, 300, max_wh=(400, 300), gray_every=5, progressive_every=4):
                 ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
                 try:
                     got = proj.decode_jpeg(data)

@@ -82,6 +82,71 @@ def test_host_huffman_stage_equals_oracle(pkg):
         assert np.array_equal(coef, np.concatenate([p.reshape(-1) for p in planes]).astype(np.int16)), name
 
 
+def _coefficients(lib, data):
+    import ctypes as C
+
+    lay = (C.c_int32 * 10)()
+    if lib.p2p_jpeg_coefficients(data, len(data), None, 0, lay) != 0:
+        return None
+    coef = np.zeros(sum(lay[4 + 2 * k] * lay[5 + 2 * k] * 64 for k in range(3)), np.int16)
+    return coef if lib.p2p_jpeg_coefficients(data, len(data), coef.ctypes.data, coef.size, lay) == 0 else None
+
+
+def progressive_cases():
+    rng = np.random.default_rng(21)
+    for (h, w) in [(1, 1), (8, 8), (17, 33), (47, 95), (128, 200), (333, 500)]:
+        for sname, sv in SAMPLING.items():
+            for q, rst in ((95, 0), (75, 0), (50, 5), (100, 1)):
+                kind = (h * 7 + w + q) % 3
+                img = (rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if kind == 0 else synth.smooth(w, h, q) if kind == 1
+                       else np.clip(synth.smooth(w, h, q).astype(int) + rng.integers(-20, 21, (h, w, 3)), 0, 255).astype(np.uint8))
+                yield f"{w}x{h}_{sname}_q{q}_rst{rst}", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,
+                                                              cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sv]
+
+
+def test_progressive_files_give_the_baseline_coefficients(pkg):
+    """Progressive files (SOF2: DC / AC, first / refinement scans, end-of-band runs, restart intervals; decoded by the
+    library's host decoder, no GPU needed): the quantised coefficients are the ones the baseline file of the same image
+    holds - the two differ only in their entropy coding - and cv2 decodes both files to the same pixels, which the oracle's
+    IDCT / upsampling / colour model reproduces from these coefficients."""
+    from oracle import jpeg_decode_model as jd
+
+    lib = pkg._lib.load()
+    n = 0
+    for name, img, params in progressive_cases():
+        base = cv2.imencode(".jpg", img, params)[1].tobytes()
+        prog = cv2.imencode(".jpg", img, params + [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()
+        assert b"\xff\xc2" in prog[:800], name
+        want, got = _coefficients(lib, base), _coefficients(lib, prog)
+        assert want is not None and got is not None, name
+        assert np.array_equal(got, want), name
+        ref = cv2.imdecode(np.frombuffer(prog, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(ref, cv2.imdecode(np.frombuffer(base, np.uint8), cv2.IMREAD_COLOR)), name
+        if img.shape[0] <= 128:   # (the NumPy model is slow)
+            p = jd.parse(base)
+            planes, _ = jd.entropy_decode(p)
+            shapes = [pl.shape for pl in planes]
+            mine, o = [], 0
+            for sh in shapes:
+                k = int(np.prod(sh))
+                mine.append(got[o:o + k].reshape(sh).astype(planes[0].dtype))
+                o += k
+            assert np.array_equal(jd.reconstruct(p, mine), ref), name
+        n += 1
+    # grayscale progressive files, and files the decoder must decline: a scan script that stops before full precision
+    # (libjpeg then smooths blocks from their neighbours), a truncated file
+    g = synth.smooth(100, 60, 3)[..., 1]
+    gb = cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes()
+    gp = cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()
+    assert np.array_equal(_coefficients(lib, gp), _coefficients(lib, gb))
+    prog = cv2.imencode(".jpg", synth.smooth(200, 120, 5), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes()
+    assert _coefficients(lib, prog) is not None
+    last_sos = prog.rfind(b"\xff\xda")
+    assert _coefficients(lib, prog[:last_sos] + b"\xff\xd9") is None      # last refinement scan missing
+    assert _coefficients(lib, prog[:len(prog) * 2 // 3]) is None            # truncated
+    assert n >= 60
+
+
 def test_unsupported_files_are_reported(pkg):
     import ctypes as C
 
@@ -93,8 +158,9 @@ def test_unsupported_files_are_reported(pkg):
     png = cv2.imencode(".png", img)[1].tobytes()
     ok = cv2.imencode(".jpg", img)[1].tobytes()
     cmyk = ok.replace(b"\xff\xc0\x00\x11\x08", b"\xff\xc0\x00\x14\x08", 1)   # a frame header announcing more data
-    for data in (prog, png, ok[:300], cmyk, b""):
+    for data in (png, ok[:300], cmyk, b""):
         assert lib.p2p_jpeg_probe(data, len(data), C.byref(w), C.byref(h)) == -6
+    assert lib.p2p_jpeg_probe(prog, len(prog), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
     assert lib.p2p_jpeg_probe(gray, len(gray), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
     assert lib.p2p_jpeg_probe(ok, len(ok), C.byref(w), C.byref(h)) == 0 and (w.value, h.value) == (64, 48)
     # a truncated scan must not be decoded with made-up bits: libjpeg has its own recovery, the file is left to it
@@ -145,7 +211,7 @@ def test_damaged_files_are_declined_or_decode_like_cv2(pkg, capfd):
 
     lib = pkg._lib.load()
     declined = same = 0
-    for label, data in damaged_files(2025, 400, gray_every=4):
+    for label, data in damaged_files(2025, 400, gray_every=4, progressive_every=3):
         ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
         st, planes = _host_stage(lib, data)
         if st:
@@ -217,7 +283,7 @@ def test_host_decoder_under_address_sanitizer(tmp_path):
         pytest.skip("sanitizer runtime not available: " + build.stderr[-300:])
     rng = np.random.default_rng(9)
     names = []
-    for k, (label, data) in enumerate(damaged_files(301, 600, gray_every=3)):
+    for k, (label, data) in enumerate(damaged_files(301, 600, gray_every=3, progressive_every=4)):
         d = bytearray(data)
         if k % 3 == 0:                                     # heavier damage: garbage runs, truncation
             for _ in range(int(rng.integers(1, 6))):

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--max-w", type=int, default=700)
     ap.add_argument("--max-h", type=int, default=500)
     ap.add_argument("--gray-every", type=int, default=0, help="every k-th file is a grayscale JPEG")
+    ap.add_argument("--progressive-every", type=int, default=0, help="every k-th file is a progressive JPEG")
     a = ap.parse_args()
     pkg = importlib.import_module("360-to-planer-images_b200")
     L = pkg._lib
@@ -37,7 +38,7 @@ def main():
         n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
         t0 = time.time()
         for seed in a.seeds:
-            for label, data in damaged_files(seed, a.count, max_wh=(a.max_w, a.max_h), gray_every=a.gray_every):
+            for label, data in damaged_files(seed, a.count, max_wh=(a.max_w, a.max_h), gray_every=a.gray_every, progressive_every=a.progressive_every):
                 st["files"] += 1
                 ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
                 st["cv2_unreadable"] += ref is None
