@@ -10,8 +10,9 @@
 //   device jidctint.c jpeg_idct_islow on dequantised coefficients, + 128, clamp            (jpegdec_idct_kernel)
 //          jdsample.c h2v2 / h2v1 fancy upsampling (triangle filters, alternating rounding; replication when the
 //                     chroma plane is at most 2 samples wide), jdcolor.c ycc_rgb_convert   (jpegdec_color_kernel)
-// Supported: 8-bit, 3 components (YCbCr; 4:4:4 / 4:2:2 / 4:2:0) or 1 (grayscale), SOF0 / SOF1, one scan, restart markers.
-// Anything else (progressive, CMYK, RGB-coded files, EXIF orientation != 1, damaged data) is reported as
+// Supported: 8-bit, 3 components (YCbCr; 4:4:4 / 4:2:2 / 4:2:0) or 1 (grayscale); SOF0 / SOF1 with one scan and restart
+// markers (Huffman stage on the device), SOF2 progressive files (jdphuff.c restated on the host, decode_progressive).
+// Anything else (CMYK, RGB-coded files, EXIF orientation != 1, damaged data) is reported as
 // unsupported and the caller falls back to cv2.imread, as the reference does for every file.
 #pragma once
 #include <cuda_runtime.h>

@@ -424,11 +424,15 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     e2e_files = None
     if not args.no_extras:
         e2e_files = files_flow(pkg, proj, synth.smooth(WP, HP, rank), shifts, consts, "jpg", world, barrier, max_over_ranks)
+        # the reference's default output format: 34 MB of PNG files per image go back over PCIe instead of 4 MB
+        e2e_files["png"] = files_flow(pkg, proj, synth.smooth(WP, HP, rank), shifts, consts, "png", world, barrier, max_over_ranks,
+                                      n_img=48)
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = files_extras(pkg, proj, synth.smooth(WP, HP, 0), shifts, consts)
         extras["configs"] = config_fractions(pkg, proj, synth, torch)
+        extras["fractional_yaw"] = fractional_yaw_times(pkg, proj, synth, torch)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -542,7 +546,7 @@ def oracle_check(proj, pano, seed):
             else "tolerance (host NumPy does not take the SVML path: the reference itself differs in the last ulp here)"}
 
 
-def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=32, n_thr=8):
+def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=96, n_thr=8):
     """Files to files on every rank: an 8192x4096 JPEG file in host memory -> the 12 views as files in page-locked host
     memory; Huffman decode, IDCT, projection and encode all on the GPU, n_thr images in flight per rank.  Whole-job
     Mpix/s = all ranks' images / the slowest rank's time."""
@@ -550,8 +554,8 @@ def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ra
     from concurrent.futures import ThreadPoolExecutor
 
     data = cv2.imencode(".jpg", pano)[1].tobytes()
-    # images in flight per rank: the host half of the decoder (removing the FF 00 stuffing) runs on the calling thread, so
-    # the ranks of one box share its cores
+    # images in flight per rank = host threads: a waiting thread spins on its stream (the CUDA default), so the ranks of one box
+    # share its cores - 8 threads on each of 8 ranks of a 32-vCPU box cost a third of the throughput (profiles/r2_files_flow_*)
     n_thr = max(2, min(n_thr, (os.cpu_count() or 8) // max(1, world)))
 
     def one(_):
@@ -616,6 +620,39 @@ def config_fractions(pkg, proj, synth, torch):
     return out
 
 
+def fractional_yaw_times(pkg, proj, synth, torch):
+    """A yaw that is not an integer column roll (ref :191-199 + :212-218), 3 pitches of the README example on a resident
+    8192x4096 panorama: the one-pass kernel (both remap passes per output pixel) against the materialised yaw pass +
+    projection it replaces.  Device time, CUDA events, same pixels (checked)."""
+    yaw = 33.3
+    ix, fx, shift = pkg.yaw_table(WP, yaw)
+    assert shift is None
+    consts = [pkg.pitch_constants(W, FOV, p) for p in PITCHES]
+    ev0, ev1 = proj.event(), proj.event()
+    with proj.slots(2) as (a, b):
+        proj.upload(a, synth.noise(WP, HP, 0))
+        proj.sync(a)
+        d1 = torch.empty((1, len(PITCHES), H, W, 3), dtype=torch.uint8, device=f"cuda:{proj.device}")
+        d2 = torch.empty_like(d1)
+        one, two = [], []
+        for _ in range(6):
+            proj.record(ev0, a)
+            proj.project_tables(a, [(ix, fx)], consts, W, H, out_device_ptr=d1.data_ptr())
+            proj.record(ev1, a)
+            proj.sync(a)
+            one.append(proj.elapsed_ms(ev0, ev1))
+            proj.record(ev0, b)
+            proj.rotate(a, b, ix, fx)
+            proj.project(b, [0], consts, W, H, out_device_ptr=d2.data_ptr())
+            proj.record(ev1, b)
+            proj.sync(b)
+            two.append(proj.elapsed_ms(ev0, ev1))
+        same = bool(torch.equal(d1, d2))
+    return {"yaw": yaw, "views": len(PITCHES), "one_pass_us": statistics.median(one[1:]) * 1e3,
+            "rotate_then_project_us": statistics.median(two[1:]) * 1e3, "identical": same,
+            "note": "the two-pass figure includes the yaw table upload the rotate entry point waits for"}
+
+
 def files_extras(pkg, proj, pano, shifts, consts):
     """Side measurement (not the headline metric): the codec rows either side of the path.  One 8192x4096
     JPEG file in host memory -> the 12 views as jpg / png files in (page-locked) host memory, (a) decoded, projected and
@@ -627,7 +664,7 @@ def files_extras(pkg, proj, pano, shifts, consts):
     from oracle import ref_port
 
     data = cv2.imencode(".jpg", pano)[1].tobytes()
-    n_img, n_thr = 8, 4
+    n_img, n_thr = 32, 4
     out = {}
     for fmt in ("jpg", "png"):
         def gpu_one(keep):

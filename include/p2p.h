@@ -246,7 +246,8 @@ int p2p_process_image_png(p2p_ctx *ctx, int slot, const uint8_t *bgr, int Wp, in
 
 /* ---- JPEG panoramas decoded on the device (replaces cv2.imread(path) of a .jpg / .jpeg input, ref :244) ---- */
 /* Headers only: size of the image if the file is in the supported subset (8-bit YCbCr 4:4:4 / 4:2:2 / 4:2:0 or
- * grayscale, baseline or extended sequential Huffman, one scan, restart markers allowed, YCbCr by libjpeg's own rule (JFIF marker, or an Adobe marker with a non-zero transform flag
+ * grayscale, baseline or extended sequential Huffman with one scan, or progressive (SOF2: any standard scan progression that
+ * reaches full precision), restart markers allowed, YCbCr by libjpeg's own rule (JFIF marker, or an Adobe marker with a non-zero transform flag
  * as Photoshop / Lightroom write it, or component ids other than 'R' 'G' 'B'), EXIF
  * orientation 1 or absent), else P2P_ERR_UNSUPPORTED - the caller then reads the file with cv2.imread as before. */
 int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
@@ -256,8 +257,9 @@ int p2p_jpeg_probe(const uint8_t *file, size_t len, int *W, int *H);
 int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t capacity, int32_t *layout);
 /* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, bit-identical pixels): Huffman
  * decoding (self-synchronising subsequences; P2P_OPT_GPU_HUFFMAN), inverse DCT, chroma upsampling and colour
- * conversion all run on the device, the host only removes the FF 00 byte stuffing; the pixels never exist in host
- * memory.  If the device Huffman stage does not converge the library's own host decoder (calling thread, outside the
+ * conversion all run on the device (the FF 00 byte stuffing is removed there too when the file has no restart markers); the
+ * pixels never exist in host memory.  The scans of a progressive file are decoded on the calling thread (jdphuff.c), everything
+ * behind them on the device.  If the device Huffman stage does not converge the library's own host decoder (calling thread, outside the
  * context lock) takes over.  Returns after the decode has finished on the device: a damaged file (truncated scan,
  * restart markers out of sequence, codes or coefficient blocks no 8-bit encoder writes) gives P2P_ERR_UNSUPPORTED
  * and leaves the slot without a panorama - such files are decoded like libjpeg or not at all, never differently. */
