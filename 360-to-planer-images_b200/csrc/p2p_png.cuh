@@ -5,12 +5,16 @@
 // memLevel 8, 32 KiB window, IDAT chunks of 8192 bytes.  Everything is deterministic integer work, restated here so the
 // file is byte-identical to cv2.imwrite's (oracle/png_model.py is the Python restatement, pinned against zlib and
 // cv2.imencode):
-//   deflate.c  deflate_rle: greedy matches at distance 1 - a pure function of the maximal byte runs, so the tokens of
-//              every position follow from "where did my run start" (one max-scan) and two look-ahead bytes
-//   trees.c    one thread per deflate block (16383 symbols) runs build_tree / gen_bitlen / gen_codes / scan_tree /
-//              send_tree / build_bl_tree exactly (heap order and depth tie-breaks included) and picks static / dynamic
-//   emission   one CTA per block: local prefix sum of code lengths, LSB-first bits OR-ed into the stream
-//   pngwrite.c Adler-32, 8192-byte IDAT chunks, CRC-32 per chunk, IHDR / IEND
+//   deflate.c  deflate_rle: greedy matches at distance 1 - a pure function of the maximal byte runs, so the token of
+//              every position follows from where its run starts and ends: a forward max-scan and a backward min-scan
+//              of the change positions inside 4096-byte tiles, prefix max / prefix sum over the tiles
+//   trees.c    one warp per deflate block (16383 symbols), state in shared memory: build_tree / gen_bitlen / gen_codes /
+//              scan_tree / send_tree / build_bl_tree exactly (heap order and depth tie-breaks included: lane 0 walks
+//              zlib's heap, the lanes share everything else) and the static / dynamic / stored decision
+//   emission   one CTA per block: tiles of 1024 positions, prefix sum of code lengths, bits assembled LSB-first in shared
+//              memory and written as whole words
+//   pngwrite.c Adler-32 (with the first tile pass), 8192-byte IDAT chunks, CRC-32 per chunk (a warp per chunk, staged in
+//              shared memory), IHDR / IEND
 // Also restated: blocks zlib stores uncompressed (_tr_stored_block: white noise), the window bits libpng writes into the
 // zlib header of small images (optimize_cmf, <= 16384 bytes of data), filter type 0 for images one pixel wide, streams
 // ending exactly on an IDAT boundary.  sizes[i] = 0 ("fall back to cv2.imwrite") is only left for a stream that would
