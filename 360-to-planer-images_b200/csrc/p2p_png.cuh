@@ -436,8 +436,8 @@ png_hist_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen
 // codes and write the tables; the header bits are assembled in shared memory.
 constexpr int kTreeWarps = 4;            // deflate blocks per CTA
 
-struct TreeShared {
-    uint32_t heap[kHeapSize + 1];        // heap entries: freq << 16 | depth << 10 | node; below heap_max: node numbers
+struct alignas(16) TreeShared {
+    uint32_t heap[kHeapSize + 3];        // heap entries: freq << 16 | depth << 10 | node; below heap_max: node numbers
     uint16_t freq[kHeapSize], dad[kHeapSize];
     uint8_t len[kHeapSize];              // depth of a node while the tree is built (trees.c depth[]), its code length after
     uint32_t bl_count[kMaxBits + 1];
@@ -509,20 +509,39 @@ __device__ int build_tree(TreeShared &t, const int lane, int *opt_len, int *stat
             d_opt--;
             d_static -= stree_len(node);
         }
+        // trees.c pqdownheap, two levels per shared-memory round trip: the children (one 8-byte load) and the four
+        // grandchildren (one 16-byte load) of the current node are fetched together - the entries a step can move are the
+        // ones above them, so the values are the ones a level-by-level walk would read; index checks come before any use
+        // (entries behind heap_len are stale or belong to the sorted region)
         auto pqdownheap = [&](int k) {
             const uint32_t v = t.heap[k];
-            int j = k << 1;
-            while (j <= heap_len) {
-                uint32_t hj = t.heap[j];
-                const uint32_t hj1 = t.heap[j + 1];              // (heap[heap_len + 1] exists; its value is not used)
-                if (j < heap_len && (hj1 >> 10) <= (hj >> 10)) {   // smaller(heap[j + 1], heap[j])
-                    hj = hj1;
+            const uint32_t vk = v >> 10;
+            for (;;) {
+                int j = k << 1;
+                if (j > heap_len) break;
+                const uint2 c = *reinterpret_cast<const uint2 *>(&t.heap[j]);
+                uint4 g = make_uint4(0u, 0u, 0u, 0u);
+                if ((j << 1) <= heap_len) g = *reinterpret_cast<const uint4 *>(&t.heap[j << 1]);
+                uint32_t hj = c.x;
+                const bool right = j < heap_len && (c.y >> 10) <= (c.x >> 10);   // smaller(heap[j + 1], heap[j])
+                if (right) {
+                    hj = c.y;
                     j++;
                 }
-                if ((v >> 10) <= (hj >> 10)) break;               // smaller(v, heap[j])
+                if (vk <= (hj >> 10)) break;                                       // smaller(v, heap[j])
                 t.heap[k] = hj;
                 k = j;
-                j <<= 1;
+                j = k << 1;
+                if (j > heap_len) break;
+                const uint32_t a = right ? g.z : g.x, b = right ? g.w : g.y;
+                hj = a;
+                if (j < heap_len && (b >> 10) <= (a >> 10)) {
+                    hj = b;
+                    j++;
+                }
+                if (vk <= (hj >> 10)) break;
+                t.heap[k] = hj;
+                k = j;
             }
             t.heap[k] = v;
         };
