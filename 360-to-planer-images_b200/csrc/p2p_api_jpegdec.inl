@@ -353,8 +353,9 @@ int device_huffman(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const
 }
 
 // IDCT, upsampling and colour conversion of the coefficients in s.jd_coef_d (or s.jd_coef_h when the host decoded them)
-// into the slot's BGR staging image (s.d_bgr, row stride = Wp * 3 rounded to 4).
-int jd_pixels(p2p_ctx *ctx, Slot &s, const p2pjdec::Parsed &P, bool coef_on_device, size_t *dstride) {
+// into the slot's BGR staging image (s.d_bgr, row stride = Wp * 3 rounded to 4) or, `packed`, straight into the slot's
+// panorama (what launch_pack would make of the staging image: p2p_upload_pano_jpeg never needs the BGR form).
+int jd_pixels(p2p_ctx *ctx, Slot &s, const p2pjdec::Parsed &P, bool coef_on_device, size_t *dstride, bool packed) {
     using namespace p2pjdec;
     const Info &I = P.info;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -367,7 +368,14 @@ int jd_pixels(p2p_ctx *ctx, Slot &s, const p2pjdec::Parsed &P, bool coef_on_devi
     *dstride = ((size_t)I.W * 3 + 3) & ~(size_t)3;
     int rc = ensure(ctx, &s.jd_coef_d, &s.jd_coef_d_cap, I.n_coef * sizeof(int16_t));
     if (!rc) rc = ensure(ctx, &s.jd_planes, &s.jd_planes_cap, plane_bytes);
-    if (!rc) rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, *dstride * I.H);
+    if (!rc && !packed) rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, *dstride * I.H);
+    if (packed) s.valid = false;   // the colour kernel writes the panorama itself: whatever the slot held is gone from here on
+    if (!rc && packed) rc = prepare_slot(ctx, s, I.W, I.H);
+    cudaSurfaceObject_t surf = 0;
+    if (!rc && packed && ctx->opt_sampler == 1) {
+        rc = ensure_array(ctx, s);
+        surf = s.surf;
+    }
     if (rc) return rc;
     if (!coef_on_device)
         CK(cudaMemcpyAsync(s.jd_coef_d, s.jd_coef_h, I.n_coef * sizeof(int16_t), cudaMemcpyHostToDevice, s.stream));
@@ -387,8 +395,20 @@ int jd_pixels(p2p_ctx *ctx, Slot &s, const p2pjdec::Parsed &P, bool coef_on_devi
     C.W = I.W; C.H = I.H; C.hmax = I.hmax; C.vmax = I.vmax; C.cw = I.cw; C.ch = I.ch;
     C.bgr = s.d_bgr;
     C.stride = *dstride;
+    C.rgba = s.d_rgba;
+    C.pitch_tex = s.pitch_tex;
+    C.surf = surf;
     if (I.H > 65535) return fail(ctx, P2P_ERR_LIMIT, "image too tall for one grid");
-    jpegdec_color_kernel<<<dim3(((I.W + 3) / 4 + 255) / 256, I.H), 256, 0, s.stream>>>(C);
+    const dim3 cgrid(((I.W + 3) / 4 + 255) / 256, I.H);
+    if (packed) {
+        jpegdec_color_kernel<true><<<cgrid, 256, 0, s.stream>>>(C);
+        s.valid = true;
+        s.row0 = 0;
+        s.row1 = I.H;
+        s.tex_current = (surf != 0);
+    } else {
+        jpegdec_color_kernel<false><<<cgrid, 256, 0, s.stream>>>(C);
+    }
     ctx->launches += 4;
     CK(cudaGetLastError());
     return P2P_OK;
@@ -407,7 +427,8 @@ int jd_host_scan(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p
 // Decode `file` into the slot's BGR staging image.  The Huffman stage runs on the device (queued optimistically in the
 // default mode: see jd_resolve) or on the calling thread WITHOUT the context lock; the lock is only taken to size
 // buffers and to enqueue.
-int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pjdec::Parsed &P, size_t *dstride) {
+int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pjdec::Parsed &P, size_t *dstride,
+                           bool packed) {
     using namespace p2pjdec;
     if (parse_headers(file, len, P)) return P2P_ERR_UNSUPPORTED;
     const Info &I = P.info;
@@ -445,13 +466,13 @@ int decode_jpeg_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t l
         const int rc = jd_host_scan(ctx, s, file, len, P);
         if (rc) return rc;
     }
-    return jd_pixels(ctx, s, P, coef_on_device, dstride);
+    return jd_pixels(ctx, s, P, coef_on_device, dstride, packed);
 }
 
 // After the caller's wait on the slot's stream: the verdict of an optimistically queued Huffman stage.  P2P_OK = the
 // staging image stands; 2 = the stage had to be completed (more rounds on the device, or the host decoder) and the
 // staging image was queued again: the caller repeats what it queued behind it and waits once more; else an error.
-int jd_resolve(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, const p2pjdec::Parsed &P, size_t *dstride) {
+int jd_resolve(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, const p2pjdec::Parsed &P, size_t *dstride, bool packed) {
     Slot &s = ctx->slots[slot];
     if (!s.jd_run.pending) return P2P_OK;
     s.jd_run.pending = false;
@@ -472,7 +493,7 @@ int jd_resolve(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, const p2
         const int rc = jd_host_scan(ctx, s, file, len, P);
         if (rc) return rc;
     }
-    const int rc = jd_pixels(ctx, s, P, coef_on_device, dstride);
+    const int rc = jd_pixels(ctx, s, P, coef_on_device, dstride, packed);
     return rc ? rc : 2;
 }
 
@@ -510,26 +531,18 @@ int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len
     if (!slot_ok(ctx, slot) || !file || !Wp || !Hp) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2pjdec::Parsed P;
     size_t dstride = 0;
-    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride);
+    Slot &s = ctx->slots[slot];
+    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride, true);
     if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
     if (rc) return rc;
-    Slot &s = ctx->slots[slot];
+    *Wp = P.info.W;
+    *Hp = P.info.H;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        {
-            std::lock_guard<std::mutex> lk(ctx->mu);
-            CK(cudaSetDevice(ctx->device));
-            rc = prepare_slot(ctx, s, P.info.W, P.info.H);
-            if (rc) return rc;
-            *Wp = P.info.W;
-            *Hp = P.info.H;
-            rc = launch_pack(ctx, s, s.d_bgr, dstride, 0, P.info.H);
-            if (rc) return rc;
-        }
         // the IDCT reports coefficient blocks no 8-bit encoder produces (damaged data), an optimistically queued Huffman
         // stage its verdict: wait for both outside the lock
         cudaSetDevice(ctx->device);
         if (wait_slot(ctx, s) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "JPEG decoder: CUDA error");
-        rc = jd_resolve(ctx, slot, file, len, P, &dstride);
+        rc = jd_resolve(ctx, slot, file, len, P, &dstride, true);
         if (rc == P2P_OK) break;
         if (rc != 2) {
             std::lock_guard<std::mutex> lk(ctx->mu);
@@ -552,7 +565,7 @@ int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uin
     if (!slot_ok(ctx, slot) || !file || !bgr_host) return fail(ctx, P2P_ERR_INVALID, "bad argument");
     p2pjdec::Parsed P;
     size_t dstride = 0;
-    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride);
+    int rc = decode_jpeg_to_staging(ctx, slot, file, len, P, &dstride, false);
     if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
     if (rc) return rc;
     if (row_stride < (size_t)P.info.W * 3 || capacity_rows < (size_t)P.info.H)
@@ -568,7 +581,7 @@ int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uin
         }
         cudaSetDevice(ctx->device);
         if (wait_slot(ctx, s) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "JPEG decoder: CUDA error");
-        rc = jd_resolve(ctx, slot, file, len, P, &dstride);
+        rc = jd_resolve(ctx, slot, file, len, P, &dstride, false);
         if (rc == P2P_OK) break;
         if (rc == P2P_ERR_UNSUPPORTED) return fail(ctx, rc, "JPEG file outside the supported subset (fall back to cv2.imread)");
         if (rc != 2) return rc;

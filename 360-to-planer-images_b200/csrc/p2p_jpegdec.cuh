@@ -1402,8 +1402,13 @@ struct ColorParams {
     const uint8_t *y, *cb, *cr;   // component planes (pitch = blocks per row * 8)
     int pitch_y, pitch_c;
     int W, H, hmax, vmax, cw, ch;
-    uint8_t *bgr;                 // output rows
+    uint8_t *bgr;                 // output rows (PACKED = false)
     size_t stride;
+    // PACKED = true: straight into the slot's panorama layout (what pack_kernel makes of a BGR image): RGBA-packed texels,
+    // pitch_tex per row, column W repeats column 0, row H repeats row H - 1, and the gather array through its surface
+    uint32_t *rgba;
+    int pitch_tex;
+    cudaSurfaceObject_t surf;
 };
 
 // chroma sample of output pixel (x, y): jdsample.c fancy upsampling (or replication for planes <= 2 samples wide)
@@ -1434,13 +1439,16 @@ __device__ __forceinline__ int chroma_at(const uint8_t *__restrict__ c, int pitc
     return (cs * 3 + (3 * r0[cx - 1] + r1[cx - 1]) + 8) >> 4;
 }
 
-// thread per 4 output pixels of a row: 12 bytes = 3 words when the row can take word stores
+// thread per 4 output pixels of a row: 12 bytes = 3 words when the row can take word stores; PACKED: one 16-byte store
+// of packed texels (+ the surface write), the staging image and the pack kernel are skipped (100 MB written and read
+// again per 8K file)
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 jpegdec_color_kernel(const __grid_constant__ ColorParams P) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     if (x0 >= P.W) return;
-    uint32_t px[4];
+    uint32_t px[4] = {0u, 0u, 0u, 0u};
     const int n = (P.W - x0 < 4) ? P.W - x0 : 4;
     for (int i = 0; i < n; ++i) {
         const int x = x0 + i;
@@ -1451,6 +1459,27 @@ jpegdec_color_kernel(const __grid_constant__ ColorParams P) {
         const int b = yy + ((116130 * cb + 32768) >> 16);
         const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
         px[i] = (uint32_t)min(max(b, 0), 255) | ((uint32_t)min(max(g, 0), 255) << 8) | ((uint32_t)min(max(r, 0), 255) << 16);
+    }
+    if (PACKED) {
+        uint32_t *drow = P.rgba + (size_t)y * P.pitch_tex;
+        const bool last_row = (y == P.H - 1);   // the clamp row below the image repeats it
+        if (n == 4) {
+            const uint4 o = make_uint4(px[0], px[1], px[2], px[3]);
+            *reinterpret_cast<uint4 *>(drow + x0) = o;
+            if (last_row) *reinterpret_cast<uint4 *>(drow + P.pitch_tex + x0) = o;
+            if (P.surf != 0) surf2Dwrite(o, P.surf, x0 * 4, y);
+        } else {
+            for (int i = 0; i < n; ++i) {
+                drow[x0 + i] = px[i];
+                if (last_row) drow[P.pitch_tex + x0 + i] = px[i];
+                if (P.surf != 0) surf2Dwrite(px[i], P.surf, (x0 + i) * 4, y);
+            }
+        }
+        if (x0 == 0) {                          // the wrap column behind the row repeats column 0
+            drow[P.W] = px[0];
+            if (last_row) drow[P.pitch_tex + P.W] = px[0];
+        }
+        return;
     }
     uint8_t *o = P.bgr + (size_t)y * P.stride + (size_t)x0 * 3;
     if (n == 4 && (P.stride & 3) == 0) {
