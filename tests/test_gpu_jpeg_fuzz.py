@@ -93,3 +93,59 @@ def test_damaged_files_are_declined_or_decode_like_cv2(pkg, proj, capfd):
     img = synth.smooth(320, 200, 3)
     data = cv2.imencode(".jpg", img)[1].tobytes()
     assert np.array_equal(proj.decode_jpeg(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+
+
+def test_many_threads_mixed_files(pkg):
+    """Eight host threads, one slot each, decoding a mix of files at once through both entry points: smooth and textured
+    files (the optimistic enqueue passes its device-side gate), white noise (needs ~80 synchronisation rounds: the gate stays
+    closed and the host continues from the states reached), restart intervals (host destuffing), grayscale, progressive
+    (host scans), a file with bytes behind its EOI (irregular for the device destuffing pass) and damaged files (declined).
+    Every result is compared with cv2; sleeping host waits (P2P_OPT_HOST_WAIT) are switched on for half of the run."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from jpeg_damage import damaged_files
+
+    L = pkg._lib
+    rng = np.random.default_rng(4)
+    smooth = synth.smooth(1024, 512, 2)
+    textured = np.clip(smooth.astype(np.int16) + rng.integers(-14, 15, smooth.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+    enc = lambda img, *p: cv2.imencode(".jpg", img, list(p))[1].tobytes()   # noqa: E731
+    files = [
+        enc(smooth, cv2.IMWRITE_JPEG_QUALITY, 95),
+        enc(textured, cv2.IMWRITE_JPEG_QUALITY, 90),
+        enc(synth.noise(768, 384, 1), cv2.IMWRITE_JPEG_QUALITY, 95),
+        enc(textured, cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_RST_INTERVAL, 7),
+        enc(smooth[..., 1], cv2.IMWRITE_JPEG_QUALITY, 92),
+        enc(textured[:333, :1000], cv2.IMWRITE_JPEG_QUALITY, 80, cv2.IMWRITE_JPEG_PROGRESSIVE, 1),
+        enc(smooth, cv2.IMWRITE_JPEG_QUALITY, 75) + b"trailing bytes behind the EOI marker",
+    ]
+    files += [d for _, d in damaged_files(5, 6, max_wh=(300, 200))]
+    refs = [cv2.imdecode(np.frombuffer(d, np.uint8), cv2.IMREAD_COLOR) for d in files]
+    proj = pkg.Projector(0, n_slots=8)
+    try:
+        def one(k):
+            i = k % len(files)
+            data, ref = files[i], refs[i]
+            try:
+                if k % 2:
+                    got = proj.decode_jpeg(data)
+                else:
+                    with proj.slots(1) as (s,):
+                        w, h = proj.upload_jpeg(s, data)
+                        got = proj.download_pano(s, w, h)
+            except pkg.P2PError as e:
+                assert e.code == -6, (i, e)
+                return "declined"
+            assert ref is not None and np.array_equal(got, ref), i
+            return "same"
+
+        for wait in (0, 1):
+            proj.set_option(L.OPT_HOST_WAIT, wait)
+            with ThreadPoolExecutor(8) as ex:
+                res = list(ex.map(one, range(26 * 8)))
+            assert res.count("same") >= 7 * 16 - 8, res
+        n0 = proj.get_option(L.OPT_GPU_HUFFMAN_COUNT)
+        assert n0 >= 2 * 26 * 4        # smooth, textured, noise, restart, gray, trailing: the device stage ran
+    finally:
+        proj.close()
+
