@@ -539,12 +539,14 @@ def _save_views(cv2, views, base_name, output_dir, yaw_angles, pitch_angles, out
 
 
 def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, output_width, output_height,
-                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=None):
+                        num_workers=4, output_format="png", fov_deg=90, devices=None, inflight=None, host_wait=None):
     """Directory front end (ref ``main`` :320-341 processes the files one after the other).
 
     Same files and names out as calling ``process_single_image`` per file, but ``inflight`` images (default: one per
     worker, at most 15) are in flight at once, each on its own slot (stream) driven by its own host thread, while the writer pool saves earlier results.
     ``devices`` shards the files round-robin over several GPUs (one pipeline per device, no data exchange).
+    ``host_wait``: 1 = the in-flight threads sleep while they wait for the device, 0 = they spin (lowest latency, one busy
+    core each); default: sleep as soon as in-flight threads plus writers outnumber the host's cores.
     """
     import cv2
 
@@ -570,6 +572,10 @@ def process_image_batch(image_files, output_dir, yaw_angles, pitch_angles, outpu
             per_slot = len(yaw_angles) * len(pitch_angles) * (W * H * 4 + 4096)
             budget = float(os.environ.get("P2P_PINNED_BUDGET_GB", "8")) * 2 ** 30
             n_in = max(1, min(n_in, int(budget // max(1, per_slot))))
+        wait = host_wait if host_wait is not None else os.environ.get("P2P_HOST_WAIT")   # (the environment: for experiments)
+        if wait is None:
+            wait = 1 if (n_in + num_workers) * len(devices) > (os.cpu_count() or 1) else 0
+        proj.set_option(_engine._lib.OPT_HOST_WAIT, int(bool(int(wait))))
 
         def one(f, writers):
             # the slot stays leased until this image's files are on disk (written straight from its page-locked buffer)
