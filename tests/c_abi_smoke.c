@@ -1,6 +1,8 @@
 /* Plain-C consumer of include/p2p.h: proves the boundary is a C ABI (no C++ / Python / torch types).
  *   gcc -std=c99 -Wall -Iinclude tests/c_abi_smoke.c -o c_abi_smoke -L<dir> -lp2p_b200 -Wl,-rpath,<dir>
- *   ./c_abi_smoke Wp Hp W H fov out.bin      (writes n_yaw * n_pitch * H * W * 3 bytes)
+ *   ./c_abi_smoke Wp Hp W H fov out.bin      (writes (n_yaw + 1) * n_pitch * H * W * 3 bytes: three integer-roll yaws
+ *                                             through p2p_project_views, then yaw 33.3 - not an integer column roll -
+ *                                             through p2p_project_views_table)
  * The panorama is a deterministic LCG pattern the Python test regenerates. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -55,6 +57,17 @@ int main(int argc, char **argv) {
     f = fopen(argv[6], "wb");
     if (!f) return 5;
     fwrite(out, 1, (size_t)n_yaw * n_pitch * W * H * 3, f);
+    {   /* a fractional yaw: both remap passes of the reference in one call, from the same slot */
+        int32_t frac_shift;
+        const int32_t *ixs[1], *fxs[1];
+        CHECK(p2p_yaw_table(Wp, 33.3, ix, fx, &frac_shift));
+        if (frac_shift >= 0) return 6;
+        ixs[0] = ix;
+        fxs[0] = fx;
+        CHECK(p2p_project_views_table(ctx, 0, 1, ixs, fxs, n_pitch, pc, W, H, out, 0));
+        CHECK(p2p_sync(ctx, 0));
+        fwrite(out, 1, (size_t)n_pitch * W * H * 3, f);
+    }
     fclose(f);
     p2p_destroy(ctx);
     free(pano); free(out); free(ix); free(fx);

@@ -759,8 +759,8 @@ def test_plain_c_consumer_matches_python_host(pkg, tmp_path):
         s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
         vals[i] = s >> 24
     pano = vals.reshape(Hp, Wp, 3)
-    got = np.fromfile(out_file, np.uint8).reshape(3, 2, H, W, 3)
-    want = pkg.Projector(0, n_slots=1).project_image(pano, [0, 90, 270], [60, 120], W, H, fov)
+    got = np.fromfile(out_file, np.uint8).reshape(4, 2, H, W, 3)
+    want = pkg.Projector(0, n_slots=1).project_image(pano, [0, 90, 270, 33.3], [60, 120], W, H, fov)
     assert np.array_equal(got, want)
 
 
