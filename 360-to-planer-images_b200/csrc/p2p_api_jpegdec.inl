@@ -4,9 +4,7 @@
 namespace {
 
 // ---- JPEG decoder (p2p_jpegdec.cuh) ------------------------------------------------------------
-// Huffman stage on the device (p2pjdec::huff_*): fills s.jd_coef_d.  Returns P2P_OK, an error, or 1 = "not handled"
-// (no convergence, inconsistent block counts, unexpected markers): the caller then runs the host decoder.
-// The destuffing pass runs on the calling thread; the lock is held only while enqueueing.
+// flags the decoder's kernels and the host share: page-locked, mapped into the device's address space
 int ensure_jd_flags(p2p_ctx *ctx, Slot &s) {
     if (s.jd_flags_h) return P2P_OK;
     CK(cudaHostAlloc(reinterpret_cast<void **>(&s.jd_flags_h), sizeof(*s.jd_flags_h), cudaHostAllocMapped | cudaHostAllocPortable));
