@@ -882,26 +882,37 @@ __device__ __forceinline__ void or_bits(uint32_t *__restrict__ z, unsigned long 
     if (sh + length > 64) atomicOr(z + i + 2, (uint32_t)(value >> (64 - sh)));
 }
 
-// A CTA walks its block in tiles of 1024 positions, 4 consecutive positions per thread (one 8-byte load of token lengths, one
-// 4-byte load of filtered bytes).  The bits of a tile are assembled in SHARED memory (a prefix sum of the code lengths gives
-// every token its place; <= 15 bits per position: 480 words) and leave as whole 32-bit words; only the first and the last
-// word of a tile, which it shares with its neighbours, go through an atomicOr in global memory.  (Round 1 issued up to three
-// global atomics per token, ~10^8 per 12 views, and three CTA barriers per 256 positions: 452 us.)
-constexpr int kEmitTile = 1024;
+// A CTA walks its block in tiles of 2048 positions, 8 consecutive positions per thread (one 16-byte load of token lengths,
+// one 8-byte load of filtered bytes).  A token is at most two pieces of <= 20 bits - a literal's code, or a match's length
+// code with its extra bits followed by the distance code - so everything stays 32-bit arithmetic and a piece touches at
+// most two words.  The bits of a tile are assembled in SHARED memory (a prefix sum of the code lengths gives every token
+// its place; <= 15 bits per position: 960 words) and leave as whole 32-bit words; only the first and the last word of a
+// tile, which it shares with its neighbours, go through an atomicOr in global memory.  (Round 1 issued up to three global
+// atomics per token, ~10^8 per 12 views, and three CTA barriers per 256 positions: 452 us.)
+constexpr int kEmitPer = 8;
+constexpr int kEmitTile = 256 * kEmitPer;
 constexpr int kEmitWords = kEmitTile * kMaxBits / 32 + 4;
 
 __global__ void __launch_bounds__(256)
 png_emit_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen, const uint32_t *__restrict__ blockpos,
                 const uint32_t *__restrict__ ntok, const BlockInfo *__restrict__ info, const uint32_t *__restrict__ blkoff,
                 const unsigned long long *__restrict__ zbits, uint32_t *__restrict__ Z, const Geom G) {
-    __shared__ uint32_t s_code[kLCodes];
+    // the first piece of every possible token, ready to place: bits | length << 24; [0, 256) literal bytes, [256, 512)
+    // match lengths 3 .. 258 (length code + extra bits) - one shared-memory look-up per position whatever it holds
+    __shared__ uint32_t s_piece[512];
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_bits[kEmitWords];
     const int img = blockIdx.y;
     const uint32_t b = blockIdx.x, T = ntok[img];
     if (b >= T / (uint32_t)kSymPerBlock + 1u || zbits[img] == 0ull) return;
     const BlockInfo &bi = info[(size_t)img * G.max_blk + b];
-    for (int i = threadIdx.x; i < kLCodes; i += blockDim.x) s_code[i] = bi.lcode[i];
+    {
+        const int lc = threadIdx.x, code = length_code(lc);   // blockDim.x == 256
+        const uint32_t cl = bi.lcode[lc], cm = bi.lcode[257 + code];
+        s_piece[lc] = (cl & 0xFFFFu) | ((cl >> 16) << 24);
+        const uint32_t n = cm >> 16;
+        s_piece[256 + lc] = ((cm & 0xFFFFu) | ((uint32_t)(lc - (int)kBaseLen[code]) << n)) | ((n + kExtraL[code]) << 24);
+    }
     for (int i = threadIdx.x; i < kEmitWords; i += blockDim.x) s_bits[i] = 0;
     uint32_t *z = Z + (size_t)img * (G.z_cap / 4);
     const unsigned long long base = blkoff[(size_t)img * G.max_blk + b];
@@ -921,51 +932,36 @@ png_emit_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen
         return;
     }
     const uint16_t *tl = tlen + (size_t)img * G.Npad;
-    const uint32_t d0 = bi.dcode0;
+    const uint32_t dcode = bi.dcode0 & 0xFFFFu, dlen = bi.dcode0 >> 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long at = base + bi.hdr_bits;   // stream position of the tile's first bit
     __syncthreads();
-    for (uint32_t t0 = p0 & ~3u; t0 < p1; t0 += kEmitTile) {
-        const uint32_t i0 = t0 + threadIdx.x * 4u;
-        unsigned long long val[4];
-        int nb[4];
-        uint32_t mine = 0;
+    for (uint32_t t0 = p0 & ~7u; t0 < p1; t0 += kEmitTile) {
+        const uint32_t i0 = t0 + threadIdx.x * kEmitPer;
+        uint32_t v0[kEmitPer];    // first piece: bits | length << 24 (length 0: no token here)
+        uint32_t mine = 0, matches = 0;
         {
-            uint2 tv = make_uint2(0u, 0u);
-            uint32_t fv = 0;
+            uint4 tv = make_uint4(0u, 0u, 0u, 0u);
+            uint2 fv = make_uint2(0u, 0u);
             if (i0 < p1) {   // (Npad is a multiple of 4096: the loads stay inside the image's arrays)
-                tv = *reinterpret_cast<const uint2 *>(tl + i0);
-                fv = *reinterpret_cast<const uint32_t *>(f + i0);
+                tv = *reinterpret_cast<const uint4 *>(tl + i0);
+                fv = *reinterpret_cast<const uint2 *>(f + i0);
             }
+            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kEmitPer; ++k) {
                 const uint32_t i = i0 + k;
-                const uint32_t t = ((k < 2 ? tv.x : tv.y) >> (16 * (k & 1))) & 0xFFFFu;
-                val[k] = 0;
-                nb[k] = 0;
-                if (i >= p0 && i < p1) {
-                    if (t == 1) {
-                        const uint32_t c = s_code[(fv >> (8 * k)) & 0xFFu];
-                        val[k] = c & 0xFFFFu;
-                        nb[k] = (int)(c >> 16);
-                    } else if (t >= 3) {
-                        const int lc = (int)t - 3, code = length_code(lc);
-                        const uint32_t c = s_code[257 + code];
-                        unsigned long long v = c & 0xFFFFu;
-                        int n = (int)(c >> 16);
-                        const int ex = kExtraL[code];
-                        if (ex) {
-                            v |= (unsigned long long)(lc - kBaseLen[code]) << n;
-                            n += ex;
-                        }
-                        v |= (unsigned long long)(d0 & 0xFFFFu) << n;
-                        n += (int)(d0 >> 16);
-                        val[k] = v;
-                        nb[k] = n;
-                    }
+                const uint32_t t = (tw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                uint32_t piece = 0;
+                if (t != 0 && i >= p0 && i < p1) {
+                    const uint32_t byte = ((k < 4 ? fv.x : fv.y) >> (8 * (k & 3))) & 0xFFu;
+                    piece = s_piece[t == 1 ? byte : 253u + t];   // 256 + (t - 3)
+                    if (t != 1) matches |= 1u << k;
                 }
-                mine += (uint32_t)nb[k];
+                v0[k] = piece;
+                mine += piece >> 24;
             }
+            mine += (uint32_t)__popc(matches) * dlen;
         }
         uint32_t inc = mine;
 #pragma unroll
@@ -981,18 +977,33 @@ png_emit_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen
             if (k < warp) wsum += s_warp[k];
             tile += s_warp[k];
         }
-        // place the tokens: bit 0 of s_bits = bit (at & ~31) of the stream
+        // place the pieces: bit 0 of s_bits = bit (at & ~31) of the stream
         const uint32_t sh0 = (uint32_t)(at & 31ull);
-        uint32_t pos = sh0 + wsum + (inc - mine);
+        // a thread's pieces are one contiguous bit run: gathered in a 64-bit register and handed to shared memory a word at a
+        // time (its first and last word are shared with the neighbouring threads: atomicOr throughout)
+        {
+            const uint32_t pos = sh0 + wsum + (inc - mine);
+            uint32_t w = pos >> 5, fill = pos & 31u;
+            unsigned long long acc = 0ull;
+            auto put = [&](uint32_t v, uint32_t n) {   // n <= 20 bits; fill < 32 on entry
+                acc |= (unsigned long long)v << fill;
+                fill += n;
+                if (fill >= 32u) {
+                    atomicOr(&s_bits[w], (uint32_t)acc);
+                    acc >>= 32;
+                    fill -= 32u;
+                    ++w;
+                }
+            };
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (nb[k]) {
-                const uint32_t w = pos >> 5, sh = pos & 31u;
-                atomicOr(&s_bits[w], (uint32_t)(val[k] << sh));
-                if (sh + nb[k] > 32) atomicOr(&s_bits[w + 1], (uint32_t)(val[k] >> (32 - sh)));
-                if (sh + nb[k] > 64) atomicOr(&s_bits[w + 2], (uint32_t)(val[k] >> (64 - sh)));
-                pos += (uint32_t)nb[k];
+            for (int k = 0; k < kEmitPer; ++k) {
+                const uint32_t n = v0[k] >> 24;
+                if (n) {
+                    put(v0[k] & 0x00FFFFFFu, n);
+                    if ((matches >> k) & 1u) put(dcode, dlen);
+                }
             }
+            if (acc) atomicOr(&s_bits[w], (uint32_t)acc);
         }
         __syncthreads();
         // flush: words 0 and last are shared with the neighbouring tiles / blocks
@@ -1011,7 +1022,7 @@ png_emit_kernel(const uint8_t *__restrict__ F, const uint16_t *__restrict__ tlen
         __syncthreads();
     }
     if (threadIdx.x == 0) {   // END_BLOCK
-        const uint32_t c = s_code[256];
+        const uint32_t c = bi.lcode[256];
         or_bits(z, at, c & 0xFFFFu, (int)(c >> 16));
     }
 }
