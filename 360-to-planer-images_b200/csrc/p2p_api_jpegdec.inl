@@ -419,7 +419,8 @@ int jd_host_scan(p2p_ctx *ctx, Slot &s, const uint8_t *file, size_t len, const p
         cudaSetDevice(ctx->device);
         wait_slot(ctx, s);   // the staging buffer was used for the stream upload
     }
-    return p2pjdec::decode_scan(file, len, P, s.jd_coef_h) ? P2P_ERR_UNSUPPORTED : P2P_OK;  // damaged: leave it to libjpeg
+    // (the block-norm check of a progressive file is left to the IDCT kernel, which makes it anyway)
+    return p2pjdec::decode_scan(file, len, P, s.jd_coef_h, false) ? P2P_ERR_UNSUPPORTED : P2P_OK;  // damaged: leave it to libjpeg
 }
 
 // Decode `file` into the slot's BGR staging image.  The Huffman stage runs on the device (queued optimistically in the

@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <thread>
 #include <vector>
 
 namespace p2pjdec {
@@ -374,10 +375,157 @@ inline int parse_headers(const uint8_t *d, size_t len, Parsed &P) {
 // refinement pass, restart markers out of sequence, bytes between a scan and the next marker.  A file whose scans do not
 // bring every coefficient to full precision is declined too: libjpeg then smooths the blocks from their neighbours'
 // DC values (jdcoefct.c decompress_smooth_data), which is not restated.  0 = ok, 1 = declined.
-inline int decode_progressive(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef) {
+struct ProgScan {
+    size_t data = 0, end = 0;    // entropy-coded bytes [data, end): `end` is the marker behind them
+    int ns = 0, comp[3] = {0, 0, 0};
+    int Ss = 0, Se = 0, Ah = 0, Al = 0, dri = 0;
+    HuffTable table[3];          // per scan component: its DC table (first DC scan) or its AC table (AC scans)
+};
+
+// the entropy-coded data of one scan (jdphuff.c decode_mcu_DC_first / DC_refine / AC_first / AC_refine)
+inline int decode_progressive_scan(const uint8_t *d, const Info &I, const ProgScan &S, int16_t *coef) {
+    const int ns = S.ns, Ss = S.Ss, Se = S.Se, Ah = S.Ah, Al = S.Al, dri = S.dri;
+    const bool dc_scan = (Ss == 0);
+    BitReader br;
+    br.p = d + S.data;
+    br.end = d + S.end;          // (the reader also stops at the marker itself)
+    int pred[3] = {0, 0, 0};
+    unsigned eobrun = 0;
+    int togo = dri, next_rst = 0;
+    const bool interleaved = ns > 1;
+    const int c0 = S.comp[0];
+    // a single-component scan walks the component's own blocks: ceil(width / 8) x ceil(height / 8)
+    const int cw = (c0 == 0 || I.ncomp == 1) ? I.W : I.cw, chh = (c0 == 0 || I.ncomp == 1) ? I.H : I.ch;
+    const int nx = interleaved ? I.mcux : (cw + 7) / 8, ny = interleaved ? I.mcuy : (chh + 7) / 8;
+    const int p1 = 1 << Al, m1 = -(1 << Al);
+    auto get_bit = [&]() -> int {
+        if (br.n < 1) br.fill();
+        const int b = (int)br.peek(1);
+        br.skip(1);
+        return b;
+    };
+    for (int my = 0; my < ny; ++my) {
+        for (int mx = 0; mx < nx; ++mx) {
+            if (dri) {
+                if (togo == 0) {
+                    if (br.overran()) return 1;
+                    br.acc = 0;
+                    br.n = 0;
+                    br.marker = false;
+                    br.zero_bits = 0;
+                    if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] != 0xD0 + next_rst) return 1;
+                    next_rst = (next_rst + 1) & 7;
+                    br.p += 2;
+                    pred[0] = pred[1] = pred[2] = 0;
+                    eobrun = 0;
+                    togo = dri;
+                }
+                --togo;
+            }
+            if (dc_scan) {
+                for (int k = 0; k < ns; ++k) {
+                    const int c = S.comp[k];
+                    const int nb = interleaved ? (c ? 1 : I.hmax * I.vmax) : 1;
+                    for (int b = 0; b < nb; ++b) {
+                        const int by = interleaved ? (c ? my : my * I.vmax + b / I.hmax) : my;
+                        const int bx = interleaved ? (c ? mx : mx * I.hmax + b % I.hmax) : mx;
+                        int16_t *blk = coef + I.coef_off[c] + ((size_t)by * I.bw[c] + bx) * 64;
+                        if (Ah == 0) {
+                            if (br.n < 32) br.fill();
+                            const int sz = decode_sym(br, S.table[k]);
+                            if (sz < 0 || sz > 11) return 1;
+                            if (sz) pred[c] += receive_extend(br, sz);
+                            blk[0] = (int16_t)(pred[c] * p1);
+                        } else if (get_bit()) {
+                            blk[0] = (int16_t)(blk[0] | p1);
+                        }
+                    }
+                }
+                continue;
+            }
+            int16_t *blk = coef + I.coef_off[c0] + ((size_t)my * I.bw[c0] + mx) * 64;
+            const HuffTable &act = S.table[0];
+            if (Ah == 0) {   // decode_mcu_AC_first
+                if (eobrun > 0) {
+                    --eobrun;
+                    continue;
+                }
+                for (int k = Ss; k <= Se; ++k) {
+                    if (br.n < 32) br.fill();
+                    const int rs = decode_sym(br, act);
+                    if (rs < 0) return 1;
+                    const int r = rs >> 4, sz = rs & 15;
+                    if (sz) {
+                        k += r;
+                        if (k > Se) return 1;
+                        blk[kNat[k]] = (int16_t)(receive_extend(br, sz) * p1);
+                    } else if (r == 15) {
+                        k += 15;
+                    } else {
+                        eobrun = 1u << r;
+                        if (r) {
+                            eobrun += br.peek(r);
+                            br.skip(r);
+                        }
+                        --eobrun;
+                        break;
+                    }
+                }
+                continue;
+            }
+            // decode_mcu_AC_refine
+            int k = Ss;
+            if (eobrun == 0) {
+                for (; k <= Se; ++k) {
+                    if (br.n < 32) br.fill();
+                    const int rs = decode_sym(br, act);
+                    if (rs < 0) return 1;
+                    int r = rs >> 4, sz = rs & 15, val = 0;
+                    if (sz) {
+                        if (sz != 1) return 1;
+                        val = get_bit() ? p1 : m1;
+                    } else if (r != 15) {
+                        eobrun = 1u << r;
+                        if (r) {
+                            eobrun += br.peek(r);
+                            br.skip(r);
+                        }
+                        break;
+                    }
+                    // over the coefficients that are already non-zero (a correction bit each) and r zero ones
+                    do {
+                        int16_t *cf = blk + kNat[k];
+                        if (*cf != 0) {
+                            if (get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                        } else if (--r < 0) {
+                            break;
+                        }
+                        ++k;
+                    } while (k <= Se);
+                    if (val) {
+                        if (k > Se) return 1;
+                        blk[kNat[k]] = (int16_t)val;
+                    }
+                }
+            }
+            if (eobrun > 0) {   // the rest of the band: correction bits only
+                for (; k <= Se; ++k) {
+                    int16_t *cf = blk + kNat[k];
+                    if (*cf != 0 && get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                }
+                --eobrun;
+            }
+        }
+    }
+    if (br.overran()) return 1;
+    return (size_t)(br.p - d) == S.end ? 0 : 1;   // the reader must stop in front of the marker that ends the scan
+}
+
+inline int decode_progressive(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef, bool check_norm) {
     const Info &I = P.info;
-    memset(coef, 0, I.n_coef * sizeof(int16_t));
+    // ---- pass 1: the scan headers in file order - tables in effect, progression checks, where each scan's data ends
     std::vector<HuffTable> dc(P.dc, P.dc + 4), ac(P.ac, P.ac + 4);
+    std::vector<ProgScan> scans;
     int dri = P.dri;
     int cbits[3][64];   // jdphuff.c coef_bits: -1 = not seen yet, else the Al of the last scan that covered the coefficient
     for (int c = 0; c < 3; ++c)
@@ -411,175 +559,81 @@ inline int decode_progressive(const uint8_t *d, size_t len, const Parsed &P, int
         }
         if ((m >= 0xE0 && m <= 0xEF) || m == 0xFE) continue;
         if (m != 0xDA) return 1;
-        // ---- scan header (jdmarker.c get_sos, jdphuff.c start_pass_phuff_decoder)
+        // scan header (jdmarker.c get_sos, jdphuff.c start_pass_phuff_decoder)
+        if (scans.size() >= 64) return 1;
+        scans.emplace_back();
+        ProgScan &S = scans.back();
         const int ns = sl ? seg[0] : 0;
         if (ns < 1 || ns > I.ncomp || sl != 1 + 2 * (size_t)ns + 3) return 1;
-        int comp[3], td[3], ta[3];
+        S.ns = ns;
+        S.Ss = seg[1 + 2 * ns];
+        S.Se = seg[2 + 2 * ns];
+        S.Ah = seg[3 + 2 * ns] >> 4;
+        S.Al = seg[3 + 2 * ns] & 15;
+        S.dri = dri;
+        const bool dc_scan = (S.Ss == 0);
+        if (dc_scan ? (S.Se != 0) : (ns != 1 || S.Se < S.Ss || S.Se > 63)) return 1;
+        if (S.Al > 13 || (S.Ah != 0 && S.Al != S.Ah - 1)) return 1;
         for (int k = 0; k < ns; ++k) {
             int c = -1;
             for (int q = 0; q < I.ncomp; ++q)
                 if (P.cid[q] == seg[1 + 2 * k]) c = q;
-            if (c < 0 || (k && c <= comp[k - 1])) return 1;
-            comp[k] = c;
-            td[k] = seg[2 + 2 * k] >> 4;
-            ta[k] = seg[2 + 2 * k] & 15;
-            if (td[k] > 3 || ta[k] > 3) return 1;
-        }
-        const int Ss = seg[1 + 2 * ns], Se = seg[2 + 2 * ns], Ah = seg[3 + 2 * ns] >> 4, Al = seg[3 + 2 * ns] & 15;
-        const bool dc_scan = (Ss == 0);
-        if (dc_scan ? (Se != 0) : (ns != 1 || Se < Ss || Se > 63)) return 1;
-        if (Al > 13 || (Ah != 0 && Al != Ah - 1)) return 1;
-        for (int k = 0; k < ns; ++k) {
-            int *cb = cbits[comp[k]];
-            if (!dc_scan && cb[0] < 0) return 1;                       // AC before DC
-            for (int z = Ss; z <= Se; ++z) {
-                if (Ah != (cb[z] < 0 ? 0 : cb[z])) return 1;           // not the standard progression
-                cb[z] = Al;
+            if (c < 0 || (k && c <= S.comp[k - 1])) return 1;
+            S.comp[k] = c;
+            const int td = seg[2 + 2 * k] >> 4, ta = seg[2 + 2 * k] & 15;
+            if (td > 3 || ta > 3) return 1;
+            int *cb = cbits[c];
+            if (!dc_scan && cb[0] < 0) return 1;                           // AC before DC
+            for (int z = S.Ss; z <= S.Se; ++z) {
+                if (S.Ah != (cb[z] < 0 ? 0 : cb[z])) return 1;             // not the standard progression
+                cb[z] = S.Al;
             }
-            if (Ah == 0 || !dc_scan) {                                 // (a DC refinement reads raw bits only)
-                const HuffTable &t = dc_scan ? dc[td[k]] : ac[ta[k]];
+            if (S.Ah == 0 || !dc_scan) {                                   // (a DC refinement reads raw bits only)
+                const HuffTable &t = dc_scan ? dc[td] : ac[ta];
                 if (!t.present) return 1;
+                S.table[k] = t;
             }
         }
-        // ---- the scan's entropy-coded data
-        BitReader br;
-        br.p = d + i;
-        br.end = d + len;
-        int pred[3] = {0, 0, 0};
-        unsigned eobrun = 0;
-        int togo = dri, next_rst = 0;
-        const bool interleaved = ns > 1;
-        const int c0 = comp[0];
-        // a single-component scan walks the component's own blocks: ceil(width / 8) x ceil(height / 8)
-        const int cw = (c0 == 0 || I.ncomp == 1) ? I.W : I.cw, chh = (c0 == 0 || I.ncomp == 1) ? I.H : I.ch;
-        const int nx = interleaved ? I.mcux : (cw + 7) / 8, ny = interleaved ? I.mcuy : (chh + 7) / 8;
-        const int p1 = 1 << Al, m1 = -(1 << Al);
-        auto get_bit = [&]() -> int {
-            if (br.n < 1) br.fill();
-            const int b = (int)br.peek(1);
-            br.skip(1);
-            return b;
-        };
-        for (int my = 0; my < ny; ++my) {
-            for (int mx = 0; mx < nx; ++mx) {
-                if (dri) {
-                    if (togo == 0) {
-                        if (br.overran()) return 1;
-                        br.acc = 0;
-                        br.n = 0;
-                        br.marker = false;
-                        br.zero_bits = 0;
-                        if (br.p + 2 > br.end || br.p[0] != 0xFF || br.p[1] != 0xD0 + next_rst) return 1;
-                        next_rst = (next_rst + 1) & 7;
-                        br.p += 2;
-                        pred[0] = pred[1] = pred[2] = 0;
-                        eobrun = 0;
-                        togo = dri;
-                    }
-                    --togo;
-                }
-                if (dc_scan) {
-                    for (int k = 0; k < ns; ++k) {
-                        const int c = comp[k];
-                        const int nb = interleaved ? (c ? 1 : I.hmax * I.vmax) : 1;
-                        for (int b = 0; b < nb; ++b) {
-                            const int by = interleaved ? (c ? my : my * I.vmax + b / I.hmax) : my;
-                            const int bx = interleaved ? (c ? mx : mx * I.hmax + b % I.hmax) : mx;
-                            int16_t *blk = coef + I.coef_off[c] + ((size_t)by * I.bw[c] + bx) * 64;
-                            if (Ah == 0) {
-                                if (br.n < 32) br.fill();
-                                const int sz = decode_sym(br, dc[td[k]]);
-                                if (sz < 0 || sz > 11) return 1;
-                                if (sz) pred[c] += receive_extend(br, sz);
-                                blk[0] = (int16_t)(pred[c] * p1);
-                            } else if (get_bit()) {
-                                blk[0] = (int16_t)(blk[0] | p1);
-                            }
-                        }
-                    }
-                    continue;
-                }
-                int16_t *blk = coef + I.coef_off[c0] + ((size_t)my * I.bw[c0] + mx) * 64;
-                const HuffTable &act = ac[ta[0]];
-                if (Ah == 0) {   // decode_mcu_AC_first
-                    if (eobrun > 0) {
-                        --eobrun;
-                        continue;
-                    }
-                    for (int k = Ss; k <= Se; ++k) {
-                        if (br.n < 32) br.fill();
-                        const int rs = decode_sym(br, act);
-                        if (rs < 0) return 1;
-                        const int r = rs >> 4, sz = rs & 15;
-                        if (sz) {
-                            k += r;
-                            if (k > Se) return 1;
-                            blk[kNat[k]] = (int16_t)(receive_extend(br, sz) * p1);
-                        } else if (r == 15) {
-                            k += 15;
-                        } else {
-                            eobrun = 1u << r;
-                            if (r) {
-                                eobrun += br.peek(r);
-                                br.skip(r);
-                            }
-                            --eobrun;
-                            break;
-                        }
-                    }
-                    continue;
-                }
-                // decode_mcu_AC_refine
-                int k = Ss;
-                if (eobrun == 0) {
-                    for (; k <= Se; ++k) {
-                        if (br.n < 32) br.fill();
-                        const int rs = decode_sym(br, act);
-                        if (rs < 0) return 1;
-                        int r = rs >> 4, sz = rs & 15, val = 0;
-                        if (sz) {
-                            if (sz != 1) return 1;
-                            val = get_bit() ? p1 : m1;
-                        } else if (r != 15) {
-                            eobrun = 1u << r;
-                            if (r) {
-                                eobrun += br.peek(r);
-                                br.skip(r);
-                            }
-                            break;
-                        }
-                        // over the coefficients that are already non-zero (a correction bit each) and r zero ones
-                        do {
-                            int16_t *cf = blk + kNat[k];
-                            if (*cf != 0) {
-                                if (get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
-                            } else if (--r < 0) {
-                                break;
-                            }
-                            ++k;
-                        } while (k <= Se);
-                        if (val) {
-                            if (k > Se) return 1;
-                            blk[kNat[k]] = (int16_t)val;
-                        }
-                    }
-                }
-                if (eobrun > 0) {   // the rest of the band: correction bits only
-                    for (; k <= Se; ++k) {
-                        int16_t *cf = blk + kNat[k];
-                        if (*cf != 0 && get_bit() && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
-                    }
-                    --eobrun;
-                }
-            }
+        // the scan's data runs to the next marker that is neither a stuffed zero nor a restart marker
+        S.data = i;
+        size_t e = i;
+        for (;;) {
+            const uint8_t *ff = static_cast<const uint8_t *>(memchr(d + e, 0xFF, len - e));
+            if (!ff || ff + 1 >= d + len) return 1;                        // no marker behind the scan: truncated
+            e = (size_t)(ff - d);
+            const uint8_t nx = ff[1];
+            if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7)) e += 2;
+            else if (nx == 0xFF) e += 1;
+            else break;
         }
-        if (br.overran()) return 1;
-        i = (size_t)(br.p - d);   // the reader stops in front of the marker that ends the scan
+        S.end = e;
+        i = e;
     }
     if (!eoi) return 1;
     for (int c = 0; c < I.ncomp; ++c)
         for (int k = 0; k < 64; ++k)
             if (cbits[c][k] != 0) return 1;   // not at full precision: libjpeg would smooth (see above)
+    // ---- pass 2: DC scans never touch what AC scans touch, and the AC scans of one component only their own planes: up
+    // to four independent chains (DC, AC of Y / Cb / Cr), each decoded in file order on its own thread
+    std::vector<int> chain[4];
+    for (size_t k = 0; k < scans.size(); ++k) chain[scans[k].Ss == 0 ? 0 : 1 + scans[k].comp[0]].push_back((int)k);
+    int failed[4] = {0, 0, 0, 0};
+    auto run = [&](int c) {
+        // every chain clears what it is about to write: the DC chain nothing (the AC chains clear whole planes and finish
+        // clearing before any thread decodes: see the barrier below)
+        for (int k : chain[c])
+            if (!failed[c] && decode_progressive_scan(d, I, scans[(size_t)k], coef)) failed[c] = 1;
+    };
+    memset(coef, 0, I.n_coef * sizeof(int16_t));
+    {
+        std::vector<std::thread> th;
+        for (int c = 1; c < 4; ++c)
+            if (!chain[c].empty()) th.emplace_back(run, c);
+        run(0);
+        for (auto &t : th) t.join();
+    }
+    if (failed[0] | failed[1] | failed[2] | failed[3]) return 1;
+    if (!check_norm) return 0;   // (the device IDCT kernel makes the same check on the upload path)
     // damaged data shows as blocks no 8-bit encoder produces (see kMaxBlockNorm): libjpeg's SIMD IDCT wraps on them
     for (int c = 0; c < I.ncomp; ++c) {
         float qf[64];
@@ -598,8 +652,8 @@ inline int decode_progressive(const uint8_t *d, size_t len, const Parsed &P, int
 }
 
 // Huffman-decode the scan into `coef` (int16, natural order, component planes [by][bx][64]).  0 = ok, 1 = damaged.
-inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef) {
-    if (P.progressive) return decode_progressive(d, len, P, coef);
+inline int decode_scan(const uint8_t *d, size_t len, const Parsed &P, int16_t *coef, bool check_norm = true) {
+    if (P.progressive) return decode_progressive(d, len, P, coef, check_norm);
     const Info &I = P.info;
     BitReader br;
     br.p = d + P.ecs;
