@@ -258,7 +258,7 @@ int p2p_jpeg_coefficients(const uint8_t *file, size_t len, int16_t *coef, size_t
 /* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, bit-identical pixels): Huffman
  * decoding (self-synchronising subsequences; P2P_OPT_GPU_HUFFMAN), inverse DCT, chroma upsampling and colour
  * conversion all run on the device (the FF 00 byte stuffing is removed there too when the file has no restart markers); the
- * pixels never exist in host memory.  The scans of a progressive file are decoded on the calling thread (jdphuff.c), everything
+ * pixels never exist in host memory.  The scans of a progressive file are decoded on host threads (jdphuff.c; up to four: DC, AC per component), everything
  * behind them on the device.  If the device Huffman stage does not converge the library's own host decoder (calling thread, outside the
  * context lock) takes over.  Returns after the decode has finished on the device: a damaged file (truncated scan,
  * restart markers out of sequence, codes or coefficient blocks no 8-bit encoder writes) gives P2P_ERR_UNSUPPORTED

@@ -29,7 +29,7 @@ def main():
     smooth = synth.smooth(Wp, Hp, 0)
     textured = np.clip(smooth.astype(np.int16) + rng.integers(-12, 13, smooth.shape, dtype=np.int16), 0, 255).astype(np.uint8)
     cases = {"smooth": (smooth, 95), "textured (smooth + noise of amplitude 12)": (textured, 92), "white noise": (synth.noise(Wp, Hp, 0), 95)}
-    cases["smooth, progressive (scans decoded on the calling thread, IDCT / colour on the device)"] = (smooth, -95)
+    cases["smooth, progressive (scans decoded on host threads, IDCT / colour on the device)"] = (smooth, -95)
     for name, (img, q) in cases.items():
         data = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, abs(q), cv2.IMWRITE_JPEG_PROGRESSIVE, int(q < 0)])[1].tobytes()
         arr = np.frombuffer(data, np.uint8)
