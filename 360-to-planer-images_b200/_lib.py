@@ -65,6 +65,10 @@ SIGNATURES = {
     "p2p_jpeg_coefficients": (_i, [_u8p, _sz, _vp, _sz, _i32p]),
     "p2p_upload_pano_jpeg": (_i, [_vp, _i, _u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),
     "p2p_decode_jpeg": (_i, [_vp, _i, _u8p, _sz, _u8p, _sz, _sz]),
+    "p2p_png_probe": (_i, [_u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "p2p_png_decode_host": (_i, [_u8p, _sz, _u8p, _sz, _sz, C.POINTER(C.c_uint64)]),
+    "p2p_upload_pano_png": (_i, [_vp, _i, _u8p, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "p2p_decode_png": (_i, [_vp, _i, _u8p, _sz, _u8p, _sz, _sz]),
     "p2p_sync": (_i, [_vp, _i]),
     "p2p_set_stream": (_i, [_vp, _i, _vp]),
     "p2p_get_stream": (_i, [_vp, _i, C.POINTER(_vp)]),

@@ -10,6 +10,7 @@
 #include "p2p_api_jpeg.inl"
 #include "p2p_api_jpegdec.inl"
 #include "p2p_api_png.inl"
+#include "p2p_api_pngdec.inl"
 
 // ============================================================================================
 extern "C" {
@@ -114,6 +115,12 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.jd_tot_d);
         cudaFree(s.jd_sub);
         if (s.jd_flags_h) cudaFreeHost(s.jd_flags_h);
+        if (s.pd_zs_h) cudaFreeHost(s.pd_zs_h);
+        if (s.pd_tab_h) cudaFreeHost(s.pd_tab_h);
+        cudaFree(s.pd_zs);
+        cudaFree(s.pd_tab);
+        cudaFree(s.pd_raw);
+        cudaFree(s.pd_ref);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);
     }

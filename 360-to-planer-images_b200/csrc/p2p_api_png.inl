@@ -3,6 +3,27 @@
 
 namespace {
 
+// CRC-32 byte table + the 4 byte tables of "advance the register by 256 zero bytes" (encoder), on the device once per context
+int ensure_crc_table(p2p_ctx *ctx) {
+    if (ctx->d_crc_table) return P2P_OK;
+    uint32_t table[5 * 256];
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        table[i] = c;
+    }
+    for (int j = 0; j < 4; ++j)
+        for (uint32_t b = 0; b < 256; ++b) {
+            uint32_t c = b << (8 * j);
+            for (int k = 0; k < 256; ++k) c = table[c & 0xFFu] ^ (c >> 8);
+            table[256 * (j + 1) + b] = c;
+        }
+    CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_crc_table), sizeof(table)));
+    CK(cudaMemcpy(ctx->d_crc_table, table, sizeof(table), cudaMemcpyHostToDevice));
+    return P2P_OK;
+}
+
+
 // ---- PNG encoder (p2p_png.cuh) -----------------------------------------------------------------
 // enqueue the encoder for n device images on the slot's stream; files land in s.j_out, sizes in s.j_sizes_h
 // (size 0 = this image is not handled on the device: the caller uses cv2.imwrite for it)
@@ -20,21 +41,9 @@ int enqueue_png(p2p_ctx *ctx, Slot &s, const uint8_t *d_bgr, int n, int W, int H
     G.img_stride = (size_t)W * H * 3;
     G.z_cap = (((size_t)G.N + G.N / 8 + 1024) + 15) & ~(size_t)15;
     G.out_cap = (G.z_cap + (G.z_cap / kIdat + 2) * 12 + 64 + 15) & ~(size_t)15;
-    if (!ctx->d_crc_table) {
-        uint32_t table[5 * 256];   // CRC-32 byte table + the 4 byte tables of "advance the register by 256 zero bytes"
-        for (uint32_t i = 0; i < 256; ++i) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            table[i] = c;
-        }
-        for (int j = 0; j < 4; ++j)
-            for (uint32_t b = 0; b < 256; ++b) {
-                uint32_t c = b << (8 * j);
-                for (int k = 0; k < 256; ++k) c = table[c & 0xFFu] ^ (c >> 8);
-                table[256 * (j + 1) + b] = c;
-            }
-        CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_crc_table), sizeof(table)));
-        CK(cudaMemcpy(ctx->d_crc_table, table, sizeof(table), cudaMemcpyHostToDevice));
+    {
+        const int rc_t = ensure_crc_table(ctx);
+        if (rc_t) return rc_t;
     }
     const size_t npos = (size_t)n * G.Npad, nblk = (size_t)n * G.max_blk;
     const size_t tile_words = npos / kTile;   // per-tile arrays: last change, inherited run start, tokens, first token index

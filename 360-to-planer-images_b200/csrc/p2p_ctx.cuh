@@ -6,6 +6,7 @@
 #include "p2p_jpeg_host.cuh"
 #include "p2p_jpegdec.cuh"
 #include "p2p_png.cuh"
+#include "p2p_pngdec.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -120,6 +121,20 @@ struct Slot {
     unsigned long long *j_sizes_h = nullptr;  // mapped host memory: file sizes
     unsigned long long *j_sizes_d = nullptr;
     int j_sizes_n = 0;
+    // PNG decoder (p2p_upload_pano_png): zlib stream (pinned + device), candidate / block lists, inflated image, history marks
+    struct PdCtr { uint32_t n_list, n_cand, n_runs; int bad; unsigned long long sums[2]; };
+    uint32_t *pd_zs_h = nullptr;              // pinned: the concatenated zlib stream
+    size_t pd_zs_h_cap = 0;
+    uint8_t *pd_tab_h = nullptr;              // pinned: CRC segments | candidates read back | blocks of the chain | counters
+    size_t pd_tab_h_cap = 0;
+    uint32_t *pd_zs = nullptr;
+    size_t pd_zs_cap = 0;
+    uint8_t *pd_tab = nullptr;                // device: CRC segments | survivor list | candidates | blocks | run starts | counters
+    size_t pd_tab_cap = 0;
+    uint8_t *pd_raw = nullptr;
+    size_t pd_raw_cap = 0;
+    uint16_t *pd_ref = nullptr;
+    size_t pd_ref_cap = 0;
     cudaEvent_t wait_ev = nullptr;            // blocking-sync event of wait_slot
 };
 

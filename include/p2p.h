@@ -269,6 +269,31 @@ int p2p_upload_pano_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len
 int p2p_decode_jpeg(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
                     size_t capacity_rows);
 
+/* ---- PNG panoramas decoded on the device (replaces cv2.imread(path) of a .png input, ref :244; the reference's own
+ *      default output format, ref :400-405, is the usual input of a second pass) ---------------------------------- */
+/* Chunk structure only: size of the image if the file is in the supported subset (8-bit gray / RGB / gray + alpha / RGBA,
+ * not interlaced, no APNG, no tRNS, every chunk CRC intact), else P2P_ERR_UNSUPPORTED - the caller then reads the file
+ * with cv2.imread as before. */
+int p2p_png_probe(const uint8_t *file, size_t len, int *W, int *H);
+/* Host model of the device decoder (no GPU, debug / tests): the same routines - block-start search, chain walk, inflate
+ * with symbolic history, resolution, Adler-32 / CRC-32 checks, unfilter - run serially.  bgr: capacity_rows rows of
+ * row_stride bytes, the array cv2.imread(path) returns.  stats (optional, 4 values): bit positions passing the first
+ * header test, block-start candidates, deflate blocks of the stream, blocks the chain walk had to measure itself. */
+int p2p_png_decode_host(const uint8_t *file, size_t len, uint8_t *bgr, size_t row_stride, size_t capacity_rows,
+                        uint64_t *stats);
+/* Decode the file into `slot` as its panorama (like cv2.imread + p2p_upload_pano, identical pixels): the deflate stream is
+ * inflated in parallel on the device (block starts found by testing every bit position for a dynamic-block header, every
+ * block decoded independently with symbolic history, back-references resolved afterwards), the scanline filters are undone
+ * there too (independent row runs, skewed wavefront inside a run); the pixels never exist in host memory.  Returns after
+ * the decode has finished: a damaged file (CRC-32 / Adler-32 mismatch, invalid codes or distances, wrong amount of data)
+ * or a stream the parallel decoder is not worth running on (fixed-Huffman-only writers, single huge blocks) gives
+ * P2P_ERR_UNSUPPORTED and leaves the slot without a panorama. */
+int p2p_upload_pano_png(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, int *Wp, int *Hp);
+/* Same decoder, pixels returned to the host (BGR, row_stride bytes per row, at least capacity_rows rows): the array
+ * cv2.imread / cv2.imdecode would return.  Synchronous; the slot's panorama is invalidated. */
+int p2p_decode_png(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, uint8_t *bgr_host, size_t row_stride,
+                   size_t capacity_rows);
+
 /* wait for everything enqueued on `slot` (slot < 0: all slots) */
 int p2p_sync(p2p_ctx *ctx, int slot);
 /* run the slot's work on a caller supplied cudaStream_t (e.g. torch's current stream) */
