@@ -32,7 +32,7 @@
 // __host__ __device__ code shared with a serial host model of the same pipeline (p2p_png_decode_host, no GPU: CPU tests
 // compare it with cv2.imdecode / zlib on every kind of file before the device sees one).
 //
-// Subset: 8-bit gray / RGB / gray + alpha / RGBA, not interlaced, no APNG, no tRNS; anything else, any damaged file and any
+// Subset: 8-bit gray / RGB / gray + alpha / RGBA, not interlaced, no APNG, no tRNS, no eXIf; anything else, any damaged file and any
 // stream whose blocks are too long to be worth it (a single huge block, fixed-Huffman-only writers) is declined
 // (P2P_ERR_UNSUPPORTED -> the caller uses cv2.imread as before).  The algorithms restated here are zlib's inflate
 // (inflate.c / inftrees.c validity rules; RFC 1951) and libpng's row filters (pngrutil.c png_read_filter_row; PNG
@@ -544,9 +544,9 @@ inline int parse_png(const uint8_t *f, size_t len, Parsed &P) {
                 break;
             }
             if (memcmp(type, "IHDR", 4) == 0) return 1;
-            // animation, transparency key, and every critical chunk other than PLTE (a suggested palette: ignored): decline
+            // animation, transparency key, EXIF block, and every critical chunk (PLTE, a suggested palette, included): decline
             if (memcmp(type, "acTL", 4) == 0 || memcmp(type, "fcTL", 4) == 0 || memcmp(type, "fdAT", 4) == 0 ||
-                memcmp(type, "tRNS", 4) == 0)
+                memcmp(type, "tRNS", 4) == 0 || memcmp(type, "eXIf", 4) == 0)  // (cv2.imread rotates by the EXIF orientation)
                 return 1;
             if (!(type[0] & 0x20)) return 1;  // critical chunk (PLTE included)
             for (int k = 0; k < 4; ++k)

@@ -119,6 +119,19 @@ def jpeg_probe(data: bytes):
     return (w.value, h.value) if rc == 0 else None
 
 
+def png_probe(data: bytes):
+    """(W, H) if the device PNG decoder accepts this file's structure (8-bit gray / RGB / gray + alpha / RGBA, not
+    interlaced, every chunk CRC intact), else None (read it with cv2.imread).  Chunk walk only, no GPU."""
+    w, h = C.c_int(), C.c_int()
+    rc = _lib.load().p2p_png_probe(data, len(data), C.byref(w), C.byref(h))
+    return (w.value, h.value) if rc == 0 else None
+
+
+def probe_encoded(data: bytes):
+    """(W, H) if one of the device decoders handles this file (PNG by its signature, else JPEG), else None."""
+    return png_probe(data) if data[:8] == b"\x89PNG\r\n\x1a\n" else jpeg_probe(data)
+
+
 def _as_u8_image(a, what="panorama") -> np.ndarray:
     a = np.asarray(a)
     if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
@@ -568,6 +581,45 @@ class Projector:
         else:
             run(slot)
         return out
+
+    # -- PNG panoramas decoded on the device (the decode side of cv2.imread for .png inputs, ref :244) ----------
+    def png_probe(self, data: bytes):
+        """(W, H) if the device decoder accepts this file's structure, else None (read it with cv2.imread)."""
+        return png_probe(data)
+
+    def upload_png(self, slot: int, data: bytes) -> tuple:
+        """Decode a PNG file into ``slot`` as its panorama (inflate, unfilter and packing on the device); returns (Wp, Hp).
+        Raises ``P2PError`` with code -6 for files outside the supported subset or damaged files."""
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.lib.p2p_upload_pano_png(self.ctx, slot, data, len(data), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def decode_png(self, data: bytes, slot: int | None = None) -> np.ndarray:
+        """The array ``cv2.imdecode(data, cv2.IMREAD_COLOR)`` returns (u8 [H, W, 3], BGR), decoded on the device."""
+        dims = png_probe(data)
+        if dims is None:
+            raise P2PError(-6, "PNG file outside the supported subset (fall back to cv2.imread)")
+        W, H = dims
+        out = np.empty((H, W, 3), np.uint8)
+
+        def run(s):
+            self._ck(self.lib.p2p_decode_png(self.ctx, s, data, len(data), out.ctypes.data, out.strides[0], H))
+
+        if slot is None:
+            with self.slots(1) as (s,):
+                run(s)
+        else:
+            run(slot)
+        return out
+
+    # -- either kind of file, chosen by its signature --------------------------------------------------------
+    def upload_encoded(self, slot: int, data: bytes) -> tuple:
+        """``upload_png`` for a PNG signature, else ``upload_jpeg``."""
+        return self.upload_png(slot, data) if data[:8] == b"\x89PNG\r\n\x1a\n" else self.upload_jpeg(slot, data)
+
+    def decode_encoded(self, data: bytes, slot: int | None = None) -> np.ndarray:
+        """``decode_png`` for a PNG signature, else ``decode_jpeg``."""
+        return self.decode_png(data, slot) if data[:8] == b"\x89PNG\r\n\x1a\n" else self.decode_jpeg(data, slot)
 
     def view_row_range(self, consts, W: int, H: int, Wp: int, Hp: int) -> tuple:
         """(first, last) panorama row (inclusive) the sampler reads for these pitch constants: what

@@ -102,7 +102,7 @@ def get_pitch_mapping(output_width, output_height, pitch_angle, pano_width, pano
 
 
 class _JpegSource:
-    """A JPEG panorama the device decoder handles, still as file bytes (the pixels will only exist on the GPU)."""
+    """A JPEG or PNG panorama one of the device decoders handles, still as file bytes (the pixels will only exist on the GPU)."""
 
     __slots__ = ("data", "Wp", "Hp", "path")
 
@@ -117,12 +117,13 @@ def _open_image(path):
     import cv2
 
     path = Path(path)
-    if path.suffix.lower() in (".jpg", ".jpeg"):
+    if path.suffix.lower() in (".jpg", ".jpeg", ".png"):
         try:
             data = path.read_bytes()
         except OSError:
             data = b""
-        dims = _engine.jpeg_probe(data) if data else None
+        # by content, like cv2.imread (which looks at the signature, not at the suffix)
+        dims = _engine.probe_encoded(data) if data else None
         if dims is not None:
             return _JpegSource(data, dims, path)
     return cv2.imread(str(path))
@@ -138,7 +139,7 @@ def _decode_source(proj, src, slot=None, device_declined=False):
         return src
     if not device_declined:
         try:
-            return proj.decode_jpeg(src.data, slot=slot)
+            return proj.decode_encoded(src.data, slot=slot)
         except _engine.P2PError as e:
             if e.code != -6:
                 raise
@@ -171,7 +172,7 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
     if isinstance(src, _JpegSource) and yaw_angles and pitch_angles:
         try:  # decode on the device straight into a slot, project from there (fractional yaws too: one pass, same slot)
             with proj.slots(1) as (s,):
-                proj.upload_jpeg(s, src.data)
+                proj.upload_encoded(s, src.data)
                 return proj.project_any(s, tables, consts, output_width, output_height)
         except _engine.P2PError as e:
             if e.code != -6:
@@ -189,7 +190,7 @@ def _split_upload(projs, src, stack):
     pano = src
     if isinstance(src, _JpegSource):
         try:
-            p0.upload_jpeg(s0, src.data)
+            p0.upload_encoded(s0, src.data)
             pano = None
         except _engine.P2PError as e:
             if e.code != -6:
@@ -332,7 +333,7 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
             pano = src
             if isinstance(src, _JpegSource):
                 try:  # JPEG in, JPEG out: no pixel ever crosses PCIe
-                    proj.upload_jpeg(s, src.data)
+                    proj.upload_encoded(s, src.data)
                     pano = None                      # the panorama is resident in the slot
                 except _engine.P2PError as e:
                     if e.code != -6:
@@ -370,7 +371,7 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
             pano = src
             if isinstance(src, _JpegSource):
                 try:
-                    proj.upload_jpeg(s, src.data)
+                    proj.upload_encoded(s, src.data)
                     pano = None                      # the panorama is resident in the slot
                 except _engine.P2PError as e:
                     if e.code != -6:

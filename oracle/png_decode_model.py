@@ -73,7 +73,7 @@ def in_subset(data: bytes):
     for n in names[1:-1]:
         if n == b"IDAT":
             continue
-        if n in (b"acTL", b"fcTL", b"fdAT", b"tRNS", b"IHDR") or not (n[0] & 0x20) or not n.isalpha():
+        if n in (b"acTL", b"fcTL", b"fdAT", b"tRNS", b"eXIf", b"IHDR") or not (n[0] & 0x20) or not n.isalpha():
             return None
     return W, H, ctype
 

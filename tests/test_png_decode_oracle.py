@@ -129,6 +129,7 @@ def test_unsupported_files_are_declined(host_decode):
         "16 bit": cv2.imencode(".png", np.zeros((5, 5, 3), np.uint16))[1].tobytes(),
         "tRNS": M.write_png(img8, 2, extra_chunks=[(b"tRNS", bytes(6))]),
         "APNG": M.write_png(img8, 2, extra_chunks=[(b"acTL", struct.pack(">II", 1, 0))]),
+        "eXIf": M.write_png(img8, 2, extra_chunks=[(b"eXIf", b"MM\0*\0\0\0\x08\0\0")]),
         "unknown critical chunk": M.write_png(img8, 2, extra_chunks=[(b"ABCD", b"x")]),
         "not a PNG": b"\xff\xd8\xff\xe0" + bytes(100),
         "empty": b"",
