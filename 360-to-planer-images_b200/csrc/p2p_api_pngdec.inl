@@ -6,7 +6,7 @@ namespace {
 // where the decoder's small arrays sit in the slot's table buffers (device: s.pd_tab, page-locked: s.pd_tab_h)
 struct PdLayout {
     uint32_t n_segs = 0, cap_list = 0, cap_cand = 0, cap_blocks = 0;
-    size_t d_segs = 0, d_list = 0, d_cands = 0, d_blocks = 0, d_runs = 0, d_ctr = 0, d_total = 0;
+    size_t d_segs = 0, d_list = 0, d_cands = 0, d_blocks = 0, d_bands = 0, d_prog = 0, d_ctr = 0, d_total = 0;
     size_t h_segs = 0, h_cands = 0, h_blocks = 0, h_ctr = 0, h_total = 0;
 };
 
@@ -27,7 +27,8 @@ PdLayout pd_layout(const p2ppdec::Parsed &P) {
     L.d_list = at; at = up(at + (size_t)L.cap_list * sizeof(uint64_t));
     L.d_cands = at; at = up(at + (size_t)L.cap_cand * sizeof(Cand));
     L.d_blocks = at; at = up(at + (size_t)L.cap_blocks * sizeof(Block));
-    L.d_runs = at; at = up(at + (size_t)P.info.H * sizeof(uint32_t));
+    L.d_bands = at; at = up(at + (size_t)P.info.H * sizeof(uint32_t));
+    L.d_prog = at; at = up(at + ((size_t)P.info.H + 1) * sizeof(uint32_t));   // progress per band | ticket
     L.d_ctr = at; at = up(at + sizeof(Slot::PdCtr));
     L.d_total = at;
     at = 0;
@@ -75,8 +76,8 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         if (!rc) rc = ensure_pinned(ctx, &s.pd_tab_h, &s.pd_tab_h_cap, L.h_total);
         if (!rc) rc = ensure_grow(ctx, &s.pd_zs, &s.pd_zs_cap, n_words * 4);
         if (!rc) rc = ensure_grow(ctx, &s.pd_tab, &s.pd_tab_cap, L.d_total);
-        if (!rc) rc = ensure(ctx, &s.pd_raw, &s.pd_raw_cap, I.raw_bytes + 16);
-        if (!rc) rc = ensure(ctx, &s.pd_ref, &s.pd_ref_cap, (I.raw_bytes + 16) * sizeof(uint16_t));
+        if (!rc) rc = ensure(ctx, &s.pd_raw, &s.pd_raw_cap, I.raw_bytes + 64);
+        if (!rc) rc = ensure(ctx, &s.pd_ref, &s.pd_ref_cap, (I.raw_bytes + 64) * sizeof(uint16_t));
         if (!rc) rc = ensure(ctx, &s.d_bgr, &s.bgr_cap, dstride * I.H);
         if (rc) return rc;
     }
@@ -95,7 +96,8 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     uint64_t *list_d = reinterpret_cast<uint64_t *>(s.pd_tab + L.d_list);
     Cand *cands_d = reinterpret_cast<Cand *>(s.pd_tab + L.d_cands);
     Block *blocks_d = reinterpret_cast<Block *>(s.pd_tab + L.d_blocks);
-    uint32_t *runs_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_runs);
+    uint32_t *bands_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_bands);
+    uint32_t *prog_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_prog);
     Slot::PdCtr *ctr_d = reinterpret_cast<Slot::PdCtr *>(s.pd_tab + L.d_ctr);
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -156,15 +158,20 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         pd_tails_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, s.pd_raw, s.pd_ref);
         pd_resolve_kernel<<<dim3(nb, 4), 256, 0, st>>>(blocks_d, s.pd_raw, s.pd_ref);
         pd_adler_kernel<<<(unsigned)((I.raw_bytes + 4095) / 4096), 256, 0, st>>>(s.pd_raw, I.raw_bytes, ctr_d->sums);
-        pd_runs_kernel<<<1, 1024, 0, st>>>(s.pd_raw, I.H, stride, runs_d, &ctr_d->n_runs, &ctr_d->bad);
+        // the history marks are done with: their buffer takes the reconstructed rows (rows of rstride bytes, word aligned)
+        uint8_t *recon = reinterpret_cast<uint8_t *>(s.pd_ref);
+        const size_t rstride = (I.row_bytes + 3) & ~(size_t)3;
+        CK(cudaMemsetAsync(prog_d, 0, ((size_t)I.H + 1) * sizeof(uint32_t), st));
+        pd_bands_kernel<<<1, 1024, 0, st>>>(s.pd_raw, I.H, stride, bands_d, &ctr_d->n_runs, &ctr_d->bad);
         const unsigned ugrid = (unsigned)((I.H + 7) / 8);
+        uint32_t *ticket = prog_d + I.H;
         switch (I.bpp) {
-            case 1: pd_unfilter_kernel<1><<<ugrid, 256, 0, st>>>(s.pd_raw, I.W, I.H, stride, runs_d, &ctr_d->n_runs); break;
-            case 2: pd_unfilter_kernel<2><<<ugrid, 256, 0, st>>>(s.pd_raw, I.W, I.H, stride, runs_d, &ctr_d->n_runs); break;
-            case 3: pd_unfilter_kernel<3><<<ugrid, 256, 0, st>>>(s.pd_raw, I.W, I.H, stride, runs_d, &ctr_d->n_runs); break;
-            default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, I.W, I.H, stride, runs_d, &ctr_d->n_runs); break;
+            case 1: pd_unfilter_kernel<1><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
+            case 2: pd_unfilter_kernel<2><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
+            case 3: pd_unfilter_kernel<3><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
+            default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
         }
-        pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(s.pd_raw, I.W, I.H, stride, I.bpp, s.d_bgr, dstride);
+        pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
         ctx->launches += 7;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));

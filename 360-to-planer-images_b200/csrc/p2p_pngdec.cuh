@@ -295,16 +295,21 @@ struct BlockOut {
     uint64_t end_bit;
     uint32_t out_len;
     int final_block;
+    uint32_t tail_marks;  // WRITE: history marks left in the block's last 32 KiB (0: pd_tails_kernel has nothing to do here)
 };
 
 // One deflate block starting at start_bit.  WRITE = false: only measured (where it ends, how many bytes it produces).
 // WRITE = true: bytes go to raw[out_off ..], and ref[] holds for every byte 0 (final) or k = 1 .. 32768 (the byte k
 // positions in front of this block's first byte, not known yet).  out_cap: size of the whole inflated image; wsize: window
 // of the zlib header.  Distances beyond the data produced so far are invalid ("invalid distance too far back").
+// expect_len (WRITE): the length the block was measured with, which says where its last 32 KiB begin.
 template <bool WRITE>
 PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bits, uint64_t start_bit, Tables &T,
                        uint8_t *lens, uint8_t *raw, uint16_t *ref, uint64_t out_off, uint64_t out_cap, uint32_t wsize,
-                       BlockOut &R) {
+                       BlockOut &R, uint32_t expect_len = 0) {
+    const uint64_t tail_from = expect_len > kWindow ? expect_len - kWindow : 0;
+    uint32_t marks = 0;
+    R.tail_marks = 0;
     Bits br;
     br.init(zs, n_words, start_bit);
     R.final_block = (int)br.get(1);
@@ -387,13 +392,16 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
             const uint64_t at = out_off + o;
             for (uint32_t i = 0; i < len; ++i) {
                 const int64_t src = (int64_t)(o + i) - (int64_t)dist;  // relative to the block's first byte
+                uint16_t r;
                 if (src < 0) {
-                    ref[at + i] = (uint16_t)(-src);
+                    r = (uint16_t)(-src);
                     raw[at + i] = 0;
                 } else {
                     raw[at + i] = raw[out_off + src];
-                    ref[at + i] = ref[out_off + src];
+                    r = ref[out_off + src];
                 }
+                ref[at + i] = r;
+                marks += (r != 0 && o + i >= tail_from);
             }
         }
         o += len;
@@ -401,6 +409,7 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
     R.end_bit = br.pos();
     if (R.end_bit > stream_bits) return PD_BAD;
     R.out_len = (uint32_t)o;
+    R.tail_marks = marks;
     return PD_OK;
 }
 
@@ -584,7 +593,8 @@ struct Cand {
 };
 struct Block {
     uint64_t bit, out_off;
-    uint32_t out_len, pad;
+    uint32_t out_len;
+    uint32_t tail_marks;  // written by the decoding pass
 };
 
 // Chain walk (host): from the first block behind the zlib header, through measured candidates where there are any and
@@ -681,12 +691,15 @@ inline int decode_host_model(const uint8_t *f, size_t len, uint8_t *bgr, size_t 
     }
     std::vector<uint8_t> raw(I.raw_bytes);
     std::vector<uint16_t> ref(I.raw_bytes);
-    for (const Block &b : blocks) {
+    for (Block &b : blocks) {
         BlockOut R;
-        if (decode_block<true>(zs, n_words, stream_bits, b.bit, T, lens, raw.data(), ref.data(), b.out_off, I.raw_bytes, I.wsize, R))
+        if (decode_block<true>(zs, n_words, stream_bits, b.bit, T, lens, raw.data(), ref.data(), b.out_off, I.raw_bytes, I.wsize, R, b.out_len))
             return 1;
+        if (R.out_len != b.out_len) return 1;
+        b.tail_marks = R.tail_marks;
     }
     for (const Block &b : blocks) {  // tails, in order
+        if (!b.tail_marks) continue;
         const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
         for (uint64_t p = t0; p < end; ++p)
             if (ref[p]) {
@@ -788,7 +801,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) pd_measure_kernel(const uin
 
 // the blocks of the chain decoded with symbolic history (ref[]); any failure raises *bad
 __global__ void __launch_bounds__(kDecodeWarps * 32) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
-                                                                       const Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw,
+                                                                       Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw,
                                                                        uint16_t *ref, uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
     __shared__ Tables tabs[kDecodeWarps];
     const uint32_t warp = threadIdx.x >> 5;
@@ -797,22 +810,36 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) pd_decode_kernel(const uint
             uint8_t lens[320];
             BlockOut R{0, 0, 0};
             const Block b = blocks[i];
-            const int rc = decode_block<true>(zs, n_words, stream_bits, b.bit, tabs[warp], lens, raw, ref, b.out_off, out_cap, wsize, R);
+            const int rc = decode_block<true>(zs, n_words, stream_bits, b.bit, tabs[warp], lens, raw, ref, b.out_off, out_cap, wsize, R, b.out_len);
             if (rc || R.out_len != b.out_len) *bad = 1;
+            blocks[i].tail_marks = R.tail_marks;
         }
         __syncwarp();
     }
 }
 
-// the last 32 KiB of every block made final, block after block (one CTA; see the header comment, step 4)
+// the last 32 KiB of every block made final, block after block (one CTA of 1024 threads = 32 positions per thread: all
+// marks are loaded first, then all history bytes, then the stores - two memory round trips per block; blocks whose last
+// 32 KiB hold no mark are skipped; see the header comment, step 4)
 __global__ void __launch_bounds__(1024) pd_tails_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw, uint16_t *ref) {
     for (uint32_t i = 0; i < n_blocks; ++i) {
         const Block b = blocks[i];
+        if (b.tail_marks == 0) continue;
         const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
-        for (uint64_t p = t0 + threadIdx.x; p < end; p += blockDim.x) {
-            const uint32_t r = ref[p];
-            if (r) {
-                raw[p] = raw[b.out_off - r];
+        uint32_t r[32];
+        uint8_t v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const uint64_t p = t0 + threadIdx.x + 1024u * q;
+            r[q] = p < end ? ref[p] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = r[q] ? raw[b.out_off - r[q]] : (uint8_t)0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const uint64_t p = t0 + threadIdx.x + 1024u * q;
+            if (r[q]) {
+                raw[p] = v[q];
                 ref[p] = 0;
             }
         }
@@ -884,9 +911,11 @@ __global__ void __launch_bounds__(128) pd_crc_kernel(const uint8_t *__restrict__
     segs[i].crc = ~crc;
 }
 
-// first rows of the independent runs (row 0 and every row filtered None / Sub), in order; a filter type above 4 raises *bad
-__global__ void __launch_bounds__(1024) pd_runs_kernel(const uint8_t *__restrict__ raw, int H, size_t stride, uint32_t *__restrict__ run_start,
-                                                       uint32_t *__restrict__ n_runs, int *__restrict__ bad) {
+// Bands of the unfilter wavefront, in order: a band starts at row 0, at every row filtered None / Sub (it does not depend on
+// the row above: an independent run starts) and at every multiple of 32 rows.  band_first[k] = first row | depends on the band
+// before << 31.  A filter type above 4 raises *bad.
+__global__ void __launch_bounds__(1024) pd_bands_kernel(const uint8_t *__restrict__ raw, int H, size_t stride, uint32_t *__restrict__ band_first,
+                                                        uint32_t *__restrict__ n_bands, int *__restrict__ bad) {
     __shared__ uint32_t s[1024];
     const int per = (H + 1023) / 1024;
     const int r0 = threadIdx.x * per, r1 = min(H, r0 + per);
@@ -894,7 +923,7 @@ __global__ void __launch_bounds__(1024) pd_runs_kernel(const uint8_t *__restrict
     for (int r = r0; r < r1; ++r) {
         const uint32_t ft = raw[(size_t)r * stride];
         if (ft > 4) *bad = 1;
-        mine += (r == 0 || ft <= 1);
+        mine += (r == 0 || ft <= 1 || (r & 31) == 0);
     }
     s[threadIdx.x] = mine;
     __syncthreads();
@@ -907,62 +936,131 @@ __global__ void __launch_bounds__(1024) pd_runs_kernel(const uint8_t *__restrict
     uint32_t at = s[threadIdx.x] - mine;
     for (int r = r0; r < r1; ++r) {
         const uint32_t ft = raw[(size_t)r * stride];
-        if (r == 0 || ft <= 1) run_start[at++] = (uint32_t)r;
+        const bool indep = (r == 0 || ft <= 1);
+        if (indep || (r & 31) == 0) band_first[at++] = (uint32_t)r | (indep ? 0u : 0x80000000u);
     }
-    if (threadIdx.x == 1023) *n_runs = s[1023];
+    if (threadIdx.x == 1023) *n_bands = s[1023];
 }
 
-// the filters undone in place: a warp per run, 32 rows per band as a skewed wavefront (lane t works on pixel s - t at step s)
+constexpr int kChunkPx = 8;  // pixels a lane reconstructs per step of the wavefront
+
+// The filters undone: raw (filter byte + filtered bytes per row, stride) -> recon (reconstructed bytes, rows of rstride bytes,
+// rstride a multiple of 4).  A warp per band (taken in image order through a ticket, so that a band only ever waits for a warp
+// that is already running); lane t owns row first + t and works on chunk s - t (8 pixels) at step s: the reconstructed
+// chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it.  Lane 0 of a band that
+// continues a run reads the row above from recon once the band before has published it (progress[band] = chunks of its last
+// row that are final; bounded polling: a wait that does not end raises *bad, it cannot hang).  The filtered bytes of the next
+// chunk are loaded (aligned words + funnel shift) while the current one is computed.
 template <int BPP>
-__global__ void __launch_bounds__(256) pd_unfilter_kernel(uint8_t *raw, int W, int H, size_t stride, const uint32_t *__restrict__ run_start,
-                                                          const uint32_t *__restrict__ n_runs) {
-    const uint32_t run = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const uint32_t nr = *n_runs;
-    if (run >= nr) return;
-    const int first = (int)run_start[run], last = run + 1 < nr ? (int)run_start[run + 1] : H;  // rows first .. last - 1
-    for (int band = first; band < last; band += 32) {
-        const int row = band + (int)lane;
-        const bool active = row < last;
-        uint8_t *cur = raw + (size_t)(active ? row : band) * stride;
-        const uint8_t *up = (band > 0) ? raw + (size_t)(band - 1) * stride : nullptr;  // the row above the band (lane 0 reads it)
-        const uint32_t ft = active ? cur[0] : 0u;
-        uint32_t a[BPP], c[BPP], out[BPP];
+__global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restrict__ raw, uint8_t *recon, int W, int H, size_t stride, size_t rstride,
+                                                          const uint32_t *__restrict__ band_first, const uint32_t *__restrict__ n_bands,
+                                                          uint32_t *ticket, uint32_t *progress, int *bad) {
+    constexpr int NW = 2 * BPP;            // words per chunk
+    constexpr int CB = kChunkPx * BPP;     // bytes per chunk
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t k = 0;
+    if (lane == 0) k = atomicAdd(ticket, 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    const uint32_t nb = *n_bands;
+    if (k >= nb) return;
+    const uint32_t bf = band_first[k];
+    const int first = (int)(bf & 0x7fffffffu);
+    const bool dep = (bf >> 31) != 0;
+    const int last = k + 1 < nb ? (int)(band_first[k + 1] & 0x7fffffffu) : H;
+    const int rows = last - first;  // 1 .. 32
+    const bool active = (int)lane < rows;
+    const int row = first + (active ? (int)lane : 0);
+    const uint8_t *src = raw + (size_t)row * stride;
+    uint8_t *dst = recon + (size_t)row * rstride;
+    const uint32_t *up_row = reinterpret_cast<const uint32_t *>(recon + (size_t)(first > 0 ? first - 1 : 0) * rstride);
+    const uint32_t ft = active ? src[0] : 0u;
+    const int row_bytes = W * BPP;
+    const int nc = (W + kChunkPx - 1) / kChunkPx;
+    // aligned words under this row's filtered bytes
+    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(src + 1);
+    const uint32_t *wbase = reinterpret_cast<const uint32_t *>(addr0 & ~(uintptr_t)3);
+    const int sh = (int)(addr0 & 3) * 8;
+    uint32_t cur[NW], nxt[NW + 1], outw[NW], left[BPP], upleft[BPP];
 #pragma unroll
-        for (int k = 0; k < BPP; ++k) a[k] = c[k] = out[k] = 0;
-        const int rows_here = min(32, last - band);
-        for (int s = 0; s < W + rows_here - 1; ++s) {
-            const int x = s - (int)lane;
-            const bool on = active && x >= 0 && x < W;
-            uint32_t b[BPP];
+    for (int i = 0; i < NW; ++i) cur[i] = outw[i] = 0;
 #pragma unroll
-            for (int k = 0; k < BPP; ++k) b[k] = __shfl_up_sync(0xffffffffu, out[k], 1);
-            if (lane == 0) {
+    for (int i = 0; i < BPP; ++i) left[i] = upleft[i] = 0;
+    volatile uint32_t *prog = progress;
+    const int steps = nc + rows - 1;
+    for (int s = 0; s < steps; ++s) {
+        const int j = s - (int)lane;           // this lane's chunk at this step
+        const bool on = active && j >= 0 && j < nc;
+        // filtered bytes of chunk j (this step) - loaded one step ahead except for the first
+        if (active && j + 1 >= 0 && j + 1 < nc) {   // prefetch chunk j + 1
 #pragma unroll
-                for (int k = 0; k < BPP; ++k) b[k] = (up && on) ? up[1 + (size_t)x * BPP + k] : 0u;
+            for (int i = 0; i <= NW; ++i) nxt[i] = __ldg(wbase + (size_t)(j + 1) * NW + i);
+        }
+        if (on && j == 0) {
+            uint32_t w0[NW + 1];
+#pragma unroll
+            for (int i = 0; i <= NW; ++i) w0[i] = __ldg(wbase + i);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(w0[i], w0[i + 1], sh);
+        }
+        // the reconstructed chunk above: from the lane above (its result of the previous step), lane 0 from memory
+        uint32_t up[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) up[i] = __shfl_up_sync(0xffffffffu, outw[i], 1);
+        if (lane == 0) {
+            const bool need = on && dep;
+            if (need) {
+                uint32_t spins = 0;
+                while (prog[k - 1] <= (uint32_t)j) {
+                    if (++spins > (1u << 24)) {
+                        *bad = 1;
+                        break;
+                    }
+                }
+                __threadfence();
             }
-            if (on) {
-                uint8_t *px = cur + 1 + (size_t)x * BPP;
 #pragma unroll
-                for (int k = 0; k < BPP; ++k) {
-                    const uint32_t v = unfilter_byte(ft, px[k], a[k], b[k], c[k]);
-                    px[k] = (uint8_t)v;
-                    c[k] = b[k];
-                    a[k] = v;
-                    out[k] = v;
+            for (int i = 0; i < NW; ++i) up[i] = need ? __ldcg(up_row + (size_t)j * NW + i) : 0u;
+        }
+        if (on) {
+#pragma unroll
+            for (int px = 0; px < kChunkPx; ++px) {
+#pragma unroll
+                for (int c = 0; c < BPP; ++c) {
+                    const int byte = px * BPP + c;
+                    const uint32_t f = (cur[byte >> 2] >> (8 * (byte & 3))) & 255u;
+                    const uint32_t b = (up[byte >> 2] >> (8 * (byte & 3))) & 255u;
+                    const uint32_t v = unfilter_byte(ft, f, left[c], b, upleft[c]);
+                    upleft[c] = b;
+                    left[c] = v;
+                    if ((byte & 3) == 0) outw[byte >> 2] = v;
+                    else outw[byte >> 2] |= v << (8 * (byte & 3));
                 }
             }
+            const int nbytes = min(CB, row_bytes - j * CB);
+            uint32_t *o = reinterpret_cast<uint32_t *>(dst + (size_t)j * CB);
+            if (nbytes == CB) {
+#pragma unroll
+                for (int i = 0; i < NW; ++i) o[i] = outw[i];
+            } else {
+                for (int i = 0; i < nbytes; ++i) dst[(size_t)j * CB + i] = (uint8_t)(outw[i >> 2] >> (8 * (i & 3)));
+            }
+            if ((int)lane == rows - 1) {   // the band's last row: publish it for the band below
+                __threadfence();
+                prog[k] = (uint32_t)(j + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(nxt[i], nxt[i + 1], sh);
         }
-        __syncwarp();  // the next band's lane 0 reads the row lane 31 has just written
     }
 }
 
-// reconstructed rows -> BGR staging image (row stride dstride)
-__global__ void __launch_bounds__(256) pd_bgr_kernel(const uint8_t *__restrict__ raw, int W, int H, size_t stride, int bpp, uint8_t *__restrict__ bgr,
+// reconstructed rows (rstride bytes each) -> BGR staging image (row stride dstride)
+__global__ void __launch_bounds__(256) pd_bgr_kernel(const uint8_t *__restrict__ recon, int W, int H, size_t rstride, int bpp, uint8_t *__restrict__ bgr,
                                                      size_t dstride) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     uint8_t v[3];
-    pixel_bgr(raw + (size_t)y * stride + 1 + (size_t)x * bpp, bpp, v);
+    pixel_bgr(recon + (size_t)y * rstride + (size_t)x * bpp, bpp, v);
     uint8_t *o = bgr + (size_t)y * dstride + 3 * (size_t)x;
     o[0] = v[0];
     o[1] = v[1];

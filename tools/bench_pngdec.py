@@ -23,6 +23,7 @@ def main():
     pkg = g.load_package()
     proj = pkg.Projector(0, n_slots=2)
     Wp, Hp = (2048, 1024) if "--small" in sys.argv else (8192, 4096)
+    reps = 1 if "--once" in sys.argv else 4   # --once: a single decode per file (under ncu)
     rng = np.random.default_rng(0)
     smooth = synth.smooth(Wp, Hp, 0)
     textured = np.clip(smooth.astype(np.int16) + rng.integers(-12, 13, smooth.shape, dtype=np.int16), 0, 255).astype(np.uint8)
@@ -45,13 +46,13 @@ def main():
             proj.sync(s)
             same = bool(np.array_equal(proj.download_pano(s, Wp, Hp), ref))
             t_dev = []
-            for _ in range(4):
+            for _ in range(reps):
                 t0 = time.perf_counter()
                 proj.upload_png(s, data)
                 proj.sync(s)
                 t_dev.append(time.perf_counter() - t0)
             t_cv = []
-            for _ in range(2):
+            for _ in range(1 if reps == 1 else 2):
                 t0 = time.perf_counter()
                 pix = cv2.imdecode(arr, cv2.IMREAD_COLOR)
                 proj.upload(s, pix)
