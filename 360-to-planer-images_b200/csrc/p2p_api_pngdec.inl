@@ -155,7 +155,10 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaMemcpyAsync(blocks_d, blocks_h, (size_t)nb * sizeof(Block), cudaMemcpyHostToDevice, st));
         pd_decode_kernel<<<(nb + kDecodeWarps - 1) / kDecodeWarps, kDecodeWarps * 32, 0, st>>>(s.pd_zs, n_words, stream_bits, blocks_d, nb, s.pd_raw,
                                                                                            s.pd_ref, I.raw_bytes, I.wsize, &ctr_d->bad);
-        pd_tails_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, s.pd_raw, s.pd_ref);
+        const uint32_t per = group_size(nb);
+        pd_tails_group_kernel<<<(nb + per - 1) / per, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
+        pd_tails_chain_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
+        pd_tails_finish_kernel<<<nb, 256, 0, st>>>(blocks_d, per, s.pd_raw, s.pd_ref);
         pd_resolve_kernel<<<dim3(nb, 4), 256, 0, st>>>(blocks_d, s.pd_raw, s.pd_ref);
         pd_adler_kernel<<<(unsigned)((I.raw_bytes + 4095) / 4096), 256, 0, st>>>(s.pd_raw, I.raw_bytes, ctr_d->sums);
         // the history marks are done with: their buffer takes the reconstructed rows (rows of rstride bytes, word aligned)
@@ -172,7 +175,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
             default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
         }
         pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
-        ctx->launches += 7;
+        ctx->launches += 9;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));
         s.valid = false;  // the staging image changed under whatever panorama the slot held

@@ -17,9 +17,12 @@
 //   3. the blocks of the chain are decoded in parallel (pd_decode_kernel) with SYMBOLIC history: a back-reference that
 //      reaches in front of its own block cannot be resolved yet, so the byte is recorded as "history byte k before my block"
 //      in a 16-bit side array (0 = final byte); copies inside the block copy those marks along.
-//   4. pd_tails_kernel walks the blocks in order and resolves the last 32 KiB of each (all its marks point into the already
-//      final 32 KiB in front of the block); after that every remaining mark anywhere points at a final byte and
-//      pd_resolve_kernel finishes the image in one parallel pass.
+//   4. the last 32 KiB of every block are made final first (all marks of a block point into the 32 KiB in front of it, i.e.
+//      into the last 32 KiB of earlier blocks).  That is a chain through all blocks, cut into ~sqrt(n) GROUPS of consecutive
+//      blocks: pd_tails_group_kernel walks every group on its own SM and re-bases what it cannot resolve inside the group to
+//      "history byte k before my GROUP"; pd_tails_chain_kernel walks the groups in order and finalises the 32 KiB in front of
+//      each; pd_tails_finish_kernel resolves the re-based marks everywhere.  After that every remaining mark anywhere points
+//      at a final byte and pd_resolve_kernel finishes the image in one parallel pass.
 //   5. Adler-32 of the inflated data and CRC-32 of every chunk are checked (pd_adler_kernel, pd_crc_kernel + host fold):
 //      a file libpng would refuse is never decoded differently - it is declined and read by cv2.imread as before.
 //   6. pd_runs_kernel / pd_unfilter_kernel undo the scanline filters in place.  Rows with filter None / Sub do not depend
@@ -438,6 +441,20 @@ PD_HD void pixel_bgr(const uint8_t *px, int bpp, uint8_t *bgr) {
     }
 }
 
+// One mark of a block's last 32 KiB during the walk through its group (block start bo, group start gs): the history byte
+// sits at abs = bo - mark.  Inside the group it has been walked already: final -> copy it; itself re-based -> inherit its
+// mark.  In front of the group -> re-base the mark to the group start (still <= 32768: abs >= gs - 32768 because bo >= gs).
+PD_HD void tail_step(uint8_t *raw, uint16_t *ref, uint64_t p, uint64_t bo, uint64_t gs) {
+    const uint64_t abs = bo - ref[p];
+    if (abs >= gs) {
+        const uint16_t rt = ref[abs];
+        if (rt == 0) raw[p] = raw[abs];
+        ref[p] = rt;
+    } else {
+        ref[p] = (uint16_t)(gs - abs);
+    }
+}
+
 // ---- CRC-32 (PNG chunk checksums) ----------------------------------------------------------------------------------
 // multiplication of two polynomials mod the CRC-32 polynomial, reflected representation (zlib crc32.c multmodp)
 inline uint32_t crc_mulmod(uint32_t a, uint32_t b) {
@@ -641,6 +658,14 @@ inline int walk_chain(const uint32_t *zs, const Parsed &P, std::vector<Cand> &ca
     return 0;
 }
 
+// blocks per group of the tail pass: ~sqrt(n), so that the serial walk inside a group and the serial walk over the groups
+// are equally long
+inline uint32_t group_size(uint32_t n_blocks) {
+    uint32_t m = 1;
+    while ((uint64_t)m * m < n_blocks) ++m;
+    return m;
+}
+
 // ---- serial host model of the whole decoder (tests; the product path runs the kernels below) ------------------------
 // quick -> full -> measure -> walk -> symbolic decode -> tails -> resolve -> Adler / CRC -> unfilter -> BGR, the same
 // routines in the same order, one "thread" after the other.  bgr: H rows of row_stride bytes.  0 = ok, 1 = declined.
@@ -698,12 +723,34 @@ inline int decode_host_model(const uint8_t *f, size_t len, uint8_t *bgr, size_t 
         if (R.out_len != b.out_len) return 1;
         b.tail_marks = R.tail_marks;
     }
-    for (const Block &b : blocks) {  // tails, in order
+    // tails: groups of consecutive blocks (re-base to the group start), the chain over the groups, the re-based marks
+    const uint32_t nb = (uint32_t)blocks.size(), per = group_size(nb), ng = (nb + per - 1) / per;
+    for (uint32_t g = 0; g < ng; ++g) {
+        const uint64_t gs = blocks[(size_t)g * per].out_off;
+        for (uint32_t i = g * per; i < std::min(nb, (g + 1) * per); ++i) {
+            const Block &b = blocks[i];
+            if (!b.tail_marks) continue;
+            const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
+            for (uint64_t p = t0; p < end; ++p)
+                if (ref[p]) tail_step(raw.data(), ref.data(), p, b.out_off, gs);
+        }
+    }
+    for (uint32_t g = 1; g + 1 < ng; ++g) {
+        const uint64_t gs = blocks[(size_t)g * per].out_off, next = blocks[(size_t)(g + 1) * per].out_off;
+        for (uint64_t p = std::max(gs, next > kWindow ? next - kWindow : 0); p < next; ++p)
+            if (ref[p]) {
+                raw[p] = raw[gs - ref[p]];
+                ref[p] = 0;
+            }
+    }
+    for (uint32_t i = per; i < nb; ++i) {
+        const Block &b = blocks[i];
         if (!b.tail_marks) continue;
+        const uint64_t gs = blocks[(size_t)(i / per) * per].out_off;
         const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
         for (uint64_t p = t0; p < end; ++p)
             if (ref[p]) {
-                raw[p] = raw[b.out_off - ref[p]];
+                raw[p] = raw[gs - ref[p]];
                 ref[p] = 0;
             }
     }
@@ -780,7 +827,7 @@ constexpr int kDecodeWarps = 8;  // warps (= blocks of the stream being decoded)
 
 // every candidate decoded to its end-of-block symbol, nothing written: a warp per candidate (lane 0 decodes: the chain of
 // dependent table look-ups is the whole cost, the other lanes would only wait)
-__global__ void __launch_bounds__(kDecodeWarps * 32) pd_measure_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
+__global__ void __launch_bounds__(kDecodeWarps * 32, 4) pd_measure_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
                                                                         Cand *__restrict__ cands, const uint32_t *__restrict__ n_cands, uint32_t cap,
                                                                         uint64_t out_cap, uint32_t wsize) {
     __shared__ Tables tabs[kDecodeWarps];
@@ -800,7 +847,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) pd_measure_kernel(const uin
 }
 
 // the blocks of the chain decoded with symbolic history (ref[]); any failure raises *bad
-__global__ void __launch_bounds__(kDecodeWarps * 32) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
+__global__ void __launch_bounds__(kDecodeWarps * 32, 4) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
                                                                        Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw,
                                                                        uint16_t *ref, uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
     __shared__ Tables tabs[kDecodeWarps];
@@ -818,23 +865,65 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) pd_decode_kernel(const uint
     }
 }
 
-// the last 32 KiB of every block made final, block after block (one CTA of 1024 threads = 32 positions per thread: all
-// marks are loaded first, then all history bytes, then the stores - two memory round trips per block; blocks whose last
-// 32 KiB hold no mark are skipped; see the header comment, step 4)
-__global__ void __launch_bounds__(1024) pd_tails_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw, uint16_t *ref) {
-    for (uint32_t i = 0; i < n_blocks; ++i) {
+// Tail pass, part 1: a CTA per group of `per` consecutive blocks walks its blocks in order (tail_step; 1024 threads = 32
+// positions per thread: marks first, then the history look-ups, then the stores; blocks without marks in their last 32 KiB
+// are skipped)
+__global__ void __launch_bounds__(1024) pd_tails_group_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint32_t per, uint8_t *raw,
+                                                              uint16_t *ref) {
+    const uint32_t i0 = blockIdx.x * per, i1 = min(n_blocks, i0 + per);
+    const uint64_t gs = blocks[i0].out_off;
+    for (uint32_t i = i0; i < i1; ++i) {
         const Block b = blocks[i];
         if (b.tail_marks == 0) continue;
         const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
+        for (int half = 0; half < 2; ++half) {   // 2 x 16 positions per thread (registers)
+            uint32_t r[16], rt[16];
+            uint8_t v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const uint64_t p = t0 + threadIdx.x + 1024u * (16 * half + q);
+                r[q] = p < end ? ref[p] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const uint64_t abs = b.out_off - r[q];
+                const bool inside = r[q] && abs >= gs;
+                rt[q] = inside ? ref[abs] : 0u;
+                v[q] = inside ? raw[abs] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (!r[q]) continue;
+                const uint64_t p = t0 + threadIdx.x + 1024u * (16 * half + q), abs = b.out_off - r[q];
+                if (abs >= gs) {
+                    if (rt[q] == 0) raw[p] = v[q];
+                    ref[p] = (uint16_t)rt[q];
+                } else {
+                    ref[p] = (uint16_t)(gs - abs);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// part 2: the 32 KiB in front of every group made final, group after group (one CTA; marks there are relative to the start
+// of the group they sit in, their history is the - already final - 32 KiB in front of that group)
+__global__ void __launch_bounds__(1024) pd_tails_chain_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint32_t per, uint8_t *raw,
+                                                              uint16_t *ref) {
+    const uint32_t ng = (n_blocks + per - 1) / per;
+    for (uint32_t g = 1; g + 1 < ng; ++g) {
+        const uint64_t gs = blocks[g * per].out_off, next = blocks[(g + 1) * per].out_off;
+        const uint64_t lo = next > kWindow ? next - kWindow : 0, t0 = lo > gs ? lo : gs;
         uint32_t r[32];
         uint8_t v[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             const uint64_t p = t0 + threadIdx.x + 1024u * q;
-            r[q] = p < end ? ref[p] : 0u;
+            r[q] = p < next ? ref[p] : 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = r[q] ? raw[b.out_off - r[q]] : (uint8_t)0;
+        for (int q = 0; q < 32; ++q) v[q] = r[q] ? raw[gs - r[q]] : (uint8_t)0;
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             const uint64_t p = t0 + threadIdx.x + 1024u * q;
@@ -844,6 +933,21 @@ __global__ void __launch_bounds__(1024) pd_tails_kernel(const Block *__restrict_
             }
         }
         __syncthreads();
+    }
+}
+
+// part 3: the re-based marks in the last 32 KiB of every block (grid.x = blocks; group 0 has none left)
+__global__ void __launch_bounds__(256) pd_tails_finish_kernel(const Block *__restrict__ blocks, uint32_t per, uint8_t *raw, uint16_t *ref) {
+    const Block b = blocks[blockIdx.x];
+    if (blockIdx.x < per || b.tail_marks == 0) return;
+    const uint64_t gs = blocks[(blockIdx.x / per) * per].out_off;
+    const uint64_t end = b.out_off + b.out_len, t0 = b.out_len > kWindow ? end - kWindow : b.out_off;
+    for (uint64_t p = t0 + threadIdx.x; p < end; p += blockDim.x) {
+        const uint32_t r = ref[p];
+        if (r) {
+            raw[p] = raw[gs - r];
+            ref[p] = 0;
+        }
     }
 }
 
@@ -943,21 +1047,25 @@ __global__ void __launch_bounds__(1024) pd_bands_kernel(const uint8_t *__restric
 }
 
 constexpr int kChunkPx = 8;  // pixels a lane reconstructs per step of the wavefront
+constexpr int kFetch = 8;    // chunks of the row above a band a warp fetches (and a band publishes) at a time
 
 // The filters undone: raw (filter byte + filtered bytes per row, stride) -> recon (reconstructed bytes, rows of rstride bytes,
 // rstride a multiple of 4).  A warp per band (taken in image order through a ticket, so that a band only ever waits for a warp
 // that is already running); lane t owns row first + t and works on chunk s - t (8 pixels) at step s: the reconstructed
-// chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it.  Lane 0 of a band that
-// continues a run reads the row above from recon once the band before has published it (progress[band] = chunks of its last
-// row that are final; bounded polling: a wait that does not end raises *bad, it cannot hang).  The filtered bytes of the next
-// chunk are loaded (aligned words + funnel shift) while the current one is computed.
+// chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it.  The first row of a band that
+// continues a run needs the last row of the band before: that band publishes its progress every kFetch chunks
+// (progress[band] = chunks of its last row that are final), this one waits for kFetch chunks at a time and brings them into
+// shared memory with the whole warp - one poll, one fence and one round of loads per kFetch steps instead of per step
+// (bounded polling: a wait that does not end raises *bad, it cannot hang).  The filtered bytes of the next chunk are loaded
+// (aligned words + funnel shift) while the current one is computed.
 template <int BPP>
 __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restrict__ raw, uint8_t *recon, int W, int H, size_t stride, size_t rstride,
                                                           const uint32_t *__restrict__ band_first, const uint32_t *__restrict__ n_bands,
                                                           uint32_t *ticket, uint32_t *progress, int *bad) {
     constexpr int NW = 2 * BPP;            // words per chunk
     constexpr int CB = kChunkPx * BPP;     // bytes per chunk
-    const uint32_t lane = threadIdx.x & 31;
+    __shared__ uint32_t upbuf[8][kFetch * NW];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t k = 0;
     if (lane == 0) k = atomicAdd(ticket, 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
@@ -966,7 +1074,9 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
     const uint32_t bf = band_first[k];
     const int first = (int)(bf & 0x7fffffffu);
     const bool dep = (bf >> 31) != 0;
-    const int last = k + 1 < nb ? (int)(band_first[k + 1] & 0x7fffffffu) : H;
+    const uint32_t bf_next = k + 1 < nb ? band_first[k + 1] : (uint32_t)H;
+    const int last = (int)(bf_next & 0x7fffffffu);
+    const bool next_dep = k + 1 < nb && (bf_next >> 31) != 0;
     const int rows = last - first;  // 1 .. 32
     const bool active = (int)lane < rows;
     const int row = first + (active ? (int)lane : 0);
@@ -984,42 +1094,51 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
 #pragma unroll
     for (int i = 0; i < NW; ++i) cur[i] = outw[i] = 0;
 #pragma unroll
+    for (int i = 0; i <= NW; ++i) nxt[i] = 0;
+#pragma unroll
     for (int i = 0; i < BPP; ++i) left[i] = upleft[i] = 0;
     volatile uint32_t *prog = progress;
     const int steps = nc + rows - 1;
     for (int s = 0; s < steps; ++s) {
         const int j = s - (int)lane;           // this lane's chunk at this step
         const bool on = active && j >= 0 && j < nc;
-        // filtered bytes of chunk j (this step) - loaded one step ahead except for the first
-        if (active && j + 1 >= 0 && j + 1 < nc) {   // prefetch chunk j + 1
-#pragma unroll
-            for (int i = 0; i <= NW; ++i) nxt[i] = __ldg(wbase + (size_t)(j + 1) * NW + i);
+        if (dep && s < nc && (s % kFetch) == 0) {   // (warp-uniform) chunks s .. s + kFetch - 1 of the row above the band
+            const uint32_t need = (uint32_t)min(s + kFetch, nc);
+            uint32_t spins = 0;
+            while (prog[k - 1] < need) {
+                if (++spins > (1u << 22)) {
+                    *bad = 1;
+                    break;
+                }
+            }
+            __threadfence();
+            __syncwarp();   // lane 0 has read the chunks fetched before
+            for (int w = (int)lane; w < kFetch * NW; w += 32) {
+                const int idx = s * NW + w;
+                upbuf[warp][w] = idx < nc * NW ? __ldcg(up_row + idx) : 0u;
+            }
+            __syncwarp();
         }
-        if (on && j == 0) {
-            uint32_t w0[NW + 1];
+        if (on) {
+            if (j == 0) {
+                uint32_t w0[NW + 1];
 #pragma unroll
-            for (int i = 0; i <= NW; ++i) w0[i] = __ldg(wbase + i);
+                for (int i = 0; i <= NW; ++i) w0[i] = __ldg(wbase + i);
 #pragma unroll
-            for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(w0[i], w0[i + 1], sh);
+                for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(w0[i], w0[i + 1], sh);
+            }
+            if (j + 1 < nc) {   // the next chunk's filtered bytes, needed one step from now
+#pragma unroll
+                for (int i = 0; i <= NW; ++i) nxt[i] = __ldg(wbase + (size_t)(j + 1) * NW + i);
+            }
         }
-        // the reconstructed chunk above: from the lane above (its result of the previous step), lane 0 from memory
+        // the reconstructed chunk above: from the lane above (its result of the previous step), lane 0 from the fetched chunks
         uint32_t up[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) up[i] = __shfl_up_sync(0xffffffffu, outw[i], 1);
         if (lane == 0) {
-            const bool need = on && dep;
-            if (need) {
-                uint32_t spins = 0;
-                while (prog[k - 1] <= (uint32_t)j) {
-                    if (++spins > (1u << 24)) {
-                        *bad = 1;
-                        break;
-                    }
-                }
-                __threadfence();
-            }
 #pragma unroll
-            for (int i = 0; i < NW; ++i) up[i] = need ? __ldcg(up_row + (size_t)j * NW + i) : 0u;
+            for (int i = 0; i < NW; ++i) up[i] = (dep && on) ? upbuf[warp][(s % kFetch) * NW + i] : 0u;
         }
         if (on) {
 #pragma unroll
@@ -1044,7 +1163,7 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
             } else {
                 for (int i = 0; i < nbytes; ++i) dst[(size_t)j * CB + i] = (uint8_t)(outw[i >> 2] >> (8 * (i & 3)));
             }
-            if ((int)lane == rows - 1) {   // the band's last row: publish it for the band below
+            if (next_dep && (int)lane == rows - 1 && (((j + 1) % kFetch) == 0 || j == nc - 1)) {   // the band's last row, for the band below
                 __threadfence();
                 prog[k] = (uint32_t)(j + 1);
             }
