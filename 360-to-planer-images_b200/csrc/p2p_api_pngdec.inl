@@ -96,7 +96,6 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     uint64_t *list_d = reinterpret_cast<uint64_t *>(s.pd_tab + L.d_list);
     Cand *cands_d = reinterpret_cast<Cand *>(s.pd_tab + L.d_cands);
     Block *blocks_d = reinterpret_cast<Block *>(s.pd_tab + L.d_blocks);
-    uint32_t *bands_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_bands);
     uint32_t *prog_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_prog);
     Slot::PdCtr *ctr_d = reinterpret_cast<Slot::PdCtr *>(s.pd_tab + L.d_ctr);
     {
@@ -110,7 +109,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         const uint64_t words_scanned = (stream_bits + 31) / 32;
         pd_quick_kernel<<<(unsigned)((words_scanned + 255) / 256), 256, 0, st>>>(s.pd_zs, n_words, 16, stream_bits, list_d, L.cap_list, &ctr_d->n_list);
         pd_full_kernel<<<148 * 8, 128, 0, st>>>(s.pd_zs, n_words, list_d, &ctr_d->n_list, L.cap_list, cands_d, L.cap_cand, &ctr_d->n_cand);
-        pd_measure_kernel<<<148 * 8, kDecodeWarps * 32, 0, st>>>(s.pd_zs, n_words, stream_bits, cands_d, &ctr_d->n_cand, L.cap_cand, I.raw_bytes, I.wsize);
+        pd_measure_kernel<<<148 * 16, 32, 0, st>>>(s.pd_zs, n_words, stream_bits, cands_d, &ctr_d->n_cand, L.cap_cand, I.raw_bytes, I.wsize);
         ctx->launches += 4;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));
@@ -153,8 +152,9 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaSetDevice(ctx->device));
         cudaStream_t st = s.stream;
         CK(cudaMemcpyAsync(blocks_d, blocks_h, (size_t)nb * sizeof(Block), cudaMemcpyHostToDevice, st));
-        pd_decode_kernel<<<(nb + kDecodeWarps - 1) / kDecodeWarps, kDecodeWarps * 32, 0, st>>>(s.pd_zs, n_words, stream_bits, blocks_d, nb, s.pd_raw,
-                                                                                           s.pd_ref, I.raw_bytes, I.wsize, &ctr_d->bad);
+        CK(cudaMemsetAsync(s.pd_ref, 0, I.raw_bytes * sizeof(uint16_t), st));   // no history marks yet
+        pd_decode_kernel<<<(nb + kDecoders - 1) / kDecoders, 32, 0, st>>>(s.pd_zs, n_words, stream_bits, blocks_d, nb, s.pd_raw, s.pd_ref, I.raw_bytes,
+                                                                         I.wsize, &ctr_d->bad);
         const uint32_t per = group_size(nb);
         pd_tails_group_kernel<<<(nb + per - 1) / per, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
         pd_tails_chain_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
@@ -165,17 +165,16 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         uint8_t *recon = reinterpret_cast<uint8_t *>(s.pd_ref);
         const size_t rstride = (I.row_bytes + 3) & ~(size_t)3;
         CK(cudaMemsetAsync(prog_d, 0, ((size_t)I.H + 1) * sizeof(uint32_t), st));
-        pd_bands_kernel<<<1, 1024, 0, st>>>(s.pd_raw, I.H, stride, bands_d, &ctr_d->n_runs, &ctr_d->bad);
-        const unsigned ugrid = (unsigned)((I.H + 7) / 8);
+        const unsigned ugrid = (unsigned)(((I.H + 31) / 32 + 7) / 8);   // a warp per band of 32 rows
         uint32_t *ticket = prog_d + I.H;
         switch (I.bpp) {
-            case 1: pd_unfilter_kernel<1><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
-            case 2: pd_unfilter_kernel<2><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
-            case 3: pd_unfilter_kernel<3><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
-            default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, bands_d, &ctr_d->n_runs, ticket, prog_d, &ctr_d->bad); break;
+            case 1: pd_unfilter_kernel<1><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
+            case 2: pd_unfilter_kernel<2><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
+            case 3: pd_unfilter_kernel<3><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
+            default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
         }
         pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
-        ctx->launches += 9;
+        ctx->launches += 8;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));
         s.valid = false;  // the staging image changed under whatever panorama the slot held

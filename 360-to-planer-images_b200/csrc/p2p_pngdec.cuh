@@ -25,9 +25,9 @@
 //      at a final byte and pd_resolve_kernel finishes the image in one parallel pass.
 //   5. Adler-32 of the inflated data and CRC-32 of every chunk are checked (pd_adler_kernel, pd_crc_kernel + host fold):
 //      a file libpng would refuse is never decoded differently - it is declined and read by cv2.imread as before.
-//   6. pd_runs_kernel / pd_unfilter_kernel undo the scanline filters in place.  Rows with filter None / Sub do not depend
-//      on the row above and start independent runs; inside a run 32 rows advance as a skewed wavefront in one warp (lane t
-//      is one pixel behind lane t - 1 and receives the pixel above through a shuffle), bands of 32 rows follow one another.
+//   6. pd_unfilter_kernel undoes the scanline filters: a warp per band of 32 rows, lane t one 8-pixel chunk behind lane
+//      t - 1 (a skewed wavefront: the reconstructed pixels above arrive through shuffles); a band whose first row needs the
+//      row above waits for the band before it (progress flags, 16 chunks at a time); rows filtered None / Sub need nothing.
 //   7. pd_bgr_kernel writes the BGR staging image (RGB / RGBA / gray / gray + alpha, 8 bit: what cv2.imread(path) with its
 //      default flag IMREAD_COLOR returns for them), which the usual pack kernel turns into the packed panorama.
 //
@@ -120,19 +120,29 @@ PD_HD int cl_order(int i) {
     return i < 12 ? (int)((lo >> (5 * i)) & 31) : (int)((hi >> (5 * (i - 12))) & 31);
 }
 
+PD_HD int popc64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
 // the first test of a candidate block start: header fields and the Kraft sum of the code-length code (inflate.c: LENLENS
-// builds it with type CODES, for which inftrees.c accepts complete codes only)
+// builds it with type CODES, for which inftrees.c accepts complete codes only).  The up to 19 three-bit lengths are counted
+// per value with bit planes and population counts instead of a loop: sum over the lengths l > 0 of 2^(7 - l) must be 128.
 PD_HD bool quick_check(uint64_t head, uint64_t lens3) {
     if (((head >> 1) & 3) != 2) return false;
     if (((head >> 3) & 31) > 29 || ((head >> 8) & 31) > 29) return false;  // more than 286 / 30 codes
     const int ncode = (int)((head >> 13) & 15) + 4;
-    int left = 128;
-#pragma unroll
-    for (int i = 0; i < 19; ++i) {
-        const int l = (int)((lens3 >> (3 * i)) & 7);
-        if (i < ncode && l) left -= 128 >> l;
-    }
-    return left == 0;
+    const uint64_t R = 0x0249249249249249ull;                // bit 0 of each of the 19 fields
+    const uint64_t m = lens3 & ((1ull << (3 * ncode)) - 1ull);
+    const uint64_t b0 = m & R, b1 = (m >> 1) & R, b2 = (m >> 2) & R;
+    const uint64_t n0 = b0 ^ R, n1 = b1 ^ R, n2 = b2 ^ R;
+    const uint64_t lo = n2 & n1, l2 = n2 & b1, l4 = b2 & n1, l6 = b2 & b1;
+    const int sum = 64 * popc64(lo & b0) + 32 * popc64(l2 & n0) + 16 * popc64(l2 & b0) + 8 * popc64(l4 & n0) + 4 * popc64(l4 & b0) +
+                    2 * popc64(l6 & n0) + popc64(l6 & b0);
+    return sum == 128;
 }
 
 // inftrees.c's test of a set of code lengths (type LENS / DISTS): over-subscribed sets are invalid, incomplete ones too
@@ -302,8 +312,8 @@ struct BlockOut {
 };
 
 // One deflate block starting at start_bit.  WRITE = false: only measured (where it ends, how many bytes it produces).
-// WRITE = true: bytes go to raw[out_off ..], and ref[] holds for every byte 0 (final) or k = 1 .. 32768 (the byte k
-// positions in front of this block's first byte, not known yet).  out_cap: size of the whole inflated image; wsize: window
+// WRITE = true: bytes go to raw[out_off ..], and ref[] (all zeros before the pass) receives for every byte that is not
+// known yet k = 1 .. 32768: it equals the byte k positions in front of this block's first byte.  out_cap: size of the whole inflated image; wsize: window
 // of the zlib header.  Distances beyond the data produced so far are invalid ("invalid distance too far back").
 // expect_len (WRITE): the length the block was measured with, which says where its last 32 KiB begin.
 template <bool WRITE>
@@ -331,10 +341,7 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
         if (WRITE) {
             if (out_off + len > out_cap) return PD_BAD;
             const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + byte0;
-            for (uint32_t i = 0; i < len; ++i) {
-                raw[out_off + i] = src[i];
-                ref[out_off + i] = 0;
-            }
+            for (uint32_t i = 0; i < len; ++i) raw[out_off + i] = src[i];
         }
         R.end_bit = (byte0 + len) * 8;
         R.out_len = len;
@@ -360,10 +367,7 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
         if (s < 0) return PD_BAD;
         if (s < 256) {
             if (o >= room) return PD_BAD;
-            if (WRITE) {
-                raw[out_off + o] = (uint8_t)s;
-                ref[out_off + o] = 0;
-            }
+            if (WRITE) raw[out_off + o] = (uint8_t)s;
             ++o;
             continue;
         }
@@ -398,13 +402,14 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
                 uint16_t r;
                 if (src < 0) {
                     r = (uint16_t)(-src);
-                    raw[at + i] = 0;
                 } else {
                     raw[at + i] = raw[out_off + src];
                     r = ref[out_off + src];
                 }
-                ref[at + i] = r;
-                marks += (r != 0 && o + i >= tail_from);
+                if (r) {
+                    ref[at + i] = r;
+                    marks += (o + i >= tail_from);
+                }
             }
         }
         o += len;
@@ -823,46 +828,42 @@ __global__ void __launch_bounds__(128) pd_full_kernel(const uint32_t *__restrict
     }
 }
 
-constexpr int kDecodeWarps = 8;  // warps (= blocks of the stream being decoded) per CTA: 8 x 3264 bytes of tables
+constexpr int kDecoders = 8;  // deflate blocks decoded side by side in one warp (lanes 0 .. 7): 8 x 3264 bytes of tables per CTA
 
-// every candidate decoded to its end-of-block symbol, nothing written: a warp per candidate (lane 0 decodes: the chain of
-// dependent table look-ups is the whole cost, the other lanes would only wait)
-__global__ void __launch_bounds__(kDecodeWarps * 32, 4) pd_measure_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
-                                                                        Cand *__restrict__ cands, const uint32_t *__restrict__ n_cands, uint32_t cap,
-                                                                        uint64_t out_cap, uint32_t wsize) {
-    __shared__ Tables tabs[kDecodeWarps];
+// Every candidate decoded to its end-of-block symbol, nothing written.  One thread per candidate - the chain of dependent
+// table look-ups of a Huffman decoder cannot be spread over lanes - and eight of them per warp, each with its tables in
+// shared memory: a warp with a single decoding lane spends the same issue slots as one with eight, and with thousands of
+// blocks in flight the issue slots, not the latency, bound the pass (measured: one lane per warp 6.0 ms per 8K file).
+__global__ void __launch_bounds__(32) pd_measure_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
+                                                        Cand *__restrict__ cands, const uint32_t *__restrict__ n_cands, uint32_t cap,
+                                                        uint64_t out_cap, uint32_t wsize) {
+    __shared__ Tables tabs[kDecoders];
     const uint32_t n = min(*n_cands, cap);
-    const uint32_t warp = threadIdx.x >> 5;
-    for (uint32_t i = blockIdx.x * kDecodeWarps + warp; i < n; i += gridDim.x * kDecodeWarps) {
-        if ((threadIdx.x & 31) == 0) {
-            uint8_t lens[320];
-            BlockOut R{0, 0, 0};
-            const int rc = decode_block<false>(zs, n_words, stream_bits, cands[i].bit, tabs[warp], lens, nullptr, nullptr, 0, out_cap, wsize, R);
-            cands[i].end_bit = R.end_bit;
-            cands[i].out_len = R.out_len;
-            cands[i].status = rc ? rc : (R.final_block << 8);
-        }
-        __syncwarp();
+    if (threadIdx.x >= kDecoders) return;
+    for (uint32_t i = blockIdx.x * kDecoders + threadIdx.x; i < n; i += gridDim.x * kDecoders) {
+        uint8_t lens[320];
+        BlockOut R{0, 0, 0, 0};
+        const int rc = decode_block<false>(zs, n_words, stream_bits, cands[i].bit, tabs[threadIdx.x], lens, nullptr, nullptr, 0, out_cap, wsize, R);
+        cands[i].end_bit = R.end_bit;
+        cands[i].out_len = R.out_len;
+        cands[i].status = rc ? rc : (R.final_block << 8);
     }
 }
 
-// the blocks of the chain decoded with symbolic history (ref[]); any failure raises *bad
-__global__ void __launch_bounds__(kDecodeWarps * 32, 4) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
-                                                                       Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw,
-                                                                       uint16_t *ref, uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
-    __shared__ Tables tabs[kDecodeWarps];
-    const uint32_t warp = threadIdx.x >> 5;
-    for (uint32_t i = blockIdx.x * kDecodeWarps + warp; i < n_blocks; i += gridDim.x * kDecodeWarps) {
-        if ((threadIdx.x & 31) == 0) {
-            uint8_t lens[320];
-            BlockOut R{0, 0, 0};
-            const Block b = blocks[i];
-            const int rc = decode_block<true>(zs, n_words, stream_bits, b.bit, tabs[warp], lens, raw, ref, b.out_off, out_cap, wsize, R, b.out_len);
-            if (rc || R.out_len != b.out_len) *bad = 1;
-            blocks[i].tail_marks = R.tail_marks;
-        }
-        __syncwarp();
-    }
+// the blocks of the chain decoded with symbolic history (ref[] holds zeros when the kernel starts); any failure raises *bad
+__global__ void __launch_bounds__(32) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
+                                                       Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw, uint16_t *ref,
+                                                       uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
+    __shared__ Tables tabs[kDecoders];
+    if (threadIdx.x >= kDecoders) return;
+    const uint32_t i = blockIdx.x * kDecoders + threadIdx.x;
+    if (i >= n_blocks) return;
+    uint8_t lens[320];
+    BlockOut R{0, 0, 0, 0};
+    const Block b = blocks[i];
+    const int rc = decode_block<true>(zs, n_words, stream_bits, b.bit, tabs[threadIdx.x], lens, raw, ref, b.out_off, out_cap, wsize, R, b.out_len);
+    if (rc || R.out_len != b.out_len) *bad = 1;
+    blocks[i].tail_marks = R.tail_marks;
 }
 
 // Tail pass, part 1: a CTA per group of `per` consecutive blocks walks its blocks in order (tail_step; 1024 threads = 32
@@ -1015,52 +1016,30 @@ __global__ void __launch_bounds__(128) pd_crc_kernel(const uint8_t *__restrict__
     segs[i].crc = ~crc;
 }
 
-// Bands of the unfilter wavefront, in order: a band starts at row 0, at every row filtered None / Sub (it does not depend on
-// the row above: an independent run starts) and at every multiple of 32 rows.  band_first[k] = first row | depends on the band
-// before << 31.  A filter type above 4 raises *bad.
-__global__ void __launch_bounds__(1024) pd_bands_kernel(const uint8_t *__restrict__ raw, int H, size_t stride, uint32_t *__restrict__ band_first,
-                                                        uint32_t *__restrict__ n_bands, int *__restrict__ bad) {
-    __shared__ uint32_t s[1024];
-    const int per = (H + 1023) / 1024;
-    const int r0 = threadIdx.x * per, r1 = min(H, r0 + per);
-    uint32_t mine = 0;
-    for (int r = r0; r < r1; ++r) {
-        const uint32_t ft = raw[(size_t)r * stride];
-        if (ft > 4) *bad = 1;
-        mine += (r == 0 || ft <= 1 || (r & 31) == 0);
-    }
-    s[threadIdx.x] = mine;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        const uint32_t v = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
-        __syncthreads();
-        s[threadIdx.x] += v;
-        __syncthreads();
-    }
-    uint32_t at = s[threadIdx.x] - mine;
-    for (int r = r0; r < r1; ++r) {
-        const uint32_t ft = raw[(size_t)r * stride];
-        const bool indep = (r == 0 || ft <= 1);
-        if (indep || (r & 31) == 0) band_first[at++] = (uint32_t)r | (indep ? 0u : 0x80000000u);
-    }
-    if (threadIdx.x == 1023) *n_bands = s[1023];
+constexpr int kChunkPx = 8;  // pixels a lane reconstructs per step of the wavefront
+constexpr int kFetch = 16;   // chunks of the row above a band a warp fetches (and a band publishes) at a time
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int kChunkPx = 8;  // pixels a lane reconstructs per step of the wavefront
-constexpr int kFetch = 8;    // chunks of the row above a band a warp fetches (and a band publishes) at a time
-
 // The filters undone: raw (filter byte + filtered bytes per row, stride) -> recon (reconstructed bytes, rows of rstride bytes,
-// rstride a multiple of 4).  A warp per band (taken in image order through a ticket, so that a band only ever waits for a warp
-// that is already running); lane t owns row first + t and works on chunk s - t (8 pixels) at step s: the reconstructed
-// chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it.  The first row of a band that
-// continues a run needs the last row of the band before: that band publishes its progress every kFetch chunks
-// (progress[band] = chunks of its last row that are final), this one waits for kFetch chunks at a time and brings them into
-// shared memory with the whole warp - one poll, one fence and one round of loads per kFetch steps instead of per step
-// (bounded polling: a wait that does not end raises *bad, it cannot hang).  The filtered bytes of the next chunk are loaded
-// (aligned words + funnel shift) while the current one is computed.
+// rstride a multiple of 4).  A warp per BAND of 32 rows (taken in image order through a ticket, so that a band only ever waits
+// for a warp that is already running); lane t owns row 32 k + t and works on chunk s - t (8 pixels) at step s: the
+// reconstructed chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it (rows filtered
+// None / Sub ignore it - a file of such rows, like everything cv2.imwrite produces, is 32 independent rows per warp).  If
+// the first row of a band needs the row above (filter Up / Average / Paeth), that is the last row of the band before: that
+// band publishes its progress every kFetch chunks (progress[band] = chunks of its last row that are final, release store),
+// this one waits for kFetch chunks at a time (acquire load; bounded polling: a wait that does not end raises *bad, it
+// cannot hang) and brings them into shared memory with the whole warp.  The filtered bytes of the next chunk are loaded
+// (aligned words + funnel shift) while the current one is computed.  A filter type above 4 raises *bad.
 template <int BPP>
 __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restrict__ raw, uint8_t *recon, int W, int H, size_t stride, size_t rstride,
-                                                          const uint32_t *__restrict__ band_first, const uint32_t *__restrict__ n_bands,
                                                           uint32_t *ticket, uint32_t *progress, int *bad) {
     constexpr int NW = 2 * BPP;            // words per chunk
     constexpr int CB = kChunkPx * BPP;     // bytes per chunk
@@ -1069,21 +1048,18 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
     uint32_t k = 0;
     if (lane == 0) k = atomicAdd(ticket, 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
-    const uint32_t nb = *n_bands;
-    if (k >= nb) return;
-    const uint32_t bf = band_first[k];
-    const int first = (int)(bf & 0x7fffffffu);
-    const bool dep = (bf >> 31) != 0;
-    const uint32_t bf_next = k + 1 < nb ? band_first[k + 1] : (uint32_t)H;
-    const int last = (int)(bf_next & 0x7fffffffu);
-    const bool next_dep = k + 1 < nb && (bf_next >> 31) != 0;
-    const int rows = last - first;  // 1 .. 32
+    const int first = (int)k * 32;
+    if (first >= H) return;
+    const int rows = min(32, H - first);
     const bool active = (int)lane < rows;
     const int row = first + (active ? (int)lane : 0);
     const uint8_t *src = raw + (size_t)row * stride;
     uint8_t *dst = recon + (size_t)row * rstride;
     const uint32_t *up_row = reinterpret_cast<const uint32_t *>(recon + (size_t)(first > 0 ? first - 1 : 0) * rstride);
     const uint32_t ft = active ? src[0] : 0u;
+    if (ft > 4) *bad = 1;
+    const bool dep = first > 0 && __shfl_sync(0xffffffffu, ft, 0) > 1;                   // this band's first row needs the band above
+    const bool next_dep = first + 32 < H && raw[(size_t)(first + 32) * stride] > 1;    // the band below needs this band's last row
     const int row_bytes = W * BPP;
     const int nc = (W + kChunkPx - 1) / kChunkPx;
     // aligned words under this row's filtered bytes
@@ -1097,7 +1073,6 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
     for (int i = 0; i <= NW; ++i) nxt[i] = 0;
 #pragma unroll
     for (int i = 0; i < BPP; ++i) left[i] = upleft[i] = 0;
-    volatile uint32_t *prog = progress;
     const int steps = nc + rows - 1;
     for (int s = 0; s < steps; ++s) {
         const int j = s - (int)lane;           // this lane's chunk at this step
@@ -1105,13 +1080,12 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
         if (dep && s < nc && (s % kFetch) == 0) {   // (warp-uniform) chunks s .. s + kFetch - 1 of the row above the band
             const uint32_t need = (uint32_t)min(s + kFetch, nc);
             uint32_t spins = 0;
-            while (prog[k - 1] < need) {
+            while (ld_acquire_u32(progress + (k - 1)) < need) {
                 if (++spins > (1u << 22)) {
                     *bad = 1;
                     break;
                 }
             }
-            __threadfence();
             __syncwarp();   // lane 0 has read the chunks fetched before
             for (int w = (int)lane; w < kFetch * NW; w += 32) {
                 const int idx = s * NW + w;
@@ -1163,10 +1137,8 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
             } else {
                 for (int i = 0; i < nbytes; ++i) dst[(size_t)j * CB + i] = (uint8_t)(outw[i >> 2] >> (8 * (i & 3)));
             }
-            if (next_dep && (int)lane == rows - 1 && (((j + 1) % kFetch) == 0 || j == nc - 1)) {   // the band's last row, for the band below
-                __threadfence();
-                prog[k] = (uint32_t)(j + 1);
-            }
+            if (next_dep && (int)lane == rows - 1 && (((j + 1) % kFetch) == 0 || j == nc - 1))   // the band's last row, for the band below
+                st_release_u32(progress + k, (uint32_t)(j + 1));
 #pragma unroll
             for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(nxt[i], nxt[i + 1], sh);
         }
