@@ -46,6 +46,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace p2ppdec {
@@ -311,23 +312,13 @@ struct BlockOut {
     uint32_t tail_marks;  // WRITE: history marks left in the block's last 32 KiB (0: pd_tails_kernel has nothing to do here)
 };
 
-// One deflate block starting at start_bit.  WRITE = false: only measured (where it ends, how many bytes it produces).
-// WRITE = true: bytes go to raw[out_off ..], and ref[] (all zeros before the pass) receives for every byte that is not
-// known yet k = 1 .. 32768: it equals the byte k positions in front of this block's first byte.  out_cap: size of the whole inflated image; wsize: window
-// of the zlib header.  Distances beyond the data produced so far are invalid ("invalid distance too far back").
-// expect_len (WRITE): the length the block was measured with, which says where its last 32 KiB begin.
-template <bool WRITE>
-PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bits, uint64_t start_bit, Tables &T,
-                       uint8_t *lens, uint8_t *raw, uint16_t *ref, uint64_t out_off, uint64_t out_cap, uint32_t wsize,
-                       BlockOut &R, uint32_t expect_len = 0) {
-    const uint64_t tail_from = expect_len > kWindow ? expect_len - kWindow : 0;
-    uint32_t marks = 0;
-    R.tail_marks = 0;
-    Bits br;
-    br.init(zs, n_words, start_bit);
-    R.final_block = (int)br.get(1);
+// Header of the block br stands on: its three type bits, then either the length of a stored block (type 0: *stored_len
+// bytes starting at byte *stored_byte0 of the stream) or the decoding tables (fixed or dynamic codes).
+PD_HD int block_begin(Bits &br, uint64_t stream_bits, Tables &T, uint8_t *lens, int *final_block, int *type_out, uint32_t *stored_len,
+                      uint64_t *stored_byte0) {
+    *final_block = (int)br.get(1);
     const int type = (int)br.get(2);
-    uint64_t o = 0;  // bytes produced by this block
+    *type_out = type;
     if (type == 3) return PD_BAD;
     if (type == 0) {
         br.drop((int)((0 - br.pos()) & 7));
@@ -338,13 +329,8 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
         if ((len ^ 0xFFFFu) != nlen) return PD_BAD;
         const uint64_t byte0 = br.pos() >> 3;
         if ((byte0 + len) * 8 > stream_bits) return PD_BAD;
-        if (WRITE) {
-            if (out_off + len > out_cap) return PD_BAD;
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + byte0;
-            for (uint32_t i = 0; i < len; ++i) raw[out_off + i] = src[i];
-        }
-        R.end_bit = (byte0 + len) * 8;
-        R.out_len = len;
+        *stored_len = len;
+        *stored_byte0 = byte0;
         return PD_OK;
     }
     int nlen = 288, ndist = 32;
@@ -359,39 +345,81 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
     }
     if (build_code(lens, nlen, T.lt, kLBits, T.lcnt, T.lsym)) return PD_BAD;
     if (build_code(lens + nlen, ndist, T.dt, kDBits, T.dcnt, T.dsym)) return PD_BAD;
+    return PD_OK;
+}
+
+// Next token of a Huffman-coded block: 0 = literal (*len = the byte), 1 = match (*len, *dist), 2 = end of block,
+// -1 = a code or symbol inflate rejects
+PD_HD int next_token(Bits &br, const Tables &T, uint32_t *len, uint32_t *dist) {
+    br.refill();
+    const int s = decode_sym(br, T.lt, kLBits, T.lcnt, T.lsym);
+    if (s < 0) return -1;
+    if (s < 256) {
+        *len = (uint32_t)s;
+        return 0;
+    }
+    if (s == 256) return 2;
+    if (s > 285) return -1;
+    const int idx = s - 257;
+    if (idx < 8) *len = 3 + idx;
+    else if (idx == 28) *len = 258;
+    else {
+        const int e = (idx >> 2) - 1;
+        *len = 3 + ((4 + (idx & 3)) << e) + br.get(e);
+    }
+    br.refill();
+    const int d = decode_sym(br, T.dt, kDBits, T.dcnt, T.dsym);
+    if (d < 0 || d > 29) return -1;
+    if (d < 4) *dist = 1 + d;
+    else {
+        const int e = (d >> 1) - 1;
+        *dist = 1 + ((2 + (d & 1)) << e) + br.get(e);
+    }
+    return 1;
+}
+
+// One deflate block starting at start_bit.  WRITE = false: only measured (where it ends, how many bytes it produces).
+// WRITE = true: bytes go to raw[out_off ..], and ref[] (all zeros before the pass) receives for every byte that is not
+// known yet k = 1 .. 32768: it equals the byte k positions in front of this block's first byte.  out_cap: size of the whole
+// inflated image; wsize: window of the zlib header.  Distances beyond the data produced so far are invalid ("invalid
+// distance too far back").  expect_len (WRITE): the length the block was measured with, which says where its last 32 KiB begin.
+template <bool WRITE>
+PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bits, uint64_t start_bit, Tables &T,
+                       uint8_t *lens, uint8_t *raw, uint16_t *ref, uint64_t out_off, uint64_t out_cap, uint32_t wsize,
+                       BlockOut &R, uint32_t expect_len = 0) {
+    const uint64_t tail_from = expect_len > kWindow ? expect_len - kWindow : 0;
+    uint32_t marks = 0;
+    R.tail_marks = 0;
+    Bits br;
+    br.init(zs, n_words, start_bit);
+    int type;
+    uint32_t slen = 0;
+    uint64_t byte0 = 0;
+    if (block_begin(br, stream_bits, T, lens, &R.final_block, &type, &slen, &byte0)) return PD_BAD;
+    uint64_t o = 0;  // bytes produced by this block
+    if (type == 0) {
+        if (WRITE) {
+            if (out_off + slen > out_cap) return PD_BAD;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + byte0;
+            for (uint32_t i = 0; i < slen; ++i) raw[out_off + i] = src[i];
+        }
+        R.end_bit = (byte0 + slen) * 8;
+        R.out_len = slen;
+        return PD_OK;
+    }
     const uint64_t room = out_cap > out_off ? out_cap - out_off : 0;
     for (uint32_t n = 0;; ++n) {
         if (n >= kMaxSyms) return PD_LONG;
-        br.refill();
-        const int s = decode_sym(br, T.lt, kLBits, T.lcnt, T.lsym);
-        if (s < 0) return PD_BAD;
-        if (s < 256) {
+        uint32_t len = 0, dist = 0;
+        const int k = next_token(br, T, &len, &dist);
+        if (k < 0) return PD_BAD;
+        if (k == 0) {
             if (o >= room) return PD_BAD;
-            if (WRITE) raw[out_off + o] = (uint8_t)s;
+            if (WRITE) raw[out_off + o] = (uint8_t)len;
             ++o;
             continue;
         }
-        if (s == 256) break;
-        if (s > 285) return PD_BAD;
-        uint32_t len;
-        {
-            const int idx = s - 257;
-            if (idx < 8) len = 3 + idx;
-            else if (idx == 28) len = 258;
-            else {
-                const int e = (idx >> 2) - 1;
-                len = 3 + ((4 + (idx & 3)) << e) + br.get(e);
-            }
-        }
-        br.refill();
-        const int d = decode_sym(br, T.dt, kDBits, T.dcnt, T.dsym);
-        if (d < 0 || d > 29) return PD_BAD;
-        uint32_t dist;
-        if (d < 4) dist = 1 + d;
-        else {
-            const int e = (d >> 1) - 1;
-            dist = 1 + ((2 + (d & 1)) << e) + br.get(e);
-        }
+        if (k == 2) break;
         if (dist > wsize) return PD_BAD;
         if (o + len > room) return PD_BAD;
         if (WRITE) {
@@ -424,15 +452,18 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
 // ---- scanline filters (PNG specification 9.2; libpng png_read_filter_row) -------------------------------------------
 // reconstructed byte from the filtered byte f, filter type ft and the reconstructed neighbours a (left), b (above),
 // c (above left)
-PD_HD uint32_t unfilter_byte(uint32_t ft, uint32_t f, uint32_t a, uint32_t b, uint32_t c) {
-    const int p = (int)a + (int)b - (int)c;
-    int pa = p - (int)a, pb = p - (int)b, pc = p - (int)c;
-    pa = pa < 0 ? -pa : pa;
-    pb = pb < 0 ? -pb : pb;
-    pc = pc < 0 ? -pc : pc;
-    const uint32_t paeth = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-    const uint32_t pred = ft == 0 ? 0u : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth;
+// (m1 .. m4: all-ones for the row's filter type 1 .. 4, else zero - every predictor is evaluated and masked, so that the
+// lanes of a warp, whose rows have different filters, run one instruction stream without branches)
+PD_HD uint32_t unfilter_byte_masked(uint32_t f, uint32_t a, uint32_t b, uint32_t c, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4) {
+    const int da = (int)b - (int)c, db = (int)a - (int)c, dc = da + db;
+    const int pa = da < 0 ? -da : da, pb = db < 0 ? -db : db, pc = dc < 0 ? -dc : dc;
+    const uint32_t bc = (pb <= pc) ? b : c;
+    const uint32_t paeth = ((pa <= pb) & (pa <= pc)) ? a : bc;
+    const uint32_t pred = (a & m1) | (b & m2) | (((a + b) >> 1) & m3) | (paeth & m4);
     return (f + pred) & 255u;
+}
+PD_HD uint32_t unfilter_byte(uint32_t ft, uint32_t f, uint32_t a, uint32_t b, uint32_t c) {
+    return unfilter_byte_masked(f, a, b, c, ft == 1 ? ~0u : 0u, ft == 2 ? ~0u : 0u, ft == 3 ? ~0u : 0u, ft >= 4 ? ~0u : 0u);
 }
 
 // BGR triple of one reconstructed pixel (cv2.imread(path), flag IMREAD_COLOR: gray replicated, alpha dropped)
@@ -603,7 +634,24 @@ inline int parse_png(const uint8_t *f, size_t len, Parsed &P) {
 // the concatenated zlib stream, zero padded to whole words plus slack (dst holds stream_words(P) * 4 bytes)
 inline size_t stream_words(const Parsed &P) { return (P.info.stream_len + 3) / 4 + 8; }
 inline void gather_stream(const uint8_t *f, const Parsed &P, uint8_t *dst) {
-    for (const Idat &c : P.idat) memcpy(dst + c.stream_off, f + c.file_off, c.len);
+    const size_t n = P.idat.size(), total = P.info.stream_len;
+    const unsigned parts = total >= (8u << 20) ? 4u : 1u;   // a large file is copied by four threads (chunk ranges of equal size)
+    if (parts == 1) {
+        for (const Idat &c : P.idat) memcpy(dst + c.stream_off, f + c.file_off, c.len);
+    } else {
+        std::vector<std::thread> th;
+        size_t i0 = 0;
+        for (unsigned k = 0; k < parts; ++k) {
+            size_t i1 = i0;
+            const size_t until = total / parts * (k + 1);
+            while (i1 < n && (k + 1 == parts || P.idat[i1].stream_off < until)) ++i1;
+            th.emplace_back([&P, f, dst, i0, i1] {
+                for (size_t i = i0; i < i1; ++i) memcpy(dst + P.idat[i].stream_off, f + P.idat[i].file_off, P.idat[i].len);
+            });
+            i0 = i1;
+        }
+        for (std::thread &t : th) t.join();
+    }
     memset(dst + P.info.stream_len, 0, stream_words(P) * 4 - P.info.stream_len);
 }
 
@@ -850,20 +898,120 @@ __global__ void __launch_bounds__(32) pd_measure_kernel(const uint32_t *__restri
     }
 }
 
-// the blocks of the chain decoded with symbolic history (ref[] holds zeros when the kernel starts); any failure raises *bad
+// The blocks of the chain decoded with symbolic history (ref[] holds zeros when the kernel starts); any failure raises *bad.
+// Eight blocks per warp again: lanes 0 .. 7 each decode the tokens of their block (block_begin / next_token) and write
+// their literals; a match is not copied by its lane - lanes in byte-by-byte copy loops of different lengths would hold each
+// other up - but handed to the whole warp: its parameters are broadcast and the 32 lanes copy it together (a match that
+// overlaps its own output repeats its first `dist` bytes, so every byte still reads data that existed before the match).
+// Stored blocks are copied the same way.
 __global__ void __launch_bounds__(32) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
                                                        Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw, uint16_t *ref,
                                                        uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
     __shared__ Tables tabs[kDecoders];
-    if (threadIdx.x >= kDecoders) return;
-    const uint32_t i = blockIdx.x * kDecoders + threadIdx.x;
-    if (i >= n_blocks) return;
-    uint8_t lens[320];
-    BlockOut R{0, 0, 0, 0};
-    const Block b = blocks[i];
-    const int rc = decode_block<true>(zs, n_words, stream_bits, b.bit, tabs[threadIdx.x], lens, raw, ref, b.out_off, out_cap, wsize, R, b.out_len);
-    if (rc || R.out_len != b.out_len) *bad = 1;
-    blocks[i].tail_marks = R.tail_marks;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t i = blockIdx.x * kDecoders + lane;
+    const bool leader = lane < kDecoders && i < n_blocks;
+    const uint32_t tab = lane < kDecoders ? lane : 0;
+    Bits br;
+    uint64_t off = 0, o = 0, room = 0, tail_from = 0, p_src = 0;
+    uint32_t expect = 0, nsym = 0, marks = 0, p_kind = 0, p_len = 0, p_dist = 0;   // p_*: the copy this lane has handed to the warp
+    int state = 1;   // 0 decoding, 1 finished, 2 failed
+    br.init(zs, n_words, 0);
+    if (leader) {
+        const Block b = blocks[i];
+        off = b.out_off;
+        expect = b.out_len;
+        room = out_cap > off ? out_cap - off : 0;
+        tail_from = expect > kWindow ? expect - kWindow : 0;
+        uint8_t lens[320];
+        int fin, type;
+        uint32_t slen = 0;
+        uint64_t byte0 = 0;
+        br.init(zs, n_words, b.bit);
+        state = 0;
+        if (block_begin(br, stream_bits, tabs[tab], lens, &fin, &type, &slen, &byte0)) state = 2;
+        else if (type == 0) {
+            if (slen > room) state = 2;
+            else if (slen == 0) state = 1;
+            else {
+                p_kind = 2;
+                p_len = slen;
+                p_src = byte0;
+            }
+        }
+    }
+    for (;;) {
+        if (state == 0 && p_kind == 0) {   // one token
+            if (nsym++ >= kMaxSyms) state = 2;
+            else {
+                uint32_t len = 0, dist = 0;
+                const int k = next_token(br, tabs[tab], &len, &dist);
+                if (k == 0) {
+                    if (o >= room) state = 2;
+                    else {
+                        raw[off + o] = (uint8_t)len;
+                        ++o;
+                    }
+                } else if (k == 1) {
+                    if (dist > wsize || o + len > room || dist > off + o) state = 2;
+                    else {
+                        p_kind = 1;
+                        p_len = len;
+                        p_dist = dist;
+                    }
+                } else if (k == 2) {
+                    state = (br.pos() <= stream_bits) ? 1 : 2;
+                } else {
+                    state = 2;
+                }
+            }
+        }
+        __syncwarp();
+        unsigned pend = __ballot_sync(0xffffffffu, p_kind != 0);
+        while (pend) {
+            const int d = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const uint32_t kind = __shfl_sync(0xffffffffu, p_kind, d), len = __shfl_sync(0xffffffffu, p_len, d),
+                           dist = __shfl_sync(0xffffffffu, p_dist, d);
+            const uint64_t o_d = __shfl_sync(0xffffffffu, o, d), off_d = __shfl_sync(0xffffffffu, off, d),
+                           tail_d = __shfl_sync(0xffffffffu, tail_from, d), src_d = __shfl_sync(0xffffffffu, p_src, d);
+            uint32_t m = 0;
+            if (kind == 1) {
+                for (uint32_t t = lane; t < len; t += 32) {
+                    const uint32_t tt = dist >= len ? t : t % dist;
+                    const int64_t srel = (int64_t)(o_d + tt) - (int64_t)dist;   // relative to the block's first byte
+                    const uint64_t at = off_d + o_d + t;
+                    uint16_t r;
+                    if (srel < 0) {
+                        r = (uint16_t)(-srel);
+                    } else {
+                        raw[at] = raw[off_d + srel];
+                        r = ref[off_d + srel];
+                    }
+                    if (r) {
+                        ref[at] = r;
+                        m += (o_d + t >= tail_d);
+                    }
+                }
+            } else {
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + src_d;
+                for (uint32_t t = lane; t < len; t += 32) raw[off_d + o_d + t] = src[t];
+            }
+            m = __reduce_add_sync(0xffffffffu, m);
+            if ((int)lane == d) {
+                marks += m;
+                o += len;
+                p_kind = 0;
+                if (kind == 2) state = 1;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, state == 0)) break;
+    }
+    if (leader) {
+        if (state != 1 || o != expect) *bad = 1;
+        blocks[i].tail_marks = marks;
+    }
 }
 
 // Tail pass, part 1: a CTA per group of `per` consecutive blocks walks its blocks in order (tail_step; 1024 threads = 32
@@ -1058,6 +1206,7 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
     const uint32_t *up_row = reinterpret_cast<const uint32_t *>(recon + (size_t)(first > 0 ? first - 1 : 0) * rstride);
     const uint32_t ft = active ? src[0] : 0u;
     if (ft > 4) *bad = 1;
+    const uint32_t m1 = ft == 1 ? ~0u : 0u, m2 = ft == 2 ? ~0u : 0u, m3 = ft == 3 ? ~0u : 0u, m4 = ft >= 4 ? ~0u : 0u;
     const bool dep = first > 0 && __shfl_sync(0xffffffffu, ft, 0) > 1;                   // this band's first row needs the band above
     const bool next_dep = first + 32 < H && raw[(size_t)(first + 32) * stride] > 1;    // the band below needs this band's last row
     const int row_bytes = W * BPP;
@@ -1122,7 +1271,7 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
                     const int byte = px * BPP + c;
                     const uint32_t f = (cur[byte >> 2] >> (8 * (byte & 3))) & 255u;
                     const uint32_t b = (up[byte >> 2] >> (8 * (byte & 3))) & 255u;
-                    const uint32_t v = unfilter_byte(ft, f, left[c], b, upleft[c]);
+                    const uint32_t v = unfilter_byte_masked(f, left[c], b, upleft[c], m1, m2, m3, m4);
                     upleft[c] = b;
                     left[c] = v;
                     if ((byte & 3) == 0) outw[byte >> 2] = v;

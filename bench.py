@@ -427,12 +427,21 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         # the reference's default output format: 34 MB of PNG files per image go back over PCIe instead of 4 MB
         e2e_files["png"] = files_flow(pkg, proj, synth.smooth(WP, HP, rank), shifts, consts, "png", world, barrier, max_over_ranks,
                                       n_img=48)
+        # PNG in, PNG out: the reference's default format on both sides (a second pass over its own outputs); the 8K file
+        # (cv2.imwrite defaults) is inflated and unfiltered on the GPU.  A new leg: a failure is recorded, not fatal.
+        try:
+            e2e_files["png_in"] = files_flow(pkg, proj, synth.smooth(WP, HP, rank), shifts, consts, "png", world, barrier,
+                                             max_over_ranks, n_img=16, n_thr=4, src="png")
+        except Exception as e:  # noqa: BLE001
+            e2e_files["png_in"] = {"error": repr(e)}
+            barrier()
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = files_extras(pkg, proj, synth.smooth(WP, HP, 0), shifts, consts)
         extras["configs"] = config_fractions(pkg, proj, synth, torch)
         extras["fractional_yaw"] = fractional_yaw_times(pkg, proj, synth, torch)
+        extras["png_decode"] = png_decode_times(pkg, proj, synth)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -546,21 +555,21 @@ def oracle_check(proj, pano, seed):
             else "tolerance (host NumPy does not take the SVML path: the reference itself differs in the last ulp here)"}
 
 
-def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=96, n_thr=8):
+def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ranks, n_img=96, n_thr=8, src="jpg"):
     """Files to files on every rank: an 8192x4096 JPEG file in host memory -> the 12 views as files in page-locked host
     memory; Huffman decode, IDCT, projection and encode all on the GPU, n_thr images in flight per rank.  Whole-job
     Mpix/s = all ranks' images / the slowest rank's time."""
     import cv2
     from concurrent.futures import ThreadPoolExecutor
 
-    data = cv2.imencode(".jpg", pano)[1].tobytes()
+    data = cv2.imencode("." + src, pano)[1].tobytes()
     # images in flight per rank = host threads: a waiting thread spins on its stream (the CUDA default), so the ranks of one box
     # share its cores - 8 threads on each of 8 ranks of a 32-vCPU box cost a third of the throughput (profiles/r2_files_flow_*)
     n_thr = max(2, min(n_thr, (os.cpu_count() or 8) // max(1, world)))
 
     def one(_):
         with proj.slots(1) as (s,):
-            proj.upload_jpeg(s, data)
+            proj.upload_encoded(s, data)   # JPEG: Huffman stage + IDCT on the device; PNG: inflate + unfilter on the device
             if fmt == "jpg":
                 files = proj.project_jpeg(s, shifts, consts, W, H, copy=False)
             else:
@@ -574,11 +583,11 @@ def files_flow(pkg, proj, pano, shifts, consts, fmt, world, barrier, max_over_ra
         list(ex.map(one, range(n_img)))
         sec = max_over_ranks(time.perf_counter() - t0)
         barrier()
-    return {"value": world * n_img * PX_PER_IMAGE / sec / 1e6, "unit": UNIT, "format": f"jpg -> {fmt}",
+    return {"value": world * n_img * PX_PER_IMAGE / sec / 1e6, "unit": UNIT, "format": f"{src} -> {fmt}",
             "ms_per_image_per_gpu": sec / n_img * 1e3, "images_per_rank": n_img, "threads_per_rank": n_thr,
             "h2d_bytes_per_image": len(data), "d2h_bytes_per_image": out_bytes,
-            "what": "8192x4096 JPEG file bytes (host) -> 12 x 1920x1080 files (host); decode, projection and encode on the "
-                    "GPU; every rank runs the same flow at once"}
+            "what": f"8192x4096 {src.upper()} file bytes (host) -> 12 x 1920x1080 files (host); decode, projection and encode on "
+                    "the GPU; every rank runs the same flow at once"}
 
 
 def config_fractions(pkg, proj, synth, torch):
@@ -651,6 +660,37 @@ def fractional_yaw_times(pkg, proj, synth, torch):
     return {"yaw": yaw, "views": len(PITCHES), "one_pass_us": statistics.median(one[1:]) * 1e3,
             "rotate_then_project_us": statistics.median(two[1:]) * 1e3, "identical": same,
             "note": "the two-pass figure includes the yaw table upload the rotate entry point waits for"}
+
+
+def png_decode_times(pkg, proj, synth):
+    """Side measurement: an 8192x4096 PNG panorama (cv2.imwrite defaults) into a slot - the device decoder (parallel
+    inflate + unfilter, csrc/p2p_pngdec.cuh) against cv2.imdecode + upload, one host thread, same pixels (checked)."""
+    import cv2
+
+    try:
+        pano = synth.smooth(WP, HP, 3)
+        data = cv2.imencode(".png", pano)[1].tobytes()
+        arr = np.frombuffer(data, np.uint8)
+        with proj.slots(1) as (s,):
+            proj.upload_png(s, data)
+            proj.sync(s)
+            same = bool(np.array_equal(proj.download_pano(s, WP, HP), pano))
+            t_dev, t_cv = [], []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                proj.upload_png(s, data)
+                proj.sync(s)
+                t_dev.append(time.perf_counter() - t0)
+            for _ in range(2):
+                t0 = time.perf_counter()
+                proj.upload(s, cv2.imdecode(arr, cv2.IMREAD_COLOR))
+                proj.sync(s)
+                t_cv.append(time.perf_counter() - t0)
+        return {"what": "8192x4096 PNG file bytes (host) -> packed panorama in a slot, one host thread",
+                "file_bytes": len(data), "same_pixels_as_cv2": same, "device_decoder_ms": min(t_dev) * 1e3,
+                "cv2_imdecode_plus_upload_ms": min(t_cv) * 1e3, "speedup": min(t_cv) / min(t_dev)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def files_extras(pkg, proj, pano, shifts, consts):
