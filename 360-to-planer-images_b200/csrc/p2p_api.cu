@@ -121,6 +121,7 @@ void p2p_destroy(p2p_ctx *ctx) {
         cudaFree(s.pd_tab);
         cudaFree(s.pd_raw);
         cudaFree(s.pd_ref);
+        cudaFree(s.pd_match);
         if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
         if (s.owned) cudaStreamDestroy(s.owned);
     }

@@ -146,15 +146,19 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     P.info.adler = be32(reinterpret_cast<const uint8_t *>(s.pd_zs_h) + I.stream_len - 4);
     memcpy(blocks_h, blocks.data(), blocks.size() * sizeof(Block));
     const uint32_t nb = (uint32_t)blocks.size();
+    const uint64_t n_match_total = blocks.back().match_off + blocks.back().n_matches;
     const size_t stride = 1 + I.row_bytes;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         CK(cudaSetDevice(ctx->device));
         cudaStream_t st = s.stream;
+        const int rc_m = ensure_grow(ctx, &s.pd_match, &s.pd_match_cap, (size_t)(n_match_total + 1) * sizeof(Match));
+        if (rc_m) return rc_m;
         CK(cudaMemcpyAsync(blocks_d, blocks_h, (size_t)nb * sizeof(Block), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(s.pd_ref, 0, I.raw_bytes * sizeof(uint16_t), st));   // no history marks yet
-        pd_decode_kernel<<<(nb + kDecoders - 1) / kDecoders, 32, 0, st>>>(s.pd_zs, n_words, stream_bits, blocks_d, nb, s.pd_raw, s.pd_ref, I.raw_bytes,
+        pd_decode_kernel<<<(nb + kDecoders - 1) / kDecoders, 32, 0, st>>>(s.pd_zs, n_words, stream_bits, blocks_d, nb, s.pd_raw, s.pd_match, I.raw_bytes,
                                                                          I.wsize, &ctr_d->bad);
+        pd_copy_kernel<<<(nb + 7) / 8, 256, 0, st>>>(blocks_d, nb, s.pd_match, s.pd_raw, s.pd_ref);
         const uint32_t per = group_size(nb);
         pd_tails_group_kernel<<<(nb + per - 1) / per, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
         pd_tails_chain_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
@@ -174,7 +178,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
             default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
         }
         pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
-        ctx->launches += 8;
+        ctx->launches += 9;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));
         s.valid = false;  // the staging image changed under whatever panorama the slot held

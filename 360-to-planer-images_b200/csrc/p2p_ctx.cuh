@@ -135,6 +135,8 @@ struct Slot {
     size_t pd_raw_cap = 0;
     uint16_t *pd_ref = nullptr;
     size_t pd_ref_cap = 0;
+    p2ppdec::Match *pd_match = nullptr;       // back-references of all blocks (decode pass -> copy pass)
+    size_t pd_match_cap = 0;
     cudaEvent_t wait_ev = nullptr;            // blocking-sync event of wait_slot
 };
 

@@ -14,9 +14,10 @@
 //      the first block: a block that ends where a measured candidate starts continues there; stored and fixed-Huffman blocks
 //      (no recognisable header) are measured by the same routine on the host when the walk reaches them.  The walk gives
 //      every block its output offset.
-//   3. the blocks of the chain are decoded in parallel (pd_decode_kernel) with SYMBOLIC history: a back-reference that
-//      reaches in front of its own block cannot be resolved yet, so the byte is recorded as "history byte k before my block"
-//      in a 16-bit side array (0 = final byte); copies inside the block copy those marks along.
+//   3. the blocks of the chain are decoded in parallel with SYMBOLIC history.  pd_decode_kernel (eight blocks per warp)
+//      writes the literals and records the back-references; pd_copy_kernel (a warp per block) executes them in order: a
+//      back-reference that reaches in front of its own block cannot be resolved yet, so the byte is recorded as "history
+//      byte k before my block" in a 16-bit side array (0 = final byte); copies inside the block copy those marks along.
 //   4. the last 32 KiB of every block are made final first (all marks of a block point into the 32 KiB in front of it, i.e.
 //      into the last 32 KiB of earlier blocks).  That is a chain through all blocks, cut into ~sqrt(n) GROUPS of consecutive
 //      blocks: pd_tails_group_kernel walks every group on its own SM and re-bases what it cannot resolve inside the group to
@@ -309,7 +310,8 @@ struct BlockOut {
     uint64_t end_bit;
     uint32_t out_len;
     int final_block;
-    uint32_t tail_marks;  // WRITE: history marks left in the block's last 32 KiB (0: pd_tails_kernel has nothing to do here)
+    uint32_t tail_marks;  // WRITE: history marks left in the block's last 32 KiB (0: the tail pass has nothing to do here)
+    uint32_t n_matches;   // back-references in the block
 };
 
 // Header of the block br stands on: its three type bits, then either the length of a stored block (type 0: *stored_len
@@ -388,8 +390,9 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
                        uint8_t *lens, uint8_t *raw, uint16_t *ref, uint64_t out_off, uint64_t out_cap, uint32_t wsize,
                        BlockOut &R, uint32_t expect_len = 0) {
     const uint64_t tail_from = expect_len > kWindow ? expect_len - kWindow : 0;
-    uint32_t marks = 0;
+    uint32_t marks = 0, n_matches = 0;
     R.tail_marks = 0;
+    R.n_matches = 0;
     Bits br;
     br.init(zs, n_words, start_bit);
     int type;
@@ -420,6 +423,7 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
             continue;
         }
         if (k == 2) break;
+        ++n_matches;
         if (dist > wsize) return PD_BAD;
         if (o + len > room) return PD_BAD;
         if (WRITE) {
@@ -446,6 +450,7 @@ PD_HD int decode_block(const uint32_t *zs, uint64_t n_words, uint64_t stream_bit
     if (R.end_bit > stream_bits) return PD_BAD;
     R.out_len = (uint32_t)o;
     R.tail_marks = marks;
+    R.n_matches = n_matches;
     return PD_OK;
 }
 
@@ -660,11 +665,18 @@ struct Cand {
     uint64_t bit, end_bit;
     uint32_t out_len;
     int32_t status;  // PD_OK | final << 8, or PD_BAD / PD_LONG
+    uint32_t n_matches, pad;
 };
 struct Block {
     uint64_t bit, out_off;
     uint32_t out_len;
-    uint32_t tail_marks;  // written by the decoding pass
+    uint32_t tail_marks;  // written by the copy pass
+    uint64_t match_off;   // first record of the block in the match list
+    uint32_t n_matches, pad;
+};
+struct Match {            // a back-reference of a block: `len` bytes at offset `o` of the block's output repeat what lies `dist` bytes before
+    uint32_t o;
+    uint16_t len, dist;
 };
 
 // Chain walk (host): from the first block behind the zlib header, through measured candidates where there are any and
@@ -676,31 +688,35 @@ inline int walk_chain(const uint32_t *zs, const Parsed &P, std::vector<Cand> &ca
     const uint64_t n_words = stream_words(P), stream_bits = (uint64_t)(I.stream_len - 4) * 8;  // the Adler-32 is not deflate data
     std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.bit < b.bit; });
     blocks.clear();
-    uint64_t bit = 16, out = 0, spent = 0;
+    uint64_t bit = 16, out = 0, spent = 0, n_match_total = 0;
     Tables T;
     uint8_t lens[320];
     for (;;) {
         if (bit + 3 > stream_bits) return 1;
         auto it = std::lower_bound(cands.begin(), cands.end(), bit, [](const Cand &c, uint64_t b) { return c.bit < b; });
         uint64_t end;
-        uint32_t out_len;
+        uint32_t out_len, n_matches;
         int fin;
         if (it != cands.end() && it->bit == bit) {
             if ((it->status & 255) != PD_OK) return 1;
             end = it->end_bit;
             out_len = it->out_len;
+            n_matches = it->n_matches;
             fin = it->status >> 8;
         } else {
             BlockOut R;
-            if (spent > host_budget) return 1;
+            const bool stored = ((window64(zs, n_words, bit) >> 1) & 3) == 0;   // (a stored block costs nothing to measure)
+            if (!stored && spent > host_budget) return 1;
             if (decode_block<false>(zs, n_words, stream_bits, bit, T, lens, nullptr, nullptr, 0, I.raw_bytes, I.wsize, R)) return 1;
-            spent += R.end_bit - bit;
+            if (!stored) spent += R.end_bit - bit;
             end = R.end_bit;
             out_len = R.out_len;
+            n_matches = R.n_matches;
             fin = R.final_block;
         }
         if (end > stream_bits || out + out_len > I.raw_bytes) return 1;
-        blocks.push_back(Block{bit, out, out_len, 0});
+        blocks.push_back(Block{bit, out, out_len, 0, n_match_total, n_matches, 0});
+        n_match_total += n_matches;
         out += out_len;
         bit = end;
         if (fin) break;
@@ -742,15 +758,16 @@ inline int decode_host_model(const uint8_t *f, size_t len, uint8_t *bgr, size_t 
     for (uint64_t bit = 16; bit + 3 <= stream_bits; ++bit) {
         if (!quick_check(window64(zs, n_words, bit), window64(zs, n_words, bit + 17))) continue;
         ++n_quick;
-        if (full_check(zs, n_words, bit)) cands.push_back(Cand{bit, 0, 0, 0});
+        if (full_check(zs, n_words, bit)) cands.push_back(Cand{bit, 0, 0, 0, 0, 0});
     }
     Tables T;
     uint8_t lens[320];
     for (Cand &c : cands) {
-        BlockOut R{0, 0, 0};
+        BlockOut R{0, 0, 0, 0, 0};
         const int rc = decode_block<false>(zs, n_words, stream_bits, c.bit, T, lens, nullptr, nullptr, 0, I.raw_bytes, I.wsize, R);
         c.end_bit = R.end_bit;
         c.out_len = R.out_len;
+        c.n_matches = R.n_matches;
         c.status = rc ? rc : (R.final_block << 8);
     }
     std::vector<Block> blocks;
@@ -890,128 +907,115 @@ __global__ void __launch_bounds__(32) pd_measure_kernel(const uint32_t *__restri
     if (threadIdx.x >= kDecoders) return;
     for (uint32_t i = blockIdx.x * kDecoders + threadIdx.x; i < n; i += gridDim.x * kDecoders) {
         uint8_t lens[320];
-        BlockOut R{0, 0, 0, 0};
+        BlockOut R{0, 0, 0, 0, 0};
         const int rc = decode_block<false>(zs, n_words, stream_bits, cands[i].bit, tabs[threadIdx.x], lens, nullptr, nullptr, 0, out_cap, wsize, R);
         cands[i].end_bit = R.end_bit;
         cands[i].out_len = R.out_len;
+        cands[i].n_matches = R.n_matches;
         cands[i].status = rc ? rc : (R.final_block << 8);
     }
 }
 
-// The blocks of the chain decoded with symbolic history (ref[] holds zeros when the kernel starts); any failure raises *bad.
-// Eight blocks per warp again: lanes 0 .. 7 each decode the tokens of their block (block_begin / next_token) and write
-// their literals; a match is not copied by its lane - lanes in byte-by-byte copy loops of different lengths would hold each
-// other up - but handed to the whole warp: its parameters are broadcast and the 32 lanes copy it together (a match that
-// overlaps its own output repeats its first `dist` bytes, so every byte still reads data that existed before the match).
-// Stored blocks are copied the same way.
+// The blocks of the chain decoded, part 1: eight blocks per warp again, one lane each.  Literals go straight to raw[]; a
+// back-reference is only RECORDED (block offset, length, distance) in the block's slice of the match list.  Executing it
+// here would make its lane - and with it the seven other decoders of the warp - wait for a read of bytes that were written
+// moments ago and sit in L2 (0.7 us each, measured: 11 ms per 8K file with 10 M matches); the copies are the business of
+// pd_copy_kernel.  Stored blocks are copied here.  Any failure raises *bad.
 __global__ void __launch_bounds__(32) pd_decode_kernel(const uint32_t *__restrict__ zs, uint64_t n_words, uint64_t stream_bits,
-                                                       Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *raw, uint16_t *ref,
-                                                       uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
+                                                       const Block *__restrict__ blocks, uint32_t n_blocks, uint8_t *__restrict__ raw,
+                                                       Match *__restrict__ matches, uint64_t out_cap, uint32_t wsize, int *__restrict__ bad) {
     __shared__ Tables tabs[kDecoders];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t i = blockIdx.x * kDecoders + lane;
-    const bool leader = lane < kDecoders && i < n_blocks;
-    const uint32_t tab = lane < kDecoders ? lane : 0;
+    if (threadIdx.x >= kDecoders) return;
+    const uint32_t i = blockIdx.x * kDecoders + threadIdx.x;
+    if (i >= n_blocks) return;
+    const Block b = blocks[i];
+    const uint64_t room = out_cap > b.out_off ? out_cap - b.out_off : 0;
+    Tables &T = tabs[threadIdx.x];
+    uint8_t lens[320];
     Bits br;
-    uint64_t off = 0, o = 0, room = 0, tail_from = 0, p_src = 0;
-    uint32_t expect = 0, nsym = 0, marks = 0, p_kind = 0, p_len = 0, p_dist = 0;   // p_*: the copy this lane has handed to the warp
-    int state = 1;   // 0 decoding, 1 finished, 2 failed
-    br.init(zs, n_words, 0);
-    if (leader) {
-        const Block b = blocks[i];
-        off = b.out_off;
-        expect = b.out_len;
-        room = out_cap > off ? out_cap - off : 0;
-        tail_from = expect > kWindow ? expect - kWindow : 0;
-        uint8_t lens[320];
-        int fin, type;
-        uint32_t slen = 0;
-        uint64_t byte0 = 0;
-        br.init(zs, n_words, b.bit);
-        state = 0;
-        if (block_begin(br, stream_bits, tabs[tab], lens, &fin, &type, &slen, &byte0)) state = 2;
-        else if (type == 0) {
-            if (slen > room) state = 2;
-            else if (slen == 0) state = 1;
-            else {
-                p_kind = 2;
-                p_len = slen;
-                p_src = byte0;
-            }
+    br.init(zs, n_words, b.bit);
+    int fin, type;
+    uint32_t slen = 0;
+    uint64_t byte0 = 0;
+    if (block_begin(br, stream_bits, T, lens, &fin, &type, &slen, &byte0)) {
+        *bad = 1;
+        return;
+    }
+    uint8_t *out = raw + b.out_off;
+    if (type == 0) {
+        if (slen != b.out_len || slen > room || b.n_matches) {
+            *bad = 1;
+            return;
+        }
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + byte0;
+        for (uint32_t k = 0; k < slen; ++k) out[k] = src[k];
+        return;
+    }
+    Match *list = matches + b.match_off;
+    uint64_t o = 0;
+    uint32_t nm = 0;
+    bool ok = false;
+    for (uint32_t n = 0; n < kMaxSyms; ++n) {
+        uint32_t len = 0, dist = 0;
+        const int k = next_token(br, T, &len, &dist);
+        if (k == 0) {
+            if (o >= room) break;
+            out[o++] = (uint8_t)len;
+        } else if (k == 1) {
+            if (dist > wsize || o + len > room || dist > b.out_off + o || nm >= b.n_matches) break;
+            list[nm++] = Match{(uint32_t)o, (uint16_t)len, (uint16_t)dist};   // (a distance of 32768 fits 16 bits)
+            o += len;
+        } else {
+            ok = (k == 2) && br.pos() <= stream_bits;
+            break;
         }
     }
-    for (;;) {
-        if (state == 0 && p_kind == 0) {   // one token
-            if (nsym++ >= kMaxSyms) state = 2;
-            else {
-                uint32_t len = 0, dist = 0;
-                const int k = next_token(br, tabs[tab], &len, &dist);
-                if (k == 0) {
-                    if (o >= room) state = 2;
-                    else {
-                        raw[off + o] = (uint8_t)len;
-                        ++o;
-                    }
-                } else if (k == 1) {
-                    if (dist > wsize || o + len > room || dist > off + o) state = 2;
-                    else {
-                        p_kind = 1;
-                        p_len = len;
-                        p_dist = dist;
-                    }
-                } else if (k == 2) {
-                    state = (br.pos() <= stream_bits) ? 1 : 2;
+    if (!ok || o != b.out_len || nm != b.n_matches) *bad = 1;
+}
+
+// part 2: the recorded back-references executed, a warp per block, in order.  The lanes copy the bytes of a match together
+// (a match that overlaps its own output repeats its first `dist` bytes, so every byte reads data that existed before the
+// match); a byte whose source lies in front of the block becomes a history mark in ref[] (all zeros before the pass), a
+// copied mark stays a mark.  With thousands of warps in flight the L2 round trip of every match hides behind the other
+// blocks' copies.  Records are fetched 32 at a time.
+__global__ void __launch_bounds__(256) pd_copy_kernel(Block *__restrict__ blocks, uint32_t n_blocks, const Match *__restrict__ matches,
+                                                      uint8_t *raw, uint16_t *ref) {
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n_blocks) return;
+    const Block b = blocks[i];
+    const Match *list = matches + b.match_off;
+    const uint64_t tail_from = b.out_len > kWindow ? b.out_len - kWindow : 0;
+    uint8_t *out = raw + b.out_off;
+    uint16_t *mark = ref + b.out_off;
+    uint32_t marks = 0;
+    for (uint32_t m0 = 0; m0 < b.n_matches; m0 += 32) {
+        const uint32_t cnt = min(32u, b.n_matches - m0);
+        Match mine{0, 0, 1};
+        if (lane < cnt) mine = list[m0 + lane];
+        for (uint32_t q = 0; q < cnt; ++q) {
+            const uint32_t o = __shfl_sync(0xffffffffu, mine.o, q), len = __shfl_sync(0xffffffffu, (uint32_t)mine.len, q);
+            uint32_t dist = __shfl_sync(0xffffffffu, (uint32_t)mine.dist, q);
+            if (dist == 0) dist = 65536u;   // (cannot happen: distances are 1 .. 32768)
+            for (uint32_t t = lane; t < len; t += 32) {
+                const uint32_t tt = dist >= len ? t : t % dist;
+                const int64_t srel = (int64_t)o + tt - (int64_t)dist;   // relative to the block's first byte
+                uint16_t r;
+                if (srel < 0) {
+                    r = (uint16_t)(-srel);
                 } else {
-                    state = 2;
+                    out[o + t] = out[srel];
+                    r = mark[srel];
                 }
-            }
-        }
-        __syncwarp();
-        unsigned pend = __ballot_sync(0xffffffffu, p_kind != 0);
-        while (pend) {
-            const int d = __ffs(pend) - 1;
-            pend &= pend - 1;
-            const uint32_t kind = __shfl_sync(0xffffffffu, p_kind, d), len = __shfl_sync(0xffffffffu, p_len, d),
-                           dist = __shfl_sync(0xffffffffu, p_dist, d);
-            const uint64_t o_d = __shfl_sync(0xffffffffu, o, d), off_d = __shfl_sync(0xffffffffu, off, d),
-                           tail_d = __shfl_sync(0xffffffffu, tail_from, d), src_d = __shfl_sync(0xffffffffu, p_src, d);
-            uint32_t m = 0;
-            if (kind == 1) {
-                for (uint32_t t = lane; t < len; t += 32) {
-                    const uint32_t tt = dist >= len ? t : t % dist;
-                    const int64_t srel = (int64_t)(o_d + tt) - (int64_t)dist;   // relative to the block's first byte
-                    const uint64_t at = off_d + o_d + t;
-                    uint16_t r;
-                    if (srel < 0) {
-                        r = (uint16_t)(-srel);
-                    } else {
-                        raw[at] = raw[off_d + srel];
-                        r = ref[off_d + srel];
-                    }
-                    if (r) {
-                        ref[at] = r;
-                        m += (o_d + t >= tail_d);
-                    }
+                if (r) {
+                    mark[o + t] = r;
+                    marks += (o + t >= tail_from);
                 }
-            } else {
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(zs) + src_d;
-                for (uint32_t t = lane; t < len; t += 32) raw[off_d + o_d + t] = src[t];
-            }
-            m = __reduce_add_sync(0xffffffffu, m);
-            if ((int)lane == d) {
-                marks += m;
-                o += len;
-                p_kind = 0;
-                if (kind == 2) state = 1;
             }
             __syncwarp();
         }
-        if (!__any_sync(0xffffffffu, state == 0)) break;
     }
-    if (leader) {
-        if (state != 1 || o != expect) *bad = 1;
-        blocks[i].tail_marks = marks;
-    }
+    marks = __reduce_add_sync(0xffffffffu, marks);
+    if (lane == 0) blocks[i].tail_marks = marks;
 }
 
 // Tail pass, part 1: a CTA per group of `per` consecutive blocks walks its blocks in order (tail_step; 1024 threads = 32
