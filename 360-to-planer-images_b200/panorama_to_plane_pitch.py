@@ -17,9 +17,9 @@ three f32 *pitch constants* instead of a full-size map (the map itself is evalua
 inside the kernel and never stored).
 
 Views are encoded on the GPU - PNG (``csrc/p2p_png.cuh``) and JPEG (``csrc/p2p_jpeg.cuh``) - byte-identical to what
-``cv2.imwrite`` (ref :277) writes at OpenCV's defaults, so only the files cross PCIe; ``.jpg`` panoramas are decoded on the
-GPU too (``csrc/p2p_jpegdec.cuh``, bit-identical to ``cv2.imread``, ref :244).  cv2 remains for PNG input files and for the
-few files / views outside the device codecs' subsets.
+``cv2.imwrite`` (ref :277) writes at OpenCV's defaults, so only the files cross PCIe; ``.jpg`` and ``.png`` panoramas are decoded
+on the GPU too (``csrc/p2p_jpegdec.cuh``, ``csrc/p2p_pngdec.cuh``: same pixels as ``cv2.imread``, ref :244).  cv2 remains for the
+few files / views outside the device codecs' subsets (and for damaged files, which the device decoders decline).
 """
 from __future__ import annotations
 
@@ -111,9 +111,9 @@ class _JpegSource:
 
 
 def _open_image(path):
-    """``cv2.imread(path)`` of the reference (ref :244): a BGR array, or None if unreadable - except that a JPEG file
-    inside the device decoder's subset (baseline YCbCr, no EXIF rotation ...) stays as bytes and is decoded on the GPU
-    (bit-identical pixels, ``csrc/p2p_jpegdec.cuh``)."""
+    """``cv2.imread(path)`` of the reference (ref :244): a BGR array, or None if unreadable - except that a JPEG or PNG file
+    inside its device decoder's subset (baseline / progressive YCbCr without EXIF rotation; 8-bit non-interlaced PNG) stays as
+    bytes and is decoded on the GPU (same pixels, ``csrc/p2p_jpegdec.cuh`` / ``csrc/p2p_pngdec.cuh``)."""
     import cv2
 
     path = Path(path)
