@@ -27,7 +27,7 @@ PdLayout pd_layout(const p2ppdec::Parsed &P) {
     L.d_list = at; at = up(at + (size_t)L.cap_list * sizeof(uint64_t));
     L.d_cands = at; at = up(at + (size_t)L.cap_cand * sizeof(Cand));
     L.d_blocks = at; at = up(at + (size_t)L.cap_blocks * sizeof(Block));
-    L.d_bands = at; at = up(at + (size_t)P.info.H * sizeof(uint32_t));
+    L.d_bands = at; at = up(at + (size_t)(L.cap_blocks + 1) * sizeof(uint32_t));   // marks in front of each group of the tail pass
     L.d_prog = at; at = up(at + ((size_t)P.info.H + 1) * sizeof(uint32_t));   // progress per band | ticket
     L.d_ctr = at; at = up(at + sizeof(Slot::PdCtr));
     L.d_total = at;
@@ -97,6 +97,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     Cand *cands_d = reinterpret_cast<Cand *>(s.pd_tab + L.d_cands);
     Block *blocks_d = reinterpret_cast<Block *>(s.pd_tab + L.d_blocks);
     uint32_t *prog_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_prog);
+    uint32_t *gmarks_d = reinterpret_cast<uint32_t *>(s.pd_tab + L.d_bands);
     Slot::PdCtr *ctr_d = reinterpret_cast<Slot::PdCtr *>(s.pd_tab + L.d_ctr);
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -160,8 +161,8 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
                                                                          I.wsize, &ctr_d->bad);
         pd_copy_kernel<<<(nb + 7) / 8, 256, 0, st>>>(blocks_d, nb, s.pd_match, s.pd_raw, s.pd_ref);
         const uint32_t per = group_size(nb);
-        pd_tails_group_kernel<<<(nb + per - 1) / per, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
-        pd_tails_chain_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref);
+        pd_tails_group_kernel<<<(nb + per - 1) / per, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref, gmarks_d);
+        pd_tails_chain_kernel<<<1, 1024, 0, st>>>(blocks_d, nb, per, s.pd_raw, s.pd_ref, gmarks_d);
         pd_tails_finish_kernel<<<nb, 256, 0, st>>>(blocks_d, per, s.pd_raw, s.pd_ref);
         pd_resolve_kernel<<<dim3(nb, 4), 256, 0, st>>>(blocks_d, s.pd_raw, s.pd_ref);
         pd_adler_kernel<<<(unsigned)((I.raw_bytes + 4095) / 4096), 256, 0, st>>>(s.pd_raw, I.raw_bytes, ctr_d->sums);
@@ -171,12 +172,19 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaMemsetAsync(prog_d, 0, ((size_t)I.H + 1) * sizeof(uint32_t), st));
         const unsigned ugrid = (unsigned)(((I.H + 31) / 32 + 7) / 8);   // a warp per band of 32 rows
         uint32_t *ticket = prog_d + I.H;
-        switch (I.bpp) {
-            case 1: pd_unfilter_kernel<1><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
-            case 2: pd_unfilter_kernel<2><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
-            case 3: pd_unfilter_kernel<3><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
-            default: pd_unfilter_kernel<4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad); break;
+        static const int chunk = [] { const char *e = getenv("P2P_PNG_CHUNK"); return e && atoi(e) == 8 ? 8 : 4; }();   // (experiment switch)
+#define P2P_UNFILTER(BPP, CH) pd_unfilter_kernel<BPP, CH><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad)
+        switch (I.bpp * 16 + chunk) {
+            case 1 * 16 + 4: P2P_UNFILTER(1, 4); break;
+            case 2 * 16 + 4: P2P_UNFILTER(2, 4); break;
+            case 3 * 16 + 4: P2P_UNFILTER(3, 4); break;
+            case 4 * 16 + 4: P2P_UNFILTER(4, 4); break;
+            case 1 * 16 + 8: P2P_UNFILTER(1, 8); break;
+            case 2 * 16 + 8: P2P_UNFILTER(2, 8); break;
+            case 3 * 16 + 8: P2P_UNFILTER(3, 8); break;
+            default: P2P_UNFILTER(4, 8); break;
         }
+#undef P2P_UNFILTER
         pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
         ctx->launches += 9;
         CK(cudaGetLastError());

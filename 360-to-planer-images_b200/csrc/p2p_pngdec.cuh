@@ -71,7 +71,8 @@ struct Tables {                 // 3264 bytes: one per decoding warp in shared m
 // ---- bit reader: the zlib stream as little-endian 32-bit words (zero padded), LSB first -----------------------------
 struct Bits {
     const uint32_t *w;
-    uint64_t n_words, wi, buf;
+    uint64_t n_words, wi, buf;   // wi: words taken into buf so far (= index of the word waiting in nextw)
+    uint32_t nextw;              // loaded one refill ahead, so that its latency is not on the decoder's dependency chain
     int cnt;
     PD_HD uint32_t word(uint64_t i) const { return i < n_words ? w[i] : 0u; }
     PD_HD void init(const uint32_t *words, uint64_t nw, uint64_t bit) {
@@ -82,13 +83,15 @@ struct Bits {
         buf = (uint64_t)(word(wi) >> sh);
         wi++;
         cnt = 32 - sh;
+        nextw = word(wi);
         refill();
     }
     PD_HD void refill() {  // afterwards 33 .. 64 valid bits
         if (cnt <= 32) {
-            buf |= (uint64_t)word(wi) << cnt;
+            buf |= (uint64_t)nextw << cnt;
             wi++;
             cnt += 32;
+            nextw = word(wi);
         }
     }
     PD_HD uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1ull)); }
@@ -867,11 +870,15 @@ __global__ void __launch_bounds__(256) pd_quick_kernel(const uint32_t *__restric
     const uint64_t w0 = wi < n_words ? zs[wi] : 0u, w1 = wi + 1 < n_words ? zs[wi + 1] : 0u, w2 = wi + 2 < n_words ? zs[wi + 2] : 0u,
                    w3 = wi + 3 < n_words ? zs[wi + 3] : 0u;
     const uint64_t lo = w0 | (w1 << 32), hi = w2 | (w3 << 32);
-    for (int p = 0; p < 32; ++p) {
+    // positions whose type bits say "dynamic Huffman" (bit p + 1 clear, bit p + 2 set): a quarter of them; only those are
+    // looked at, so that the lanes of a warp stay busy instead of waiting for the quarter that passes
+    uint32_t todo = (uint32_t)(~(lo >> 1) & (lo >> 2));
+    while (todo) {
+        const int p = __ffs(todo) - 1;
+        todo &= todo - 1;
         const uint64_t bit = wi * 32 + p;
         if (bit < first_bit || bit + 3 > stream_bits) continue;
         const uint64_t head = p ? (lo >> p) | (hi << (64 - p)) : lo;
-        if (((head >> 1) & 3) != 2) continue;
         const int q = p + 17;
         const uint64_t lens3 = (lo >> q) | (hi << (64 - q));
         if (!quick_check(head, lens3)) continue;
@@ -1022,7 +1029,7 @@ __global__ void __launch_bounds__(256) pd_copy_kernel(Block *__restrict__ blocks
 // positions per thread: marks first, then the history look-ups, then the stores; blocks without marks in their last 32 KiB
 // are skipped)
 __global__ void __launch_bounds__(1024) pd_tails_group_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint32_t per, uint8_t *raw,
-                                                              uint16_t *ref) {
+                                                              uint16_t *ref, uint32_t *__restrict__ group_marks) {
     const uint32_t i0 = blockIdx.x * per, i1 = min(n_blocks, i0 + per);
     const uint64_t gs = blocks[i0].out_off;
     for (uint32_t i = i0; i < i1; ++i) {
@@ -1058,14 +1065,23 @@ __global__ void __launch_bounds__(1024) pd_tails_group_kernel(const Block *__res
         }
         __syncthreads();
     }
+    // marks left in the 32 KiB in front of the next group (what pd_tails_chain_kernel has to look at; usually nothing)
+    if (i1 < n_blocks) {
+        const uint64_t next = blocks[i1].out_off, lo = next > kWindow ? next - kWindow : 0, t0 = lo > gs ? lo : gs;
+        int mine = 0;
+        for (uint64_t p = t0 + threadIdx.x; p < next; p += 1024) mine |= ref[p] != 0;
+        const int any = __syncthreads_or(mine);
+        if (threadIdx.x == 0) group_marks[blockIdx.x] = (uint32_t)any;
+    }
 }
 
 // part 2: the 32 KiB in front of every group made final, group after group (one CTA; marks there are relative to the start
 // of the group they sit in, their history is the - already final - 32 KiB in front of that group)
 __global__ void __launch_bounds__(1024) pd_tails_chain_kernel(const Block *__restrict__ blocks, uint32_t n_blocks, uint32_t per, uint8_t *raw,
-                                                              uint16_t *ref) {
+                                                              uint16_t *ref, const uint32_t *__restrict__ group_marks) {
     const uint32_t ng = (n_blocks + per - 1) / per;
     for (uint32_t g = 1; g + 1 < ng; ++g) {
+        if (group_marks[g] == 0) continue;
         const uint64_t gs = blocks[g * per].out_off, next = blocks[(g + 1) * per].out_off;
         const uint64_t lo = next > kWindow ? next - kWindow : 0, t0 = lo > gs ? lo : gs;
         uint32_t r[32];
@@ -1168,8 +1184,7 @@ __global__ void __launch_bounds__(128) pd_crc_kernel(const uint8_t *__restrict__
     segs[i].crc = ~crc;
 }
 
-constexpr int kChunkPx = 8;  // pixels a lane reconstructs per step of the wavefront
-constexpr int kFetch = 16;   // chunks of the row above a band a warp fetches (and a band publishes) at a time
+constexpr int kFetchPx = 128;  // pixels of the row above a band a warp fetches (and a band publishes) at a time
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;
@@ -1190,10 +1205,13 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 // this one waits for kFetch chunks at a time (acquire load; bounded polling: a wait that does not end raises *bad, it
 // cannot hang) and brings them into shared memory with the whole warp.  The filtered bytes of the next chunk are loaded
 // (aligned words + funnel shift) while the current one is computed.  A filter type above 4 raises *bad.
-template <int BPP>
+// CH = pixels a lane reconstructs per step (4 or 8: the chunk is what one row lags behind the row above, so the whole
+// image is a chain of H chunk-times; smaller chunks shorten it, larger ones amortise the per-step shuffles and loads).
+template <int BPP, int CH>
 __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restrict__ raw, uint8_t *recon, int W, int H, size_t stride, size_t rstride,
                                                           uint32_t *ticket, uint32_t *progress, int *bad) {
-    constexpr int NW = 2 * BPP;            // words per chunk
+    constexpr int kChunkPx = CH, kFetch = kFetchPx / CH;
+    constexpr int NW = CH * BPP / 4;       // words per chunk
     constexpr int CB = kChunkPx * BPP;     // bytes per chunk
     __shared__ uint32_t upbuf[8][kFetch * NW];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
