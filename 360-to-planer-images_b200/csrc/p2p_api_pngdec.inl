@@ -117,20 +117,6 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaMemcpyAsync(segs_h, segs_d, (size_t)L.n_segs * sizeof(CrcSeg), cudaMemcpyDeviceToHost, st));
     }
     if (wait_slot(ctx, s) != cudaSuccess) return fail(ctx, P2P_ERR_CUDA, "PNG decoder: CUDA error");
-    // chunk checksums: the segments' CRCs folded per IDAT chunk (libpng refuses a file with a damaged IDAT chunk)
-    {
-        const uint32_t x_full = crc_xpow8n(kPdSeg);
-        const uint32_t idat0 = crc32_host(reinterpret_cast<const uint8_t *>("IDAT"), 4);
-        uint32_t k = 0;
-        for (const Idat &c : P.idat) {
-            uint32_t crc = idat0;
-            for (uint32_t o = 0; o < c.len; o += kPdSeg, ++k) {
-                const uint32_t n = segs_h[k].len;
-                crc = crc_mulmod(n == kPdSeg ? x_full : crc_xpow8n(n), crc) ^ segs_h[k].crc;
-            }
-            if (crc != c.crc) return P2P_ERR_UNSUPPORTED;
-        }
-    }
     // the candidates (a second, short copy now that their number is known), then the chain
     const uint32_t n_cand = std::min(ctr_h->n_cand, L.cap_cand);
     if (n_cand) {
@@ -172,17 +158,14 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaMemsetAsync(prog_d, 0, ((size_t)I.H + 1) * sizeof(uint32_t), st));
         const unsigned ugrid = (unsigned)(((I.H + 31) / 32 + 7) / 8);   // a warp per band of 32 rows
         uint32_t *ticket = prog_d + I.H;
-        static const int chunk = [] { const char *e = getenv("P2P_PNG_CHUNK"); return e && atoi(e) == 8 ? 8 : 4; }();   // (experiment switch)
-#define P2P_UNFILTER(BPP, CH) pd_unfilter_kernel<BPP, CH><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad)
-        switch (I.bpp * 16 + chunk) {
-            case 1 * 16 + 4: P2P_UNFILTER(1, 4); break;
-            case 2 * 16 + 4: P2P_UNFILTER(2, 4); break;
-            case 3 * 16 + 4: P2P_UNFILTER(3, 4); break;
-            case 4 * 16 + 4: P2P_UNFILTER(4, 4); break;
-            case 1 * 16 + 8: P2P_UNFILTER(1, 8); break;
-            case 2 * 16 + 8: P2P_UNFILTER(2, 8); break;
-            case 3 * 16 + 8: P2P_UNFILTER(3, 8); break;
-            default: P2P_UNFILTER(4, 8); break;
+        // 4 pixels per lane and step (8: 1.98 instead of 1.75 ms on files without row dependencies, 10.0 instead of 9.1 ms with
+        // adaptive filters, profiles/r2_png_decoder_chunk8.jsonl)
+#define P2P_UNFILTER(BPP) pd_unfilter_kernel<BPP, 4><<<ugrid, 256, 0, st>>>(s.pd_raw, recon, I.W, I.H, stride, rstride, ticket, prog_d, &ctr_d->bad)
+        switch (I.bpp) {
+            case 1: P2P_UNFILTER(1); break;
+            case 2: P2P_UNFILTER(2); break;
+            case 3: P2P_UNFILTER(3); break;
+            default: P2P_UNFILTER(4); break;
         }
 #undef P2P_UNFILTER
         pd_bgr_kernel<<<dim3((I.W + 255) / 256, I.H), 256, 0, st>>>(recon, I.W, I.H, rstride, I.bpp, s.d_bgr, dstride);
@@ -190,6 +173,21 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(ctr_h, ctr_d, sizeof(Slot::PdCtr), cudaMemcpyDeviceToHost, st));
         s.valid = false;  // the staging image changed under whatever panorama the slot held
+    }
+    // chunk checksums: the segments' CRCs (read back before the chain walk) folded per IDAT chunk while the device works on the
+    // passes queued above (libpng refuses a file with a damaged IDAT chunk: so does this decoder, whatever the passes produce)
+    {
+        const uint32_t x_full = crc_xpow8n(kPdSeg);
+        const uint32_t idat0 = crc32_host(reinterpret_cast<const uint8_t *>("IDAT"), 4);
+        uint32_t k = 0;
+        for (const Idat &c : P.idat) {
+            uint32_t crc = idat0;
+            for (uint32_t o = 0; o < c.len; o += kPdSeg, ++k) {
+                const uint32_t n = segs_h[k].len;
+                crc = crc_mulmod(n == kPdSeg ? x_full : crc_xpow8n(n), crc) ^ segs_h[k].crc;
+            }
+            if (crc != c.crc) return P2P_ERR_UNSUPPORTED;
+        }
     }
     *dstride_out = dstride;
     return P2P_OK;
