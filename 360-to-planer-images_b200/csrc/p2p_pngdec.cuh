@@ -1001,8 +1001,10 @@ __global__ void __launch_bounds__(256) pd_copy_kernel(Block *__restrict__ blocks
         if (lane < cnt) mine = list[m0 + lane];
         for (uint32_t q = 0; q < cnt; ++q) {
             const uint32_t o = __shfl_sync(0xffffffffu, mine.o, q), len = __shfl_sync(0xffffffffu, (uint32_t)mine.len, q);
-            uint32_t dist = __shfl_sync(0xffffffffu, (uint32_t)mine.dist, q);
-            if (dist == 0) dist = 65536u;   // (cannot happen: distances are 1 .. 32768)
+            const uint32_t dist = __shfl_sync(0xffffffffu, (uint32_t)mine.dist, q);
+            // A record is only trusted after it has been checked again: if the decoding pass gave up on this block (it has
+            // raised *bad; the file will be declined) the rest of the block's slice holds whatever an earlier file left there.
+            if (dist == 0 || (uint64_t)o + len > b.out_len || dist > b.out_off + o) continue;   // (warp-uniform)
             for (uint32_t t = lane; t < len; t += 32) {
                 const uint32_t tt = dist >= len ? t : t % dist;
                 const int64_t srel = (int64_t)o + tt - (int64_t)dist;   // relative to the block's first byte

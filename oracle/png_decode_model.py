@@ -214,3 +214,35 @@ def test_image(H: int, W: int, channels: int, seed: int, kind: str = "mixed") ->
         img[:, 3 * W // 4:] = rng.integers(0, 256, (H, W - 3 * W // 4, channels))
     img = (img & 255).astype(np.uint8)
     return img[:, :, 0] if channels == 1 else img
+
+
+def fixed_huffman_png(n_lit: int, dist_code: int, dist_extra_bits: int = 0, dist_extra: int = 0, cmf: int = 0x78,
+                      stored_prefix: bytes = b"") -> bytes:
+    """A hand-made one-row gray PNG whose zlib stream is [an optional stored block holding stored_prefix,] then ONE
+    fixed-Huffman block: n_lit literals 'A', a match of length 3 with the given distance code (+ extra bits), end of block.
+    The Adler-32 is left zero: the files are for the decoders' validity checks (distances in front of the data, beyond the
+    window of the zlib header), which must decline them before the checksum matters."""
+
+    def huff(code, n):  # Huffman codes are packed starting with their most significant bit
+        return [(code >> (n - 1 - k)) & 1 for k in range(n)]
+
+    bits = []
+    if stored_prefix:
+        bits += [0, 0, 0] + [0] * 5   # not final, stored, padding to the byte boundary
+        n = len(stored_prefix)
+        for v in (n & 255, n >> 8, (n ^ 0xFFFF) & 255, (n ^ 0xFFFF) >> 8) + tuple(stored_prefix):
+            bits += [(v >> k) & 1 for k in range(8)]
+    bits += [1, 1, 0]             # final block, fixed Huffman
+    for _ in range(n_lit):
+        bits += huff(0x30 + 65, 8)  # literal 'A'
+    bits += huff(0b0000001, 7)      # length code 257: length 3
+    bits += huff(dist_code, 5)
+    bits += [(dist_extra >> k) & 1 for k in range(dist_extra_bits)]
+    bits += huff(0, 7)              # end of block
+    deflate = bytearray()
+    for i in range(0, len(bits), 8):
+        deflate.append(sum(b << k for k, b in enumerate(bits[i:i + 8])))
+    flg = (31 - (cmf * 256) % 31) % 31
+    body = bytes([cmf, flg]) + bytes(deflate) + bytes(4)
+    W = len(stored_prefix) + n_lit + 3 - 1
+    return SIG + chunk(b"IHDR", struct.pack(">IIBBBBB", W, 1, 8, 0, 0, 0, 0)) + chunk(b"IDAT", body) + chunk(b"IEND", b"")

@@ -216,42 +216,66 @@ def test_damaged_files_decode_like_libpng_or_not_at_all(host_decode):
 
 
 def test_distance_beyond_the_window_or_the_data_is_declined(host_decode):
-    """A hand-made fixed-Huffman stream whose first match reaches in front of the first byte ("invalid distance too far
-    back"), and one whose distance exceeds the window the zlib header declares."""
+    """Hand-made fixed-Huffman streams whose match reaches in front of the first byte ("invalid distance too far back"; in
+    the first block and in a second block behind a stored one), and one whose distance exceeds the window the zlib header
+    declares.  The same stream with a 32 KiB window is valid except for its Adler-32: still declined, never decoded differently."""
+    cases = {
+        "in front of the data, first block": M.fixed_huffman_png(2, 3),                                   # 2 literals, distance 4
+        "in front of the data, second block": M.fixed_huffman_png(2, 5, 1, 0, stored_prefix=b"\0abc"),   # 6 bytes so far, distance 7
+        "beyond the declared window": M.fixed_huffman_png(300, 16, 7, 0, cmf=0x08),                        # window 256, distance 257
+        "wrong Adler-32 only": M.fixed_huffman_png(300, 16, 7, 0),
+    }
+    for name, f in cases.items():
+        assert M.in_subset(f) is not None, name
+        assert cv2_decode(f) is None or name == "wrong Adler-32 only", name
+        rc, out, _ = host_decode(f)
+        assert rc == -6 and out is None, name
 
-    def bits_to_bytes(bits):
-        out = bytearray()
-        for i in range(0, len(bits), 8):
-            out.append(sum(b << k for k, b in enumerate(bits[i:i + 8])))
-        return bytes(out)
 
-    def huff(code, n):  # Huffman codes are packed starting with their most significant bit
-        return [(code >> (n - 1 - k)) & 1 for k in range(n)]
+def test_host_model_under_address_sanitizer(tmp_path):
+    """The decoder's routines (chunk walk, bit reader, header parser, table builder, block decoder with symbolic history,
+    tail / resolution passes, filters), built with ASan + UBSan (tools/asan_png_host.cu), on seeded damaged files incl.
+    garbage runs and truncations: no out-of-bounds access, no undefined behaviour."""
+    import shutil
+    import subprocess
+    from pathlib import Path
 
-    def stream(dist_code, dist_extra_bits, dist_extra, n_lit):
-        bits = [1, 1, 0]  # final block, fixed Huffman
-        for _ in range(n_lit):
-            bits += huff(0x30 + 65, 8)  # literal 'A'
-        bits += huff(0b0000001, 7)  # length code 257: length 3
-        bits += huff(dist_code, 5)
-        bits += [(dist_extra >> k) & 1 for k in range(dist_extra_bits)]
-        bits += huff(0, 7)  # end of block
-        return bits_to_bytes(bits)
-
-    def png_of(deflate, n_raw, cmf=0x78):
-        flg = (31 - (cmf * 256) % 31) % 31
-        body = bytes([cmf, flg]) + deflate
-        # the Adler-32 cannot be known for an invalid stream; any value: the decoder must decline before it matters
-        body += bytes(4)
-        W = n_raw - 1
-        return M.SIG + M.chunk(b"IHDR", struct.pack(">IIBBBBB", W, 1, 8, 0, 0, 0, 0)) + M.chunk(b"IDAT", body) + M.chunk(b"IEND", b"")
-
-    # 2 literals, then a match of length 3 at distance 4: in front of the data
-    rc, out, _ = host_decode(png_of(stream(3, 0, 0, 2), 5))
-    assert rc == -6
-    # window of 256 bytes declared (CINFO = 0), 300 literals, distance 257 .. (code 16: 257 + 7 extra bits)
-    rc, out, _ = host_decode(png_of(stream(16, 7, 0, 300), 303, cmf=0x08))
-    assert rc == -6
-    # the same stream with a 32 KiB window is a valid image except for its Adler-32: still declined, never decoded differently
-    rc, out, _ = host_decode(png_of(stream(16, 7, 0, 300), 303))
-    assert rc == -6
+    root = Path(__file__).resolve().parents[1]
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = tmp_path / "asan_png_host"
+    build = subprocess.run(["nvcc", "-O1", "-g", "-Xcompiler", "-fsanitize=address,-fsanitize=undefined,-fno-omit-frame-pointer",
+                            "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(exe), str(root / "tools" / "asan_png_host.cu"),
+                            "-lasan", "-lubsan"], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + build.stderr[-300:])
+    rng = np.random.default_rng(19)
+    bases = [M.write_png(M.test_image(60, 90, ch, ct), ct, level=lv, idat=[700], flush_every=fl)
+             for (ct, ch), lv, fl in zip(COLOUR, (6, 1, 9, 0), (0, 900, 0, 0))]
+    bases.append(M.fixed_huffman_png(2, 5, 1, 0, stored_prefix=b"\0abc"))
+    names = []
+    for k in range(400):
+        base = bases[k % len(bases)]
+        d = bytearray(base)
+        if k >= len(bases):
+            if k % 2:   # inside the deflate data, chunk CRC recomputed: only the inflate's own checks stand in the way
+                ch = M.chunks(base)
+                z = bytearray(b"".join(b for t, b, _, _ in ch if t == b"IDAT"))
+                for _ in range(int(rng.integers(1, 4))):
+                    a, n = int(rng.integers(2, len(z))), int(rng.integers(1, 12))
+                    z[a:a + n] = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+                if rng.integers(0, 4) == 0:
+                    z = z[:int(rng.integers(2, len(z)))]
+                d = bytearray(M.SIG + M.chunk(b"IHDR", ch[0][1]) + M.chunk(b"IDAT", bytes(z)) + M.chunk(b"IEND", b""))
+            else:
+                for _ in range(int(rng.integers(1, 4))):
+                    a, n = int(rng.integers(8, len(d))), int(rng.integers(1, 12))
+                    d[a:a + n] = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+                if rng.integers(0, 4) == 0:
+                    d = d[:int(rng.integers(8, len(d)))]
+        f = tmp_path / f"{k:04d}.png"
+        f.write_bytes(bytes(d))
+        names.append(str(f))
+    run = subprocess.run([str(exe)] + names, capture_output=True, text=True, env={"ASAN_OPTIONS": "detect_leaks=0"})
+    assert run.returncode == 0 and "runtime error" not in run.stderr and "ERROR" not in run.stderr, run.stderr[-2000:]
+    assert run.stdout.startswith("decoded ")
