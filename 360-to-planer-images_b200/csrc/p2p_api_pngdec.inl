@@ -63,6 +63,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     const Info &I = P.info;
     Slot &s = ctx->slots[slot];
     const PdLayout L = pd_layout(P);
+    if (L.n_segs > (1u << 22)) return P2P_ERR_UNSUPPORTED;   // millions of tiny IDAT chunks: not worth a table of them
     const uint64_t n_words = stream_words(P), stream_bits = (uint64_t)(I.stream_len - 4) * 8;
     const size_t dstride = ((size_t)I.W * 3 + 3) & ~(size_t)3;
     {
