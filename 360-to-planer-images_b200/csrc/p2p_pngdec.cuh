@@ -1205,8 +1205,8 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 // the first row of a band needs the row above (filter Up / Average / Paeth), that is the last row of the band before: that
 // band publishes its progress every kFetch chunks (progress[band] = chunks of its last row that are final, release store),
 // this one waits for kFetch chunks at a time (acquire load; bounded polling: a wait that does not end raises *bad, it
-// cannot hang) and brings them into shared memory with the whole warp.  The filtered bytes of the next chunk are loaded
-// (aligned words + funnel shift) while the current one is computed.  A filter type above 4 raises *bad.
+// cannot hang) and brings them into shared memory with the whole warp.  The filtered bytes of a chunk are loaded (aligned
+// words + funnel shift) four steps before they are used.  A filter type above 4 raises *bad.
 // CH = pixels a lane reconstructs per step (4 or 8: the chunk is what one row lags behind the row above, so the whole
 // image is a chain of H chunk-times; smaller chunks shorten it, larger ones amortise the per-step shuffles and loads).
 template <int BPP, int CH>
@@ -1239,81 +1239,86 @@ __global__ void __launch_bounds__(256) pd_unfilter_kernel(const uint8_t *__restr
     const uintptr_t addr0 = reinterpret_cast<uintptr_t>(src + 1);
     const uint32_t *wbase = reinterpret_cast<const uint32_t *>(addr0 & ~(uintptr_t)3);
     const int sh = (int)(addr0 & 3) * 8;
-    uint32_t cur[NW], nxt[NW + 1], outw[NW], left[BPP], upleft[BPP];
+    constexpr int PF = 4;   // the filtered bytes of a chunk are loaded PF steps before they are used (a step is shorter than an L2 round trip)
+    uint32_t pre[PF][NW + 1], outw[NW], left[BPP], upleft[BPP];
 #pragma unroll
-    for (int i = 0; i < NW; ++i) cur[i] = outw[i] = 0;
-#pragma unroll
-    for (int i = 0; i <= NW; ++i) nxt[i] = 0;
+    for (int i = 0; i < NW; ++i) outw[i] = 0;
 #pragma unroll
     for (int i = 0; i < BPP; ++i) left[i] = upleft[i] = 0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {   // the chunks of this lane's first PF steps
+        const int j = u - (int)lane;
+#pragma unroll
+        for (int i = 0; i <= NW; ++i) pre[u][i] = (active && j >= 0 && j < nc) ? __ldg(wbase + (size_t)j * NW + i) : 0u;
+    }
     const int steps = nc + rows - 1;
-    for (int s = 0; s < steps; ++s) {
-        const int j = s - (int)lane;           // this lane's chunk at this step
-        const bool on = active && j >= 0 && j < nc;
-        if (dep && s < nc && (s % kFetch) == 0) {   // (warp-uniform) chunks s .. s + kFetch - 1 of the row above the band
-            const uint32_t need = (uint32_t)min(s + kFetch, nc);
-            uint32_t spins = 0;
-            while (ld_acquire_u32(progress + (k - 1)) < need) {
-                if (++spins > (1u << 22)) {
-                    *bad = 1;
-                    break;
+    for (int s0 = 0; s0 < steps; s0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int s = s0 + u;
+            if (s >= steps) break;                 // (warp-uniform)
+            const int j = s - (int)lane;           // this lane's chunk at this step
+            const bool on = active && j >= 0 && j < nc;
+            if (dep && s < nc && (s % kFetch) == 0) {   // (warp-uniform) chunks s .. s + kFetch - 1 of the row above the band
+                const uint32_t need = (uint32_t)min(s + kFetch, nc);
+                uint32_t spins = 0;
+                while (ld_acquire_u32(progress + (k - 1)) < need) {
+                    if (++spins > (1u << 22)) {
+                        *bad = 1;
+                        break;
+                    }
+                }
+                __syncwarp();   // lane 0 has read the chunks fetched before
+                for (int w = (int)lane; w < kFetch * NW; w += 32) {
+                    const int idx = s * NW + w;
+                    upbuf[warp][w] = idx < nc * NW ? __ldcg(up_row + idx) : 0u;
+                }
+                __syncwarp();
+            }
+            uint32_t cur[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(pre[u][i], pre[u][i + 1], sh);
+            {   // the filtered bytes this lane needs PF steps from now
+                const int jn = j + PF;
+                if (active && jn >= 0 && jn < nc) {
+#pragma unroll
+                    for (int i = 0; i <= NW; ++i) pre[u][i] = __ldg(wbase + (size_t)jn * NW + i);
                 }
             }
-            __syncwarp();   // lane 0 has read the chunks fetched before
-            for (int w = (int)lane; w < kFetch * NW; w += 32) {
-                const int idx = s * NW + w;
-                upbuf[warp][w] = idx < nc * NW ? __ldcg(up_row + idx) : 0u;
+            // the reconstructed chunk above: from the lane above (its result of the previous step), lane 0 from the fetched chunks
+            uint32_t up[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) up[i] = __shfl_up_sync(0xffffffffu, outw[i], 1);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < NW; ++i) up[i] = (dep && on) ? upbuf[warp][(s % kFetch) * NW + i] : 0u;
             }
-            __syncwarp();
-        }
-        if (on) {
-            if (j == 0) {
-                uint32_t w0[NW + 1];
+            if (on) {
 #pragma unroll
-                for (int i = 0; i <= NW; ++i) w0[i] = __ldg(wbase + i);
+                for (int px = 0; px < kChunkPx; ++px) {
 #pragma unroll
-                for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(w0[i], w0[i + 1], sh);
-            }
-            if (j + 1 < nc) {   // the next chunk's filtered bytes, needed one step from now
-#pragma unroll
-                for (int i = 0; i <= NW; ++i) nxt[i] = __ldg(wbase + (size_t)(j + 1) * NW + i);
-            }
-        }
-        // the reconstructed chunk above: from the lane above (its result of the previous step), lane 0 from the fetched chunks
-        uint32_t up[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) up[i] = __shfl_up_sync(0xffffffffu, outw[i], 1);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < NW; ++i) up[i] = (dep && on) ? upbuf[warp][(s % kFetch) * NW + i] : 0u;
-        }
-        if (on) {
-#pragma unroll
-            for (int px = 0; px < kChunkPx; ++px) {
-#pragma unroll
-                for (int c = 0; c < BPP; ++c) {
-                    const int byte = px * BPP + c;
-                    const uint32_t f = (cur[byte >> 2] >> (8 * (byte & 3))) & 255u;
-                    const uint32_t b = (up[byte >> 2] >> (8 * (byte & 3))) & 255u;
-                    const uint32_t v = unfilter_byte_masked(f, left[c], b, upleft[c], m1, m2, m3, m4);
-                    upleft[c] = b;
-                    left[c] = v;
-                    if ((byte & 3) == 0) outw[byte >> 2] = v;
-                    else outw[byte >> 2] |= v << (8 * (byte & 3));
+                    for (int c = 0; c < BPP; ++c) {
+                        const int byte = px * BPP + c;
+                        const uint32_t f = (cur[byte >> 2] >> (8 * (byte & 3))) & 255u;
+                        const uint32_t b = (up[byte >> 2] >> (8 * (byte & 3))) & 255u;
+                        const uint32_t v = unfilter_byte_masked(f, left[c], b, upleft[c], m1, m2, m3, m4);
+                        upleft[c] = b;
+                        left[c] = v;
+                        if ((byte & 3) == 0) outw[byte >> 2] = v;
+                        else outw[byte >> 2] |= v << (8 * (byte & 3));
+                    }
                 }
-            }
-            const int nbytes = min(CB, row_bytes - j * CB);
-            uint32_t *o = reinterpret_cast<uint32_t *>(dst + (size_t)j * CB);
-            if (nbytes == CB) {
+                const int nbytes = min(CB, row_bytes - j * CB);
+                uint32_t *o = reinterpret_cast<uint32_t *>(dst + (size_t)j * CB);
+                if (nbytes == CB) {
 #pragma unroll
-                for (int i = 0; i < NW; ++i) o[i] = outw[i];
-            } else {
-                for (int i = 0; i < nbytes; ++i) dst[(size_t)j * CB + i] = (uint8_t)(outw[i >> 2] >> (8 * (i & 3)));
+                    for (int i = 0; i < NW; ++i) o[i] = outw[i];
+                } else {
+                    for (int i = 0; i < nbytes; ++i) dst[(size_t)j * CB + i] = (uint8_t)(outw[i >> 2] >> (8 * (i & 3)));
+                }
+                if (next_dep && (int)lane == rows - 1 && (((j + 1) % kFetch) == 0 || j == nc - 1))   // the band's last row, for the band below
+                    st_release_u32(progress + k, (uint32_t)(j + 1));
             }
-            if (next_dep && (int)lane == rows - 1 && (((j + 1) % kFetch) == 0 || j == nc - 1))   // the band's last row, for the band below
-                st_release_u32(progress + k, (uint32_t)(j + 1));
-#pragma unroll
-            for (int i = 0; i < NW; ++i) cur[i] = __funnelshift_r(nxt[i], nxt[i + 1], sh);
         }
     }
 }
