@@ -234,3 +234,36 @@ def test_host_assumptions_report(pkg):
     assert rep["numpy_nep50"] is True            # NumPy >= 2 in this image
     assert set(rep["versions"]) == {"numpy", "cv2"} and set(rep["versions_match_pinned"]) == {"numpy", "cv2"}
     assert pkg.warn_if_host_differs() == rep
+
+
+def test_input_files_are_routed_by_content(pkg, tmp_path):
+    """``_open_image`` (the front end's ``cv2.imread``, ref :244) without a GPU: a JPEG / PNG file inside its device decoder's
+    subset stays as file bytes with the probed size, whatever its suffix says (cv2.imread looks at the signature too); files
+    outside the subsets come back as the array cv2.imread returns; junk is None."""
+    import cv2
+    import numpy as np
+
+    from oracle import png_decode_model as M
+    from p2p_b200 import engine
+    from p2p_b200 import panorama_to_plane_pitch as front
+
+    img = M.test_image(40, 64, 3, 1)
+    files = {
+        "a.png": cv2.imencode(".png", img)[1].tobytes(),
+        "b.jpg": cv2.imencode(".jpg", img)[1].tobytes(),
+        "c_is_a_png.jpg": M.write_png(img[:, :, ::-1], 2, level=9),
+        "d_16bit.png": cv2.imencode(".png", img.astype(np.uint16) * 257)[1].tobytes(),
+        "e_rgba.png": M.write_png(np.dstack([img[:, :, ::-1], img[:, :, :1]]), 6),
+        "f_junk.png": b"\x89PNG\r\n\x1a\n" + bytes(40),
+    }
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+    for name in ("a.png", "b.jpg", "c_is_a_png.jpg", "e_rgba.png"):
+        src = front._open_image(tmp_path / name)
+        assert isinstance(src, front._JpegSource) and (src.Wp, src.Hp) == (64, 40) and src.data == files[name], name
+        assert engine.probe_encoded(files[name]) == (64, 40)
+    assert engine.png_probe(files["a.png"]) == (64, 40) and engine.png_probe(files["b.jpg"]) is None
+    assert engine.jpeg_probe(files["b.jpg"]) == (64, 40) and engine.jpeg_probe(files["a.png"]) is None
+    got = front._open_image(tmp_path / "d_16bit.png")            # outside the PNG decoder's subset: cv2's array
+    assert isinstance(got, np.ndarray) and np.array_equal(got, cv2.imread(str(tmp_path / "d_16bit.png")))
+    assert front._open_image(tmp_path / "f_junk.png") is None and engine.probe_encoded(files["f_junk.png"]) is None
