@@ -129,8 +129,7 @@ int png_to_staging(p2p_ctx *ctx, int slot, const uint8_t *file, size_t len, p2pp
     std::vector<Cand> cands(cands_h, cands_h + n_cand);
     std::vector<Block> blocks;
     uint64_t end_bit = 0;
-    if (walk_chain(s.pd_zs_h, P, cands, blocks, kPdHostBudget, &end_bit)) return P2P_ERR_UNSUPPORTED;
-    if (blocks.size() > L.cap_blocks) return P2P_ERR_UNSUPPORTED;
+    if (walk_chain(s.pd_zs_h, P, cands, blocks, kPdHostBudget, &end_bit, L.cap_blocks)) return P2P_ERR_UNSUPPORTED;
     P.info.adler = be32(reinterpret_cast<const uint8_t *>(s.pd_zs_h) + I.stream_len - 4);
     memcpy(blocks_h, blocks.data(), blocks.size() * sizeof(Block));
     const uint32_t nb = (uint32_t)blocks.size();

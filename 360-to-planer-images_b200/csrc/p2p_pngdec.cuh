@@ -684,9 +684,9 @@ struct Match {            // a back-reference of a block: `len` bytes at offset 
 
 // Chain walk (host): from the first block behind the zlib header, through measured candidates where there are any and
 // measuring the other blocks (stored, fixed, or dynamic ones the search was not given) with the block decoder itself.
-// host_budget bounds the bits the host decodes that way.  0 = ok (blocks filled, *end_bit = end of the deflate data).
+// host_budget bounds the bits the host decodes that way, max_blocks the length of the chain.  0 = ok (blocks filled, *end_bit = end of the deflate data).
 inline int walk_chain(const uint32_t *zs, const Parsed &P, std::vector<Cand> &cands, std::vector<Block> &blocks,
-                      uint64_t host_budget, uint64_t *end_bit) {
+                      uint64_t host_budget, uint64_t *end_bit, size_t max_blocks = (size_t)1 << 24) {
     const Info &I = P.info;
     const uint64_t n_words = stream_words(P), stream_bits = (uint64_t)(I.stream_len - 4) * 8;  // the Adler-32 is not deflate data
     std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.bit < b.bit; });
@@ -718,6 +718,7 @@ inline int walk_chain(const uint32_t *zs, const Parsed &P, std::vector<Cand> &ca
             fin = R.final_block;
         }
         if (end > stream_bits || out + out_len > I.raw_bytes) return 1;
+        if (blocks.size() >= max_blocks) return 1;   // (a stream of millions of empty blocks)
         blocks.push_back(Block{bit, out, out_len, 0, n_match_total, n_matches, 0});
         n_match_total += n_matches;
         out += out_len;
