@@ -26,9 +26,9 @@
 //      at a final byte and pd_resolve_kernel finishes the image in one parallel pass.
 //   5. Adler-32 of the inflated data and CRC-32 of every chunk are checked (pd_adler_kernel, pd_crc_kernel + host fold):
 //      a file libpng would refuse is never decoded differently - it is declined and read by cv2.imread as before.
-//   6. pd_unfilter_kernel undoes the scanline filters: a warp per band of 32 rows, lane t one 8-pixel chunk behind lane
+//   6. pd_unfilter_kernel undoes the scanline filters: a warp per band of 32 rows, lane t one 4-pixel chunk behind lane
 //      t - 1 (a skewed wavefront: the reconstructed pixels above arrive through shuffles); a band whose first row needs the
-//      row above waits for the band before it (progress flags, 16 chunks at a time); rows filtered None / Sub need nothing.
+//      row above waits for the band before it (progress flags, 128 pixels at a time); rows filtered None / Sub need nothing.
 //   7. pd_bgr_kernel writes the BGR staging image (RGB / RGBA / gray / gray + alpha, 8 bit: what cv2.imread(path) with its
 //      default flag IMREAD_COLOR returns for them), which the usual pack kernel turns into the packed panorama.
 //
