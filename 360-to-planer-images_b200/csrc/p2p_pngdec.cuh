@@ -1200,7 +1200,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
 
 // The filters undone: raw (filter byte + filtered bytes per row, stride) -> recon (reconstructed bytes, rows of rstride bytes,
 // rstride a multiple of 4).  A warp per BAND of 32 rows (taken in image order through a ticket, so that a band only ever waits
-// for a warp that is already running); lane t owns row 32 k + t and works on chunk s - t (8 pixels) at step s: the
+// for a warp that is already running); lane t owns row 32 k + t and works on chunk s - t (CH pixels) at step s: the
 // reconstructed chunk above arrives from lane t - 1 through shuffles, one step after that lane finished it (rows filtered
 // None / Sub ignore it - a file of such rows, like everything cv2.imwrite produces, is 32 independent rows per warp).  If
 // the first row of a band needs the row above (filter Up / Average / Paeth), that is the last row of the band before: that
