@@ -101,6 +101,11 @@ def get_pitch_mapping(output_width, output_height, pitch_angle, pano_width, pano
     return pitch_mapping_cache[key]
 
 
+# what makes the front end read a file with cv2.imread after all: the device decoder declined it (-6: outside its subset, or
+# damaged), or it could not get the scratch memory / the size is beyond its limits (-3, -5: huge files, many images in flight)
+_DECLINED = (-6, -3, -5)
+
+
 class _JpegSource:
     """A JPEG or PNG panorama one of the device decoders handles, still as file bytes (the pixels will only exist on the GPU)."""
 
@@ -141,7 +146,7 @@ def _decode_source(proj, src, slot=None, device_declined=False):
         try:
             return proj.decode_encoded(src.data, slot=slot)
         except _engine.P2PError as e:
-            if e.code != -6:
+            if e.code not in _DECLINED:
                 raise
     # the reference's own call: cv2.imread, not imdecode (for a truncated file libjpeg's file reader pads the scan and
     # returns an image where its memory reader gives up)
@@ -175,7 +180,7 @@ def _project(proj, pano_image, yaw_angles, pitch_angles, output_width, output_he
                 proj.upload_encoded(s, src.data)
                 return proj.project_any(s, tables, consts, output_width, output_height)
         except _engine.P2PError as e:
-            if e.code != -6:
+            if e.code not in _DECLINED:
                 raise
             src = _decode_source(proj, src, device_declined=True)
     return proj.project_image(_decode_source(proj, src), yaw_angles, pitch_angles, output_width, output_height, fov_deg,
@@ -193,7 +198,7 @@ def _split_upload(projs, src, stack):
             p0.upload_encoded(s0, src.data)
             pano = None
         except _engine.P2PError as e:
-            if e.code != -6:
+            if e.code not in _DECLINED:
                 raise
             pano = _decode_source(p0, src, slot=s0, device_declined=True)
     if pano is not None:
@@ -336,7 +341,7 @@ def _project_jpeg(proj, pano_image, yaw_angles, pitch_angles, output_width, outp
                     proj.upload_encoded(s, src.data)
                     pano = None                      # the panorama is resident in the slot
                 except _engine.P2PError as e:
-                    if e.code != -6:
+                    if e.code not in _DECLINED:
                         raise
                     pano = _decode_source(proj, src, slot=s, device_declined=True)
             if pano is None:
@@ -374,7 +379,7 @@ def _project_png(proj, pano_image, yaw_angles, pitch_angles, output_width, outpu
                     proj.upload_encoded(s, src.data)
                     pano = None                      # the panorama is resident in the slot
                 except _engine.P2PError as e:
-                    if e.code != -6:
+                    if e.code not in _DECLINED:
                         raise
                     pano = _decode_source(proj, src, slot=s, device_declined=True)
             flat, _ = proj.process_image_png(s, pano, shifts, consts, output_width, output_height, want_pixels=False,
